@@ -1,0 +1,117 @@
+"""ctypes wrapper of the CPU oracle (oracle/lwfb90_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "liblwfb90_oracle.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "lwfb90_oracle.c")
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "lwfb90.h")
+    if (force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src)
+            or os.path.getmtime(_SO) < os.path.getmtime(hdr)):
+        subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.lwfb_oracle_run.restype = C.c_int
+        _lib.lwfb_oracle_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
+                                         C.c_int64, _ip, _dp, _dp, _dp, C.c_double, C.c_double,
+                                         C.c_double, C.c_double, C.c_int64, C.c_int, _dp, _ip, _lp]
+        _lib.lwfb_oracle_run_member.restype = C.c_int
+        _lib.lwfb_oracle_run_member.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp,
+                                                _dp, C.c_double, C.c_double, C.c_double, C.c_double,
+                                                C.c_int64, _dp, _dp, _lp, _dp]
+        _lib.lwfb_oracle_eval_rhs.restype = None
+        _lib.lwfb_oracle_eval_rhs.argtypes = [C.c_int, _dp, _dp, C.c_double, _dp, C.c_double, _dp, _dp, _dp]
+        _lib.lwfb_oracle_kkmean.restype = C.c_double
+        _lib.lwfb_oracle_kkmean.argtypes = [C.c_double] * 4
+        _lib.lwfb_oracle_pm.restype = C.c_double
+        _lib.lwfb_oracle_pm.argtypes = [C.c_double] * 5
+        _lib.lwfb_oracle_esat.restype = None
+        _lib.lwfb_oracle_esat.argtypes = [C.c_double, _dp, _dp]
+        _lib.lwfb_oracle_fastpow.restype = C.c_double
+        _lib.lwfb_oracle_fastpow.argtypes = [C.c_double, C.c_double]
+    return _lib
+
+
+def _p(a, t=_dp):
+    return a.ctypes.data_as(t)
+
+
+def run(N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, *, reltol=1e-5, abstol=1e-6,
+        dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000, n_threads=1, record=True):
+    """Integrate a batch of members on the CPU.  Shapes as in include/lwfb90.h.
+    Returns (daily [M, n_days+1, L] or None, status [M], counters [M,3])."""
+    forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+    if forcing.ndim == 2:
+        forcing = forcing[None]
+    n_sites, n_rows, nf = forcing.shape
+    scal = np.ascontiguousarray(scal, dtype=np.float64)
+    lay = np.ascontiguousarray(lay, dtype=np.float64)
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    if scal.ndim == 1:
+        scal, lay, u0 = scal[None], lay[None], u0[None]
+    M = scal.shape[0]
+    L = 9 * N + 51 if iso else 5 * N + 39
+    assert u0.shape == (M, L), (u0.shape, (M, L))
+    assert lay.shape[0] == M and lay.shape[2] == N
+    som = np.ascontiguousarray(site_of_member, dtype=np.int32)
+    assert som.shape == (M,)
+    out = np.empty((M, n_days + 1, L)) if record else None
+    status = np.zeros(M, dtype=np.int32)
+    counters = np.zeros((M, 3), dtype=np.int64)
+    lib().lwfb_oracle_run(N, int(iso), int(t0_day), int(n_days), n_sites, n_rows, _p(forcing), M, _p(som, _ip),
+                          _p(scal), _p(lay), _p(u0), reltol, abstol, dt_init, dtmax, maxiters, int(n_threads),
+                          _p(out) if record else None, _p(status, _ip), _p(counters, _lp))
+    return out, status, counters
+
+
+def run_member(N, iso, t0_day, n_days, forcing, scal, lay, u0, *, reltol=1e-5, abstol=1e-6, dt_init=1e-3,
+               dtmax=60 / 60 / 24, maxiters=1_000_000, ntfli_init=None):
+    """One member; optionally with warm du_NTFLI cache (re-run on the same problem).
+    Returns (daily [n_days+1, L], status, counters[3], ntfli_final[N])."""
+    forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+    n_rows = forcing.shape[0]
+    L = 9 * N + 51 if iso else 5 * N + 39
+    out = np.empty((n_days + 1, L))
+    counters = np.zeros(3, dtype=np.int64)
+    nt_out = np.empty(N)
+    nt_in = None if ntfli_init is None else np.ascontiguousarray(ntfli_init, dtype=np.float64)
+    st = lib().lwfb_oracle_run_member(N, int(iso), int(t0_day), int(n_days), n_rows, _p(forcing),
+                                      _p(np.ascontiguousarray(scal, dtype=np.float64)),
+                                      _p(np.ascontiguousarray(lay, dtype=np.float64)),
+                                      _p(np.ascontiguousarray(u0, dtype=np.float64)),
+                                      reltol, abstol, dt_init, dtmax, maxiters,
+                                      None if nt_in is None else _p(nt_in), _p(out), _p(counters, _lp), _p(nt_out))
+    return out, st, counters, nt_out
+
+
+def eval_rhs(N, scal, lay, t, swati, gwat, frozen, ntfli_prev):
+    sw = np.ascontiguousarray(swati, dtype=np.float64).copy()
+    du = np.empty(N + 9)
+    lib().lwfb_oracle_eval_rhs(N, _p(np.ascontiguousarray(scal, dtype=np.float64)),
+                               _p(np.ascontiguousarray(lay, dtype=np.float64)), float(t), _p(sw), float(gwat),
+                               _p(np.ascontiguousarray(frozen, dtype=np.float64)),
+                               _p(np.ascontiguousarray(ntfli_prev, dtype=np.float64)), _p(du))
+    return du, sw
