@@ -200,6 +200,9 @@ int lwfb_sync(lwfb_handle* h);
  * out [member_count][n_days+1][LWFB_STATE_LEN]; record k = state saved at t = t0_day + k. */
 int lwfb_get_daily(lwfb_handle* h, int64_t member_first, int64_t member_count, double* out);
 
+/* final state only (always available, also with record_daily = 0): out [member_count][LWFB_STATE_LEN] */
+int lwfb_get_final(lwfb_handle* h, int64_t member_first, int64_t member_count, double* out);
+
 /* replaces ODESolution.retcode / .destats (src/LWFBrook90.jl:645-650):
  * status [n_members] (LWFB_ST_*), counters [n_members][LWFB_NCOUNTERS] */
 int lwfb_get_status(lwfb_handle* h, int32_t* status, int64_t* counters);

@@ -1,0 +1,192 @@
+"""ctypes binding of the C ABI (include/lwfb90.h) of liblwfb90.so.
+
+This is the Python equivalent of the Julia `ccall` shim shown in INTEGRATION.md.  There is no CPU
+fallback: if the CUDA library is missing or no GPU is present the calls fail loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import layout as lo
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblwfb90.so")
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+
+class LwfbOpts(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("simulate_isotopes", C.c_int32), ("t0_day", C.c_int32),
+                ("n_days", C.c_int32), ("reltol", C.c_double), ("abstol", C.c_double),
+                ("dt_init", C.c_double), ("dtmax", C.c_double), ("maxiters", C.c_int64),
+                ("device", C.c_int32), ("record_daily", C.c_int32)]
+
+
+class LwfbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+# every symbol include/lwfb90.h declares
+SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error", "lwfb_set_sites",
+           "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
+           "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats"]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LwfbError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.lwfb_default_opts.argtypes = [C.POINTER(LwfbOpts)]; L.lwfb_default_opts.restype = None
+        L.lwfb_create.argtypes = [C.POINTER(vp), C.POINTER(LwfbOpts)]; L.lwfb_create.restype = C.c_int
+        L.lwfb_destroy.argtypes = [vp]; L.lwfb_destroy.restype = None
+        L.lwfb_last_error.argtypes = [vp]; L.lwfb_last_error.restype = C.c_char_p
+        L.lwfb_set_sites.argtypes = [vp, C.c_int32, C.c_int32, _dp]; L.lwfb_set_sites.restype = C.c_int
+        L.lwfb_set_members.argtypes = [vp, C.c_int64, _ip, _dp, _dp, _dp]; L.lwfb_set_members.restype = C.c_int
+        L.lwfb_run.argtypes = [vp, vp]; L.lwfb_run.restype = C.c_int
+        L.lwfb_run_async.argtypes = [vp, vp]; L.lwfb_run_async.restype = C.c_int
+        L.lwfb_sync.argtypes = [vp]; L.lwfb_sync.restype = C.c_int
+        L.lwfb_get_daily.argtypes = [vp, C.c_int64, C.c_int64, _dp]; L.lwfb_get_daily.restype = C.c_int
+        L.lwfb_get_final.argtypes = [vp, C.c_int64, C.c_int64, _dp]; L.lwfb_get_final.restype = C.c_int
+        L.lwfb_get_status.argtypes = [vp, _ip, _lp]; L.lwfb_get_status.restype = C.c_int
+        L.lwfb_scores.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp, _dp]; L.lwfb_scores.restype = C.c_int
+        L.lwfb_scores_device.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp, C.POINTER(vp)]
+        L.lwfb_scores_device.restype = C.c_int
+        L.lwfb_eval_rhs.argtypes = [vp, C.c_double, _dp, _dp, _dp, _dp, _dp]; L.lwfb_eval_rhs.restype = C.c_int
+        L.lwfb_last_run_stats.argtypes = [vp, _ip, C.POINTER(C.c_float)]; L.lwfb_last_run_stats.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a, t=_dp):
+    return a.ctypes.data_as(t)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Handle:
+    """Owns one lwfb_handle (device memory of one ensemble on one GPU)."""
+
+    def __init__(self, N: int, iso: bool, t0_day: int, n_days: int, *, device: int = 0, record_daily: bool = True,
+                 reltol=1e-5, abstol=1e-6, dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000):
+        self._L = lib()
+        o = LwfbOpts()
+        self._L.lwfb_default_opts(C.byref(o))
+        o.n_layers, o.simulate_isotopes, o.t0_day, o.n_days = int(N), int(bool(iso)), int(t0_day), int(n_days)
+        o.reltol, o.abstol, o.dt_init, o.dtmax, o.maxiters = reltol, abstol, dt_init, dtmax, int(maxiters)
+        o.device, o.record_daily = int(device), int(bool(record_daily))
+        self.N, self.iso, self.t0_day, self.n_days = int(N), bool(iso), int(t0_day), int(n_days)
+        self.L = lo.state_len(self.N, self.iso)
+        self.M = 0
+        self._h = C.c_void_p()
+        rc = self._L.lwfb_create(C.byref(self._h), C.byref(o))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise LwfbError(f"lwfb_create failed with code {rc} (is a CUDA device available?)")
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._L.lwfb_last_error(self._h)
+            raise LwfbError(f"liblwfb90 error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.lwfb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_sites(self, forcing):
+        f = _f64(forcing)
+        if f.ndim == 2:
+            f = f[None]
+        assert f.shape[2] == lo.NF
+        self._ck(self._L.lwfb_set_sites(self._h, f.shape[0], f.shape[1], _p(f)))
+
+    def set_members(self, site_of_member, scal, lay, u0):
+        scal, lay, u0 = _f64(scal), _f64(lay), _f64(u0)
+        if scal.ndim == 1:
+            scal, lay, u0 = scal[None], lay[None], u0[None]
+        M = scal.shape[0]
+        assert scal.shape == (M, lo.NPS) and lay.shape == (M, lo.NPL, self.N) and u0.shape == (M, self.L)
+        som = np.ascontiguousarray(site_of_member, dtype=np.int32).reshape(M)
+        self._ck(self._L.lwfb_set_members(self._h, M, _p(som, _ip), _p(scal), _p(lay), _p(u0)))
+        self.M = M
+
+    def run(self, stream=None):
+        self._ck(self._L.lwfb_run(self._h, C.c_void_p(stream) if stream else None))
+
+    def run_async(self, stream=None):
+        self._ck(self._L.lwfb_run_async(self._h, C.c_void_p(stream) if stream else None))
+
+    def sync(self):
+        self._ck(self._L.lwfb_sync(self._h))
+
+    def get_daily(self, first=0, count=None, out=None):
+        count = self.M - first if count is None else count
+        if out is None:
+            out = np.empty((count, self.n_days + 1, self.L))
+        self._ck(self._L.lwfb_get_daily(self._h, first, count, _p(out)))
+        return out
+
+    def get_final(self, first=0, count=None):
+        count = self.M - first if count is None else count
+        out = np.empty((count, self.L))
+        self._ck(self._L.lwfb_get_final(self._h, first, count, _p(out)))
+        return out
+
+    def get_status(self):
+        st = np.empty(self.M, dtype=np.int32)
+        cnt = np.empty((self.M, lo.NCOUNTERS), dtype=np.int64)
+        self._ck(self._L.lwfb_get_status(self._h, _p(st, _ip), _p(cnt, _lp)))
+        return st, cnt
+
+    def scores(self, obs_day, obs_layer, obs_theta=None, obs_d18o=None):
+        od = np.ascontiguousarray(obs_day, dtype=np.int32)
+        ol = np.ascontiguousarray(obs_layer, dtype=np.int32)
+        th = None if obs_theta is None else _f64(obs_theta).reshape(len(od), len(ol))
+        d18 = None if obs_d18o is None else _f64(obs_d18o).reshape(len(od), len(ol))
+        out = np.empty((self.M, lo.NSCORES))
+        self._ck(self._L.lwfb_scores(self._h, len(od), _p(od, _ip), len(ol), _p(ol, _ip),
+                                     None if th is None else _p(th), None if d18 is None else _p(d18), _p(out)))
+        return out
+
+    def scores_device(self, obs_day, obs_layer, obs_theta=None, obs_d18o=None) -> int:
+        """Like scores() but leaves the [M][NSCORES] block on the GPU and returns its device address."""
+        od = np.ascontiguousarray(obs_day, dtype=np.int32)
+        ol = np.ascontiguousarray(obs_layer, dtype=np.int32)
+        th = None if obs_theta is None else _f64(obs_theta).reshape(len(od), len(ol))
+        d18 = None if obs_d18o is None else _f64(obs_d18o).reshape(len(od), len(ol))
+        ptr = C.c_void_p()
+        self._ck(self._L.lwfb_scores_device(self._h, len(od), _p(od, _ip), len(ol), _p(ol, _ip),
+                                            None if th is None else _p(th), None if d18 is None else _p(d18),
+                                            C.byref(ptr)))
+        return int(ptr.value)
+
+    def eval_rhs(self, t, swati, gwat, frozen, ntfli_prev):
+        sw, gw, fr, nt = _f64(swati), _f64(gwat), _f64(frozen), _f64(ntfli_prev)
+        du = np.empty((self.M, self.N + 9))
+        self._ck(self._L.lwfb_eval_rhs(self._h, float(t), _p(sw), _p(gw), _p(fr), _p(nt), _p(du)))
+        return du
+
+    def last_run_stats(self):
+        n = C.c_int32()
+        ms = C.c_float()
+        self._ck(self._L.lwfb_last_run_stats(self._h, C.byref(n), C.byref(ms)))
+        return int(n.value), float(ms.value)

@@ -1,0 +1,667 @@
+// lwfb90.cu — kernels and C ABI of liblwfb90 (see include/lwfb90.h).
+//
+// Kernels:
+//   integrate_kernel<NT>   persistent per-member integration: Tsit5 stages + RHS + error norm + PI
+//                          controller + per-step isotope transport + daily callbacks, one member per
+//                          thread, whole record in one launch.
+//   aos_to_soa / soa_to_aos layout transposes between the ABI's member-major blocks and the device's
+//                          [field][member] layout.
+//   score_kernel           per-member RMSE / KGE against observations, reading the daily record.
+//   rhs_kernel             one RHS evaluation per member (unit parity tests).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "lwfb90_device.cuh"
+
+using namespace lwfb;
+
+#ifndef LWFB_BLOCK
+#define LWFB_BLOCK 128
+#endif
+
+// Tsit5 tableau (Tsitouras 2011) as used by OrdinaryDiffEq's Tsit5
+__device__ constexpr double c1 = 0.161, c2 = 0.327, c3 = 0.9, c4 = 0.9800255409045097;
+__device__ constexpr double a21 = 0.161, a31 = -0.008480655492356989, a32 = 0.335480655492357,
+                            a41 = 2.8971530571054935, a42 = -6.359448489975075, a43 = 4.3622954328695815,
+                            a51 = 5.325864828439257, a52 = -11.748883564062828, a53 = 7.4955393428898365,
+                            a54 = -0.09249506636175525, a61 = 5.86145544294642, a62 = -12.92096931784711,
+                            a63 = 8.159367898576159, a64 = -0.071584973281401, a65 = -0.028269050394068383,
+                            a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996,
+                            a74 = 1.379008574103742, a75 = -3.290069515436081, a76 = 2.324710524099774;
+__device__ constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469,
+                            bt3 = 0.007880878010261995, bt4 = -0.1447110071732629, bt5 = 0.5823571654525552,
+                            bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
+
+// position of the 8 integrated accumulators inside `accum`
+__device__ constexpr int kAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LWFB_A_SLFL,
+                                       LWFB_A_BYFL, LWFB_A_DSFL, LWFB_A_GWFL, LWFB_A_VRFLN};
+
+template <int NT>
+__global__ void __launch_bounds__(LWFB_BLOCK) integrate_kernel(DevData d) {
+  constexpr int NMAX = Member<NT>::NMAX;
+  constexpr int NEMAX = NMAX + 9;
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= d.M) return;
+  const int64_t M = d.M;
+  Member<NT> mb;
+  mb.load(d, m);
+  const int N = mb.N, NE = N + 9, L = d.L;
+  const bool iso = d.iso != 0;
+  const SIdx ix(N, d.iso);
+  const double* __restrict__ forc = d.forc + (int64_t)__ldg(d.site + m) * d.n_rows * LWFB_F;
+  auto U0 = [&](int j) { return __ldg(d.u0 + (int64_t)j * M + m); };
+
+  // ---- evolving state y = (SWATI[N], GWAT, 8 integrated accumulators) and the rest of u
+  double y[NEMAX], yprev[NEMAX], k[7][NEMAX];
+  double TRANIst[NMAX], RWUst, XYmm;
+  DayState ds;
+  IsoState<NT> is;
+  double dISN[3][2];  // delta of INTS, INTR, SNOW
+  for (int i = 0; i < N; i++) { y[i] = U0(ix.SWATI + i); TRANIst[i] = U0(ix.TRANI + i); }
+  y[N] = U0(ix.GWAT);
+  for (int a = 0; a < LWFB_NACCUM; a++) ds.acc[a] = U0(ix.ACC + a);
+  for (int q = 0; q < 8; q++) y[N + 1 + q] = ds.acc[kAccPos[q]];
+  ds.INTS = U0(ix.INTS); ds.INTR = U0(ix.INTR); ds.SNOW = U0(ix.SNOW); ds.CC = U0(ix.CC); ds.SNOWLQ = U0(ix.SNOWLQ);
+  RWUst = U0(ix.RWU); XYmm = U0(ix.XYLEM);
+  if (iso) {
+    for (int s = 0; s < 2; s++) {
+      for (int i = 0; i < N; i++) is.dS[s][i] = U0(ix.SWATI + (s + 1) * N + i);
+      is.dG[s] = U0(ix.GWAT + 1 + s); is.dRWU[s] = U0(ix.RWU + 1 + s); is.dXY[s] = U0(ix.XYLEM + 1 + s);
+      dISN[0][s] = U0(ix.INTS + 1 + s); dISN[1][s] = U0(ix.INTR + 1 + s); dISN[2][s] = U0(ix.SNOW + 1 + s);
+    }
+  }
+
+  // writes the full reference-order state record (src/func_DiffEq_definition_u0.jl:42-73)
+  auto write_record = [&](double* __restrict__ dst) {
+    auto W = [&](int j, double v) { dst[(int64_t)j * M + m] = v; };
+    for (int i = 0; i < N; i++) W(ix.SWATI + i, y[i]);
+    W(ix.GWAT, y[N]); W(ix.INTS, ds.INTS); W(ix.INTR, ds.INTR); W(ix.SNOW, ds.SNOW);
+    W(ix.RWU, RWUst); W(ix.XYLEM, XYmm); W(ix.CC, ds.CC); W(ix.SNOWLQ, ds.SNOWLQ);
+    for (int i = 0; i < N; i++) W(ix.TRANI + i, TRANIst[i]);
+    if (iso) {
+      for (int s = 0; s < 2; s++) {
+        for (int i = 0; i < N; i++) {
+          W(ix.SWATI + (s + 1) * N + i, is.dS[s][i]);
+          W(ix.TRANI + (s + 1) * N + i, U0(ix.TRANI + (s + 1) * N + i));  // never updated by the reference
+        }
+        W(ix.GWAT + 1 + s, is.dG[s]); W(ix.RWU + 1 + s, is.dRWU[s]); W(ix.XYLEM + 1 + s, is.dXY[s]);
+        W(ix.INTS + 1 + s, dISN[0][s]); W(ix.INTR + 1 + s, dISN[1][s]); W(ix.SNOW + 1 + s, dISN[2][s]);
+      }
+    }
+    for (int j = 0; j < 3 * N; j++) W(ix.AUX + j, U0(ix.AUX + j));  // aux is never written after init
+    for (int a = 0; a < LWFB_NACCUM; a++) W(ix.ACC + a, ds.acc[a]);
+    for (int q = 0; q < 8; q++) W(ix.ACC + kAccPos[q], y[N + 1 + q]);
+  };
+  // delta of precipitation at time t: the value of forcing row r holds for t in (r-0.5, r+0.5]
+  auto prec_delta = [&](double t, double* dp) {
+    int r = (int)ceil(t - 0.5);
+    r = r < 0 ? 0 : (r > d.n_rows - 1 ? d.n_rows - 1 : r);
+    dp[0] = __ldg(forc + (int64_t)r * LWFB_F + LWFB_F_D18O);
+    dp[1] = __ldg(forc + (int64_t)r * LWFB_F + LWFB_F_D2H);
+  };
+  auto cb_deltas = [&](double t) {  // src/func_DiffEq_definition_cb.jl:304-530 (live :380-387, :520-525)
+    if (!iso) return;
+    double dp[2];
+    prec_delta(t, dp);
+    for (int c = 0; c < 3; c++) { dISN[c][0] = dp[0]; dISN[c][1] = dp[1]; }
+  };
+
+  const double qmin = 0.2, qmax = 10.0, gamma = 0.9, beta1 = 0.14, beta2 = 0.08, qoldinit = 1e-4;
+  const double t0 = (double)d.t0_day, tend = (double)(d.t0_day + d.n_days);
+  double t = t0, tprev = t0, dt = d.dt_init, dtpropose = d.dt_init, qold = qoldinit, q11 = 1.0;
+  const double dtmin_opt = fmax(eps_of(tend), eps_of(t0));
+  long long naccept = 0, nreject = 0, iter = 0;
+  bool accept = false, reeval = false;
+  int status = LWFB_ST_OK;
+
+  // ---- init: save u0, initial_affect of the daily callbacks, FSAL
+  if (d.rec) write_record(d.rec);
+  cb_amounts<NT>(mb, forc + (int64_t)d.t0_day * LWFB_F, t0, y, ds, TRANIst, RWUst);
+  for (int q = 0; q < 8; q++) y[N + 1 + q] = 0.0;
+  cb_deltas(t0);
+  for (int j = 0; j < NE; j++) yprev[j] = y[j];
+  mb.rhs(yprev, yprev[N], t, k[0]);
+  double tstop = fmin(t0 + 1.0, tend);
+  int rec = 1;
+
+  while (t < tend) {
+    // loopheader!
+    if (iter > 0) {
+      if (accept) {
+        for (int j = 0; j < NE; j++) yprev[j] = y[j];
+        dt = dtpropose;
+        if (reeval) mb.rhs(y, y[N], t, k[0]);
+        else for (int j = 0; j < NE; j++) k[0][j] = k[6][j];
+      } else {
+        dt = dt / jmin(1 / qmin, q11 / gamma);
+      }
+    }
+    iter++;
+    if (iter > d.maxiters) { status = LWFB_ST_MAXITERS; break; }
+    {
+      bool bad = false;
+      for (int i = 0; i < N; i++) bad |= (y[i] != y[i]);
+      if (bad) { status = LWFB_ST_UNSTABLE; break; }
+    }
+    dt = dt < d.dtmax ? dt : d.dtmax;
+    { double dtmin_t = fmax(eps_of(t), dtmin_opt); if (dt < dtmin_t) dt = dtmin_t; }
+    if (dt > tstop - t) dt = tstop - t;
+    if (!(fabs(dt) > dtmin_opt)) { status = LWFB_ST_DTMIN; break; }
+    // perform_step! Tsit5; only SWATI and GWAT feed the RHS, the accumulators ride along
+    double tmp[NEMAX];
+    for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + (dt * a21) * k[0][j];
+    mb.rhs(tmp, tmp[N], t + c1 * dt, k[1]);
+    for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + dt * (a31 * k[0][j] + a32 * k[1][j]);
+    mb.rhs(tmp, tmp[N], t + c2 * dt, k[2]);
+    for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + dt * (a41 * k[0][j] + a42 * k[1][j] + a43 * k[2][j]);
+    mb.rhs(tmp, tmp[N], t + c3 * dt, k[3]);
+    for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + dt * (a51 * k[0][j] + a52 * k[1][j] + a53 * k[2][j] + a54 * k[3][j]);
+    mb.rhs(tmp, tmp[N], t + c4 * dt, k[4]);
+    for (int j = 0; j <= N; j++)
+      tmp[j] = yprev[j] + dt * (a61 * k[0][j] + a62 * k[1][j] + a63 * k[2][j] + a64 * k[3][j] + a65 * k[4][j]);
+    mb.rhs(tmp, tmp[N], t + dt, k[5]);
+    for (int j = 0; j < NE; j++)
+      y[j] = yprev[j] + dt * (a71 * k[0][j] + a72 * k[1][j] + a73 * k[2][j] + a74 * k[3][j] + a75 * k[4][j] + a76 * k[5][j]);
+    mb.rhs(y, y[N], t + dt, k[6]);  // clamps the new SWATI in place
+    // residuals + norm_to_use (src/func_DiffEq_definition_ode.jl:20-37): RMS over 3N+39 entries
+    double ss = 0;
+    for (int j = 0; j < NE; j++) {
+      double ut = dt * (bt1 * k[0][j] + bt2 * k[1][j] + bt3 * k[2][j] + bt4 * k[3][j] + bt5 * k[4][j] + bt6 * k[5][j] + bt7 * k[6][j]);
+      double r = ut / (d.abstol + jmax(fabs(yprev[j]), fabs(y[j])) * d.reltol);
+      ss += r * r;
+    }
+    double EEst = sqrt(ss / (double)(3 * N + 39));
+    // loopfooter!: PI controller
+    reeval = false;
+    double ttmp = t + dt;
+    double q;
+    if (EEst == 0.0) q = 1 / qmax;
+    else {
+      q11 = fastpow(EEst, beta1);
+      q = q11 / fastpow(qold, beta2);
+      q = jmax(1 / qmax, jmin(1 / qmin, q / gamma));
+    }
+    accept = (EEst <= 1.0);
+    if (accept) {
+      naccept++;
+      qold = jmax(EEst, qoldinit);
+      double dtnew = dt / q;
+      tprev = t;
+      t = (fabs(ttmp - tstop) < 100 * eps_of(fmax(t, tstop))) ? tstop : ttmp;
+      dtpropose = d.dtmax < dtnew ? d.dtmax : dtnew;
+      { double dtmin_t = fmax(eps_of(t), dtmin_opt); if (dtpropose < dtmin_t) dtpropose = dtmin_t; }
+      double dp[2] = {0, 0};
+      if (iso) prec_delta(t, dp);
+      if (t == tstop) {
+        // the record is saved before the callbacks of this instant (and before this step's ADE update)
+        if (d.rec) write_record(d.rec + (int64_t)rec * L * M);
+        rec++;
+        if (t < tend) {
+          // LWFBrook90R_check_balance_errors! src/func_DiffEq_definition_cb.jl:1255-1314
+          {
+            double* a = ds.acc;
+            double Ssum = 0;
+            for (int i = 0; i < N; i++) Ssum += y[i];
+            double Wt = ds.INTR + ds.INTS + ds.SNOW + Ssum + y[N];
+            double qin = 0 + (y[N + 4] - y[N + 5]);
+            double qout = y[N + 8] + y[N + 6] + a[LWFB_A_CUM_D_TRAN] + a[LWFB_A_CUM_D_SLVP];
+            double qin_t = a[LWFB_A_CUM_D_PREC];
+            double qout_t = a[LWFB_A_CUM_D_EVAP] + y[N + 1] + y[N + 2];
+            a[LWFB_A_BALERD_SWAT] = (qin - qout) - (Ssum - a[LWFB_A_STORAGESWAT]);
+            a[LWFB_A_BALERD_TOTAL] = (qin_t - qout_t) - (Wt - a[LWFB_A_STORAGEWATER]);
+            a[LWFB_A_STORAGESWAT] = Ssum;
+            a[LWFB_A_STORAGEWATER] = Wt;
+          }
+          if (iso) ade_step<NT>(mb, is, y, y[N], t - tprev, dp);
+          int day = (int)floor(t + 0.5);
+          cb_amounts<NT>(mb, forc + (int64_t)day * LWFB_F, t, y, ds, TRANIst, RWUst);
+          for (int q8 = 0; q8 < 8; q8++) y[N + 1 + q8] = 0.0;
+          cb_deltas(t);
+          reeval = true;
+          tstop = fmin(tstop + 1.0, tend);
+        }
+      } else {
+        if (iso) ade_step<NT>(mb, is, y, y[N], t - tprev, dp);
+      }
+    } else {
+      nreject++;
+    }
+    if (mb.status != LWFB_ST_OK) { status = mb.status; break; }
+  }
+  if (d.rec) {
+    for (; rec <= d.n_days; rec++)
+      for (int j = 0; j < L; j++) d.rec[((int64_t)rec * L + j) * M + m] = NAN;
+  }
+  write_record(d.fin);
+  d.status[m] = status;
+  d.counters[(int64_t)LWFB_C_NACCEPT * M + m] = naccept;
+  d.counters[(int64_t)LWFB_C_NREJECT * M + m] = nreject;
+  d.counters[(int64_t)LWFB_C_NF * M + m] = mb.nf;
+}
+
+// one RHS evaluation per member (parity tests)
+template <int NT>
+__global__ void rhs_kernel(DevData d, double t, const double* __restrict__ swati, const double* __restrict__ gwat,
+                           const double* __restrict__ frozen, const double* __restrict__ ntfli_prev,
+                           double* __restrict__ du) {
+  constexpr int NMAX = Member<NT>::NMAX;
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= d.M) return;
+  Member<NT> mb;
+  mb.load(d, m);
+  const int N = mb.N;
+  double sw[NMAX], out[NMAX + 9];
+  for (int i = 0; i < N; i++) sw[i] = swati[m * N + i];
+  mb.RNET = frozen[m * (N + 3) + 0]; mb.SMLT = frozen[m * (N + 3) + 1]; mb.SLVP = frozen[m * (N + 3) + 2];
+  for (int i = 0; i < N; i++) { mb.TRANI[i] = frozen[m * (N + 3) + 3 + i]; mb.NTFLI[i] = ntfli_prev[m * N + i]; }
+  mb.rhs(sw, gwat[m], t, out);
+  for (int j = 0; j < N + 9; j++) du[m * (N + 9) + j] = out[j];
+}
+
+// [K][M] rows k in [0,K) of members [m_first, m_first+cnt) -> [cnt][K]
+__global__ void soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, int64_t M, int64_t m_first,
+                           int64_t cnt, int K) {
+  __shared__ double tile[32][33];
+  int64_t m0 = (int64_t)blockIdx.x * 32;
+  int k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int kk = k0 + r;
+    int64_t mm = m0 + threadIdx.x;
+    if (mm < cnt && kk < K) tile[r][threadIdx.x] = src[(int64_t)kk * M + m_first + mm];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int64_t mm = m0 + r;
+    int kk = k0 + threadIdx.x;
+    if (mm < cnt && kk < K) dst[mm * K + kk] = tile[threadIdx.x][r];
+  }
+}
+
+// per-member goodness of fit against observed theta / delta18O (RMSE, KGE)
+__global__ void score_kernel(DevData d, int n_obs_days, const int32_t* __restrict__ obs_day, int n_obs_layers,
+                             const int32_t* __restrict__ obs_layer, const double* __restrict__ obs_theta,
+                             const double* __restrict__ obs_d18o, double* __restrict__ scores) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= d.M) return;
+  const int64_t M = d.M;
+  const int N = d.N, L = d.L;
+  double res[LWFB_NSCORES];
+  for (int v = 0; v < 2; v++) {
+    const double* obs = v == 0 ? obs_theta : obs_d18o;
+    double n = 0, se = 0, so = 0, ss = 0, soo = 0, sss = 0, sos = 0;
+    if (obs != nullptr && (v == 0 || d.iso)) {
+      for (int l = 0; l < n_obs_layers; l++) {
+        int i = obs_layer[l];
+        double ths = __ldg(d.lay + ((int64_t)LWFB_L_THSAT * N + i) * M + m);
+        double thr = __ldg(d.lay + ((int64_t)LWFB_L_THR * N + i) * M + m);
+        double smax = __ldg(d.lay + ((int64_t)LWFB_L_SWATMAX * N + i) * M + m);
+        for (int k = 0; k < n_obs_days; k++) {
+          double o = obs[(int64_t)k * n_obs_layers + l];
+          if (o != o) continue;
+          const double* r = d.rec + (int64_t)obs_day[k] * L * M;
+          double sim;
+          if (v == 0) {
+            double sw = r[(int64_t)i * M + m];
+            double w = jmin(1.0, (ths * sw / smax - thr) / (ths - thr));
+            sim = w * (ths - thr) + thr;
+          } else {
+            sim = r[(int64_t)(N + i) * M + m];
+          }
+          double e = sim - o;
+          n += 1; se += e * e; so += o; ss += sim; soo += o * o; sss += sim * sim; sos += o * sim;
+        }
+      }
+    }
+    double rmse = NAN, kge = NAN;
+    if (n > 0) {
+      rmse = sqrt(se / n);
+      double mo = so / n, ms = ss / n;
+      double vo = soo / n - mo * mo, vs = sss / n - ms * ms, cov = sos / n - mo * ms;
+      double r = cov / sqrt(vo * vs), al = sqrt(vs / vo), be = ms / mo;
+      kge = 1 - sqrt((r - 1) * (r - 1) + (al - 1) * (al - 1) + (be - 1) * (be - 1));
+    }
+    res[2 * v] = rmse; res[2 * v + 1] = kge;
+  }
+  for (int s = 0; s < LWFB_NSCORES; s++) scores[m * LWFB_NSCORES + s] = res[s];
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+struct lwfb_handle {
+  lwfb_opts o;
+  int L = 0;
+  int n_sites = 0, n_rows = 0;
+  int64_t M = 0;
+  double *d_forc = nullptr, *d_scal = nullptr, *d_lay = nullptr, *d_u0 = nullptr, *d_rec = nullptr, *d_fin = nullptr;
+  int32_t *d_site = nullptr, *d_status = nullptr;
+  long long* d_counters = nullptr;
+  double* d_stage = nullptr;  // staging for layout transposes
+  size_t stage_bytes = 0;
+  double* d_scores = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int n_launches = 0;
+  float last_ms = 0.f;
+  bool ran = false;
+  std::string err;
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+      return LWFB_ERR_CUDA;                                                                   \
+    }                                                                                         \
+  } while (0)
+
+static int ensure_stage(lwfb_handle* h, size_t bytes) {
+  if (h->stage_bytes >= bytes) return LWFB_OK;
+  if (h->d_stage) cudaFree(h->d_stage);
+  h->d_stage = nullptr; h->stage_bytes = 0;
+  CK(cudaMalloc(&h->d_stage, bytes));
+  h->stage_bytes = bytes;
+  return LWFB_OK;
+}
+
+extern "C" void lwfb_default_opts(lwfb_opts* o) {
+  memset(o, 0, sizeof(*o));
+  o->n_layers = 0; o->simulate_isotopes = 1; o->t0_day = 0; o->n_days = 0;
+  o->reltol = 1e-5; o->abstol = 1e-6; o->dt_init = 1e-3; o->dtmax = 60.0 / 60.0 / 24.0;
+  o->maxiters = 1000000; o->device = 0; o->record_daily = 1;
+}
+
+extern "C" int lwfb_create(lwfb_handle** out, const lwfb_opts* opts) {
+  if (!out || !opts) return LWFB_ERR_ARG;
+  *out = nullptr;
+  if (opts->n_layers < 1 || opts->n_layers > LWFB_MAX_LAYERS) return LWFB_ERR_UNSUPPORTED;
+  if (opts->n_days < 1 || opts->t0_day < 0) return LWFB_ERR_ARG;
+  lwfb_handle* h = new lwfb_handle();
+  h->o = *opts;
+  h->L = LWFB_STATE_LEN(opts->n_layers, opts->simulate_isotopes);
+  cudaError_t e = cudaSetDevice(opts->device);
+  if (e != cudaSuccess) { delete h; return LWFB_ERR_CUDA; }
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  *out = h;
+  return LWFB_OK;
+}
+
+static void free_members(lwfb_handle* h) {
+  cudaFree(h->d_scal); cudaFree(h->d_lay); cudaFree(h->d_u0); cudaFree(h->d_rec); cudaFree(h->d_fin);
+  cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores);
+  h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
+  h->d_site = h->d_status = nullptr; h->d_counters = nullptr;
+  h->M = 0; h->ran = false;
+}
+
+extern "C" void lwfb_destroy(lwfb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->o.device);
+  free_members(h);
+  cudaFree(h->d_forc); cudaFree(h->d_stage);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+}
+
+extern "C" const char* lwfb_last_error(const lwfb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+extern "C" int lwfb_set_sites(lwfb_handle* h, int32_t n_sites, int32_t n_rows, const double* forcing) {
+  if (!h || !forcing || n_sites < 1) return LWFB_ERR_ARG;
+  if (n_rows < h->o.t0_day + h->o.n_days + 1) { h->err = "forcing table shorter than t0_day+n_days+1 rows"; return LWFB_ERR_ARG; }
+  CK(cudaSetDevice(h->o.device));
+  cudaFree(h->d_forc); h->d_forc = nullptr;
+  size_t bytes = (size_t)n_sites * n_rows * LWFB_F * sizeof(double);
+  CK(cudaMalloc(&h->d_forc, bytes));
+  CK(cudaMemcpy(h->d_forc, forcing, bytes, cudaMemcpyHostToDevice));
+  h->n_sites = n_sites; h->n_rows = n_rows;
+  return LWFB_OK;
+}
+
+// strided transpose: [cnt][K] -> dst[k*M + m0 + m]
+__global__ void aos_to_soa_strided(const double* __restrict__ src, double* __restrict__ dst, int64_t cnt, int K,
+                                   int64_t M, int64_t m0) {
+  __shared__ double tile[32][33];
+  int64_t mb = (int64_t)blockIdx.x * 32;
+  int k0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int64_t mm = mb + r;
+    int kk = k0 + threadIdx.x;
+    if (mm < cnt && kk < K) tile[r][threadIdx.x] = src[mm * K + kk];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int kk = k0 + r;
+    int64_t mm = mb + threadIdx.x;
+    if (mm < cnt && kk < K) dst[(int64_t)kk * M + m0 + mm] = tile[threadIdx.x][r];
+  }
+}
+
+static int upload_soa(lwfb_handle* h, const double* src, double* dst, int64_t M, int K) {
+  const int64_t chunk = 1 << 16;
+  int rc = ensure_stage(h, (size_t)chunk * K * sizeof(double));
+  if (rc) return rc;
+  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+    int64_t cnt = M - m0 < chunk ? M - m0 : chunk;
+    CK(cudaMemcpy(h->d_stage, src + m0 * K, (size_t)cnt * K * sizeof(double), cudaMemcpyHostToDevice));
+    dim3 blk(32, 8), grd((unsigned)((cnt + 31) / 32), (unsigned)((K + 31) / 32));
+    aos_to_soa_strided<<<grd, blk>>>(h->d_stage, dst, cnt, K, M, m0);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+  }
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t* site_of_member,
+                                const double* scal, const double* lay, const double* u0) {
+  if (!h || n_members < 1 || !site_of_member || !scal || !lay || !u0) return LWFB_ERR_ARG;
+  if (!h->d_forc) { h->err = "lwfb_set_sites must be called first"; return LWFB_ERR_ARG; }
+  for (int64_t i = 0; i < n_members; i++)
+    if (site_of_member[i] < 0 || site_of_member[i] >= h->n_sites) { h->err = "site index out of range"; return LWFB_ERR_ARG; }
+  CK(cudaSetDevice(h->o.device));
+  const int N = h->o.n_layers, L = h->L;
+  if (n_members != h->M) {
+    free_members(h);
+    int64_t M = n_members;
+    CK(cudaMalloc(&h->d_scal, (size_t)M * LWFB_PS * sizeof(double)));
+    CK(cudaMalloc(&h->d_lay, (size_t)M * LWFB_PL * N * sizeof(double)));
+    CK(cudaMalloc(&h->d_u0, (size_t)M * L * sizeof(double)));
+    CK(cudaMalloc(&h->d_fin, (size_t)M * L * sizeof(double)));
+    CK(cudaMalloc(&h->d_site, (size_t)M * sizeof(int32_t)));
+    CK(cudaMalloc(&h->d_status, (size_t)M * sizeof(int32_t)));
+    CK(cudaMalloc(&h->d_counters, (size_t)M * LWFB_NCOUNTERS * sizeof(long long)));
+    CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
+    if (h->o.record_daily) {
+      size_t bytes = (size_t)M * (h->o.n_days + 1) * L * sizeof(double);
+      cudaError_t e = cudaMalloc(&h->d_rec, bytes);
+      if (e != cudaSuccess) { h->err = "cannot allocate the daily record (" + std::to_string(bytes >> 20) + " MiB)"; free_members(h); return LWFB_ERR_NOMEM; }
+    }
+    h->M = M;
+  }
+  CK(cudaMemcpy(h->d_site, site_of_member, (size_t)h->M * sizeof(int32_t), cudaMemcpyHostToDevice));
+  int rc;
+  if ((rc = upload_soa(h, scal, h->d_scal, h->M, LWFB_PS))) return rc;
+  if ((rc = upload_soa(h, lay, h->d_lay, h->M, LWFB_PL * N))) return rc;
+  if ((rc = upload_soa(h, u0, h->d_u0, h->M, L))) return rc;
+  h->ran = false;
+  return LWFB_OK;
+}
+
+static DevData make_dev(lwfb_handle* h) {
+  DevData d;
+  d.M = h->M; d.N = h->o.n_layers; d.iso = h->o.simulate_isotopes; d.t0_day = h->o.t0_day; d.n_days = h->o.n_days;
+  d.n_rows = h->n_rows; d.L = h->L;
+  d.scal = h->d_scal; d.lay = h->d_lay; d.forc = h->d_forc; d.site = h->d_site; d.u0 = h->d_u0;
+  d.rec = h->d_rec; d.fin = h->d_fin; d.status = h->d_status; d.counters = h->d_counters;
+  d.reltol = h->o.reltol; d.abstol = h->o.abstol; d.dt_init = h->o.dt_init; d.dtmax = h->o.dtmax;
+  d.maxiters = h->o.maxiters;
+  return d;
+}
+
+extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
+  if (!h || h->M < 1) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  DevData d = make_dev(h);
+  unsigned grid = (unsigned)((h->M + LWFB_BLOCK - 1) / LWFB_BLOCK);
+  CK(cudaEventRecord(h->ev0, st));
+  switch (d.N) {
+    case 5: integrate_kernel<5><<<grid, LWFB_BLOCK, 0, st>>>(d); break;
+    case 7: integrate_kernel<7><<<grid, LWFB_BLOCK, 0, st>>>(d); break;
+    default: integrate_kernel<0><<<grid, LWFB_BLOCK, 0, st>>>(d); break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, st));
+  h->n_launches = 1;
+  h->ran = true;
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_sync(lwfb_handle* h) {
+  if (!h) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  CK(cudaEventSynchronize(h->ev1));
+  CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
+  int rc = lwfb_run_async(h, cuda_stream);
+  if (rc) return rc;
+  return lwfb_sync(h);
+}
+
+extern "C" int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* device_ms) {
+  if (!h) return LWFB_ERR_ARG;
+  if (n_launches) *n_launches = h->n_launches;
+  if (device_ms) *device_ms = h->last_ms;
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_get_daily(lwfb_handle* h, int64_t member_first, int64_t member_count, double* out) {
+  if (!h || !out || !h->ran) return LWFB_ERR_ARG;
+  if (!h->d_rec) { h->err = "handle was created with record_daily = 0"; return LWFB_ERR_ARG; }
+  if (member_first < 0 || member_count < 1 || member_first + member_count > h->M) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  const int K = (h->o.n_days + 1) * h->L;  // rows of the [K][M] device record
+  // chunk over members so that the staging buffer stays moderate
+  int64_t chunk = (int64_t)((256u << 20) / ((size_t)K * sizeof(double)));
+  if (chunk < 32) chunk = 32;
+  int rc = ensure_stage(h, (size_t)chunk * K * sizeof(double));
+  if (rc) return rc;
+  for (int64_t m0 = 0; m0 < member_count; m0 += chunk) {
+    int64_t cnt = member_count - m0 < chunk ? member_count - m0 : chunk;
+    dim3 blk(32, 8), grd((unsigned)((cnt + 31) / 32), (unsigned)((K + 31) / 32));
+    soa_to_aos<<<grd, blk>>>(h->d_rec, h->d_stage, h->M, member_first + m0, cnt, K);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(out + m0 * K, h->d_stage, (size_t)cnt * K * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_get_final(lwfb_handle* h, int64_t member_first, int64_t member_count, double* out) {
+  if (!h || !out || !h->ran) return LWFB_ERR_ARG;
+  if (member_first < 0 || member_count < 1 || member_first + member_count > h->M) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  const int K = h->L;
+  int rc = ensure_stage(h, (size_t)member_count * K * sizeof(double));
+  if (rc) return rc;
+  dim3 blk(32, 8), grd((unsigned)((member_count + 31) / 32), (unsigned)((K + 31) / 32));
+  soa_to_aos<<<grd, blk>>>(h->d_fin, h->d_stage, h->M, member_first, member_count, K);
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(out, h->d_stage, (size_t)member_count * K * sizeof(double), cudaMemcpyDeviceToHost));
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_get_status(lwfb_handle* h, int32_t* status, int64_t* counters) {
+  if (!h || !h->ran) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  if (status) CK(cudaMemcpy(status, h->d_status, (size_t)h->M * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  if (counters) {
+    std::vector<long long> tmp((size_t)h->M * LWFB_NCOUNTERS);
+    CK(cudaMemcpy(tmp.data(), h->d_counters, tmp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int64_t m = 0; m < h->M; m++)
+      for (int c = 0; c < LWFB_NCOUNTERS; c++) counters[m * LWFB_NCOUNTERS + c] = tmp[(size_t)c * h->M + m];
+  }
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_scores_device(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_day, int32_t n_obs_layers,
+                                  const int32_t* obs_layer, const double* obs_theta, const double* obs_d18o,
+                                  double** d_scores) {
+  if (!h || !h->ran || n_obs_days < 1 || n_obs_layers < 1 || !obs_day || !obs_layer) return LWFB_ERR_ARG;
+  if (!h->d_rec) { h->err = "scores need the daily record (record_daily = 1)"; return LWFB_ERR_ARG; }
+  for (int k = 0; k < n_obs_days; k++)
+    if (obs_day[k] < 0 || obs_day[k] > h->o.n_days) { h->err = "obs_day out of range"; return LWFB_ERR_ARG; }
+  for (int l = 0; l < n_obs_layers; l++)
+    if (obs_layer[l] < 0 || obs_layer[l] >= h->o.n_layers) { h->err = "obs_layer out of range"; return LWFB_ERR_ARG; }
+  CK(cudaSetDevice(h->o.device));
+  size_t nobs = (size_t)n_obs_days * n_obs_layers;
+  size_t bytes = sizeof(int32_t) * (n_obs_days + n_obs_layers) + 2 * nobs * sizeof(double) + 64;
+  int rc = ensure_stage(h, bytes);
+  if (rc) return rc;
+  char* p = (char*)h->d_stage;
+  double* d_th = (double*)p; p += nobs * sizeof(double);
+  double* d_18 = (double*)p; p += nobs * sizeof(double);
+  int32_t* d_day = (int32_t*)p; p += n_obs_days * sizeof(int32_t);
+  int32_t* d_layer = (int32_t*)p;
+  if (obs_theta) CK(cudaMemcpy(d_th, obs_theta, nobs * sizeof(double), cudaMemcpyHostToDevice));
+  if (obs_d18o) CK(cudaMemcpy(d_18, obs_d18o, nobs * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_day, obs_day, n_obs_days * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_layer, obs_layer, n_obs_layers * sizeof(int32_t), cudaMemcpyHostToDevice));
+  DevData d = make_dev(h);
+  unsigned grid = (unsigned)((h->M + 255) / 256);
+  score_kernel<<<grid, 256>>>(d, n_obs_days, d_day, n_obs_layers, d_layer, obs_theta ? d_th : nullptr,
+                              obs_d18o ? d_18 : nullptr, h->d_scores);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  if (d_scores) *d_scores = h->d_scores;
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_scores(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_day, int32_t n_obs_layers,
+                           const int32_t* obs_layer, const double* obs_theta, const double* obs_d18o, double* scores) {
+  if (!scores) return LWFB_ERR_ARG;
+  double* dptr = nullptr;
+  int rc = lwfb_scores_device(h, n_obs_days, obs_day, n_obs_layers, obs_layer, obs_theta, obs_d18o, &dptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(scores, dptr, (size_t)h->M * LWFB_NSCORES * sizeof(double), cudaMemcpyDeviceToHost));
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, const double* gwat, const double* frozen,
+                             const double* ntfli_prev, double* du) {
+  if (!h || h->M < 1 || !swati || !gwat || !frozen || !ntfli_prev || !du) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  const int N = h->o.n_layers;
+  const int64_t M = h->M;
+  size_t n_sw = (size_t)M * N, n_fr = (size_t)M * (N + 3), n_du = (size_t)M * (N + 9);
+  int rc = ensure_stage(h, (2 * n_sw + M + n_fr + n_du) * sizeof(double));
+  if (rc) return rc;
+  double* p = h->d_stage;
+  double* d_sw = p; p += n_sw;
+  double* d_gw = p; p += M;
+  double* d_fr = p; p += n_fr;
+  double* d_nt = p; p += n_sw;
+  double* d_du = p;
+  CK(cudaMemcpy(d_sw, swati, n_sw * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_gw, gwat, M * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_fr, frozen, n_fr * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_nt, ntfli_prev, n_sw * sizeof(double), cudaMemcpyHostToDevice));
+  DevData d = make_dev(h);
+  unsigned grid = (unsigned)((M + 127) / 128);
+  switch (N) {
+    case 5: rhs_kernel<5><<<grid, 128>>>(d, t, d_sw, d_gw, d_fr, d_nt, d_du); break;
+    case 7: rhs_kernel<7><<<grid, 128>>>(d, t, d_sw, d_gw, d_fr, d_nt, d_du); break;
+    default: rhs_kernel<0><<<grid, 128>>>(d, t, d_sw, d_gw, d_fr, d_nt, d_du); break;
+  }
+  CK(cudaGetLastError());
+  CK(cudaMemcpy(du, d_du, n_du * sizeof(double), cudaMemcpyDeviceToHost));
+  return LWFB_OK;
+}

@@ -1,0 +1,983 @@
+// lwfb90_device.cuh — device-side model and integrator for sm_100a.
+//
+// One ensemble member per thread.  Everything a member needs between two daily callbacks lives in
+// registers / thread-local storage; per-member parameters are read from structure-of-arrays global
+// memory ([field][member], coalesced across a warp); the per-site forcing table is read through the
+// read-only path (all lanes of a warp normally share a site, so a row is one broadcast 128 B line).
+//
+// What each function replaces in the reference (fabern/LWFBrook90.jl v0.9.9, paths relative to the
+// reference root) is cited next to it.  The arithmetic follows the reference formulas; the time
+// stepping restates OrdinaryDiffEq's Tsit5 + PI controller + callback ordering.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/lwfb90.h"
+#include "lwfb90_math.cuh"
+
+namespace lwfb {
+
+// src/module_CONSTANTS.jl:5-23
+__device__ constexpr double p_WTOMJ = 0.0864, p_ETOM = 0.4085, p_CPRHO = 1240., p_GAMMA = 0.067,
+                            p_CVLQ = 0.00418, p_CVICE = 0.00192, p_LF = 0.335, p_LS = 2.824,
+                            p_RHOWG = 0.00981, p_SIGMA = 5.67E-08, p_SC = 1367., p_K = 0.4,
+                            p_PI = 3.1416, p_DTIMIN = 1.e-9;
+
+// Julia min/max propagate NaN (fmin/fmax do not)
+__device__ __forceinline__ double jmin(double a, double b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
+__device__ __forceinline__ double jmax(double a, double b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
+
+struct DevData {
+  int64_t M;        // members
+  int N, iso, t0_day, n_days, n_rows, L;
+  const double* __restrict__ scal;   // [LWFB_PS][M]
+  const double* __restrict__ lay;    // [LWFB_PL][N][M]
+  const double* __restrict__ forc;   // [n_sites][n_rows][LWFB_F]
+  const int32_t* __restrict__ site;  // [M]
+  const double* __restrict__ u0;     // [L][M]
+  double* __restrict__ rec;          // [n_days+1][L][M]  (may be null: no daily record)
+  double* __restrict__ fin;          // [L][M] final state (always written)
+  int32_t* __restrict__ status;      // [M]
+  long long* __restrict__ counters;  // [LWFB_NCOUNTERS][M]
+  double reltol, abstol, dt_init, dtmax;
+  long long maxiters;
+};
+
+// state-vector offsets, src/func_DiffEq_definition_u0.jl:42-73
+struct SIdx {
+  int k, SWATI, GWAT, INTS, INTR, SNOW, RWU, XYLEM, CC, SNOWLQ, TRANI, AUX, ACC, L;
+  __host__ __device__ SIdx(int N, int iso) {
+    k = iso ? 3 : 1;
+    int o = 0;
+    SWATI = 0; o += k * N;
+    GWAT = o; o += k; INTS = o; o += k; INTR = o; o += k; SNOW = o; o += k; RWU = o; o += k; XYLEM = o; o += k;
+    CC = o; SNOWLQ = o + 1; o += 2;
+    TRANI = o; o += k * N;
+    AUX = o; o += 3 * N;
+    ACC = o; o += LWFB_NACCUM;
+    L = o;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Per-thread model: parameters of the hot loop cached in thread storage + mutable caches that the
+// reference keeps in `p` (src/func_DiffEq_definition_p.jl:503-581).
+// NT > 0: compile-time layer count (loops unrolled, arrays in registers); NT == 0: runtime N.
+// ---------------------------------------------------------------------------------------------
+template <int NT>
+struct Member {
+  static constexpr int NMAX = NT > 0 ? NT : LWFB_MAX_LAYERS;
+  int N;
+  int64_t m, M;
+  const double* __restrict__ scal;
+  const double* __restrict__ lay;
+  // per-layer constants of the RHS
+  double THSAT[NMAX], THR[NMAX], SWATMAX[NMAX], KSAT[NMAX], TORT[NMAX], PSIG[NMAX], THICK[NMAX], STONEF[NMAX],
+      INFRAC[NMAX];
+  double cpsi[NMAX];   // 9.81 * (-1/alpha)
+  double e_negInvM[NMAX], e_invN[NMAX], e_nOverNm1[NMAX], e_oneMinusInvN[NMAX];
+  // scalars of the RHS
+  double DPSIMAX, DSWMAX, DTIMAX, DRAIN, GSC, GSP, IMPERV, QFFC, QFPAR, SWATQX, SWATQF, DSLOPE, LENGTH_SLOPE;
+  int QLAYER, BYPAR;
+  // daily-frozen fluxes and flux caches
+  double RNET, SMLT, SLVP, TA;
+  double TRANI[NMAX], NTFLI[NMAX], VRFLI[NMAX], INFLI[NMAX], DSFLI[NMAX];
+  long long nf;
+  int status;
+
+  __device__ __forceinline__ double S(int k) const { return __ldg(scal + (int64_t)k * M + m); }
+  __device__ __forceinline__ double Lp(int k, int i) const { return __ldg(lay + ((int64_t)k * N + i) * M + m); }
+
+  __device__ void load(const DevData& d, int64_t mm) {
+    m = mm; M = d.M; N = NT > 0 ? NT : d.N; scal = d.scal; lay = d.lay;
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) {
+      THSAT[i] = Lp(LWFB_L_THSAT, i); THR[i] = Lp(LWFB_L_THR, i); SWATMAX[i] = Lp(LWFB_L_SWATMAX, i);
+      KSAT[i] = Lp(LWFB_L_KSAT, i); TORT[i] = Lp(LWFB_L_TORT, i); PSIG[i] = Lp(LWFB_L_PSIG, i);
+      THICK[i] = Lp(LWFB_L_THICK, i); STONEF[i] = Lp(LWFB_L_STONEF, i); INFRAC[i] = Lp(LWFB_L_INFRAC, i);
+      double n = Lp(LWFB_L_NPAR, i), mp = Lp(LWFB_L_MPAR, i);
+      cpsi[i] = 9.81 * (-1.0 / Lp(LWFB_L_ALPHA, i));
+      e_negInvM[i] = -1.0 / mp; e_invN[i] = 1.0 / n; e_nOverNm1[i] = n / (n - 1.0); e_oneMinusInvN[i] = 1.0 - 1.0 / n;
+      TRANI[i] = NAN; NTFLI[i] = NAN; VRFLI[i] = NAN; INFLI[i] = NAN; DSFLI[i] = NAN;
+    }
+    DPSIMAX = S(LWFB_S_DPSIMAX); DSWMAX = S(LWFB_S_DSWMAX); DTIMAX = S(LWFB_S_DTIMAX); DRAIN = S(LWFB_S_DRAIN);
+    GSC = S(LWFB_S_GSC); GSP = S(LWFB_S_GSP); IMPERV = S(LWFB_S_IMPERV); QFFC = S(LWFB_S_QFFC);
+    QFPAR = S(LWFB_S_QFPAR); SWATQX = S(LWFB_S_SWATQX); SWATQF = S(LWFB_S_SWATQF); DSLOPE = S(LWFB_S_DSLOPE);
+    LENGTH_SLOPE = S(LWFB_S_LENGTH_SLOPE);
+    QLAYER = (int)S(LWFB_S_QLAYER); BYPAR = (S(LWFB_S_BYPAR) == 1.0) ? 1 : 0;
+    RNET = SMLT = SLVP = TA = NAN;
+    nf = 0; status = LWFB_ST_OK;
+  }
+
+  // SWCHEK! src/module_KPT.jl:761-790
+  __device__ __forceinline__ void swchek(double* sw) const {
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) {
+      if (sw[i] <= 0.0) sw[i] = 0.0;
+      else if (sw[i] > SWATMAX[i]) sw[i] = SWATMAX[i];
+    }
+  }
+
+  // derive_auxiliary_SOILVAR! src/module_KPT.jl:445-464 (FPSIM_MvG! :596-605, FK_MvG! :502-509,
+  // FTheta_MvG! :692-696) for one layer
+  __device__ __forceinline__ void soilvar1(int i, double sw, double& W, double& psim, double& theta, double& kk) const {
+    double w = jmin(1.0, (THSAT[i] * sw / SWATMAX[i] - THR[i]) / (THSAT[i] - THR[i]));
+    W = w;
+    double a = jmax(w, 1.e-6);
+    double la = m_log(a);
+    double p1 = m_exp_of_scaled_log(e_negInvM[i], la, a);       // a^(-1/m)
+    psim = cpsi[i] * m_pow(p1 - 1.0, e_invN[i]);
+    theta = w * (THSAT[i] - THR[i]) + THR[i];
+    double p3 = m_exp_of_scaled_log(e_nOverNm1[i], la, a);      // a^(n/(n-1))
+    double inner = 1.0 - m_pow(1.0 - p3, e_oneMinusInvN[i]);
+    kk = KSAT[i] * m_exp_of_scaled_log(TORT[i], la, a) * (inner * inner);
+  }
+
+  // f_LWFBrook90! src/func_DiffEq_definition_f.jl:7-243 with MSBITERATE! src/func_MSB_functions.jl:565-697,
+  // INFLOW! src/module_WAT.jl:313-457, ITER :459-571, VERT/KKMEAN :206-252, DSLOP! :178-198,
+  // BYFLFR! :133-142, SRFLFR :144-150, GWATER :578-596.
+  // du = (dSWATI[N], dGWAT, flow, seep, srfl, slfl, byfl, dsfl, gwfl, vrfln); sw is clamped in place.
+  __device__ void rhs(double* sw, double gwat, double t, double* du) {
+    double W[NMAX], psim[NMAX], psiti[NMAX], theta[NMAX], kk[NMAX], BYFRAC[NMAX], V0[NMAX], BYFLI[NMAX];
+    nf++;
+    swchek(sw);
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) {
+      soilvar1(i, sw[i], W[i], psim[i], theta[i], kk[i]);
+      psiti[i] = psim[i] + PSIG[i];
+    }
+    if (BYPAR) {
+#pragma unroll(NT > 0 ? NT : 1)
+      for (int i = 0; i < N; i++) {
+        double wf = Lp(LWFB_L_WETF, i);
+        BYFRAC[i] = jmin(1.0, m_pow(QFFC, 1 - (1 / QFPAR) * (W[i] - wf) / (1 - wf)));
+        if (W[i] > 0.99) BYFRAC[i] = 1;
+      }
+    } else {
+#pragma unroll(NT > 0 ? NT : 1)
+      for (int i = 0; i < N; i++) BYFRAC[i] = 0;
+    }
+    double SAFRAC = 0.;
+    if (QLAYER > 0) {
+      double s = 0;
+      for (int i = 0; i < QLAYER; i++) s += sw[i];
+      SAFRAC = jmin(1.0, m_pow(QFFC, 1 - (1 / QFPAR) * (s - SWATQF) / (SWATQX - SWATQF)));
+    }
+    double SRFL = jmin(1., (IMPERV + SAFRAC)) * (RNET + SMLT);
+    double SLFL = RNET + SMLT - SRFL;
+    if (LENGTH_SLOPE == 0 || DSLOPE == 0) {
+#pragma unroll(NT > 0 ? NT : 1)
+      for (int i = 0; i < N; i++) DSFLI[i] = 0;
+    } else {
+      double cs = cos(DSLOPE), sn = sin(DSLOPE);
+#pragma unroll(NT > 0 ? NT : 1)
+      for (int i = 0; i < N; i++) {
+        double GRAD = cs * (psim[i] * 2 / (1000 * LENGTH_SLOPE)) + sn * p_RHOWG;
+        double ARATIO = THICK[i] * (1 - STONEF[i]) * cs / (1000 * LENGTH_SLOPE);
+        double dd = kk[i] * ARATIO * GRAD / p_RHOWG;
+        DSFLI[i] = dd < 0 ? 0 : dd;
+      }
+    }
+    // first approximation of the vertical flow; log(K) is evaluated once per layer
+    {
+      double lk[NMAX];
+#pragma unroll(NT > 0 ? NT : 1)
+      for (int i = 0; i < N; i++) lk[i] = m_log(kk[i]);
+#pragma unroll(NT > 0 ? NT : 1)
+      for (int i = 0; i < N - 1; i++) {
+        if (fabs(psiti[i] - psiti[i + 1]) < DPSIMAX) V0[i] = 0;
+        else {
+          double kkmean = m_exp((THICK[i + 1] * lk[i] + THICK[i] * lk[i + 1]) / (THICK[i] + THICK[i + 1]));
+          kkmean = jmin(jmin(kkmean, KSAT[i]), KSAT[i + 1]);
+          double grad = (psiti[i] - psiti[i + 1]) / ((THICK[i] + THICK[i + 1]) / 2.0);
+          V0[i] = (grad * kkmean / p_RHOWG) * (1.0 - (STONEF[i] + STONEF[i + 1]) / 2.0);
+        }
+      }
+      V0[N - 1] = (DRAIN > 0.00001) ? DRAIN * kk[N - 1] * (1 - STONEF[N - 1]) : 0.0;
+    }
+    double DTRI = 1.0 - fmod(t, 1.0);
+    double DTI = jmin(DTRI, DTIMAX);
+    inflow(DTI, BYFRAC, SLFL, sw, V0, BYFLI);
+    // ITER (MvG branch), consumes the NTFLI left by the previous call
+    double DTINEW = DTI;
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) {
+      DTINEW = jmin(DTINEW, 0.01 * DSWMAX * THICK[i] * THSAT[i] * (1 - STONEF[i]) / jmax(0.000001, fabs(NTFLI[i])));
+      double avail = (THR[i] - theta[i]) * THICK[i];
+      if (NTFLI[i] < 0) {
+        DTINEW = jmin(DTINEW, avail / NTFLI[i] / 1.30);
+        if (DTINEW < p_DTIMIN) DTINEW = p_DTIMIN;
+      }
+    }
+    if (DTINEW < DTI) {
+      DTI = DTINEW;
+      inflow(DTI, BYFRAC, SLFL, sw, V0, BYFLI);
+    }
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = N - 1; i >= 0; i--) {
+      if (i == 0) NTFLI[i] = INFLI[i] - VRFLI[i] - DSFLI[i] - TRANI[i] - SLVP;
+      else NTFLI[i] = VRFLI[i - 1] + INFLI[i] - VRFLI[i] - DSFLI[i] - TRANI[i];
+    }
+    double GWFL, SEEP, VN = VRFLI[N - 1];
+    if (GSC < 1.0e-8) { SEEP = GSP * VN; GWFL = VN - SEEP; }
+    else {
+      SEEP = gwat * GSC * GSP;
+      GWFL = gwat * GSC * (1. - GSP);
+      if (gwat - (GWFL + SEEP) * 1 < 0) { SEEP = gwat / 1 * GSP; GWFL = gwat / 1 * (1. - GSP); }
+    }
+    double sby = 0, sds = 0;
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) sby += BYFLI[i];
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) sds += DSFLI[i];
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) du[i] = NTFLI[i];
+    du[N + 0] = VN - GWFL - SEEP;
+    du[N + 1] = SRFL + sby + sds + GWFL;
+    du[N + 2] = SEEP;
+    du[N + 3] = SRFL;
+    du[N + 4] = SLFL;
+    du[N + 5] = sby;
+    du[N + 6] = sds;
+    du[N + 7] = GWFL;
+    du[N + 8] = VN;
+  }
+
+  // INFLOW! src/module_WAT.jl:313-457 (bottom-up oversaturation limiter)
+  __device__ __forceinline__ void inflow(double DTI, const double* BYFRAC, double SLFL, const double* sw,
+                                         const double* V0, double* BYFLI) {
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = N - 1; i >= 0; i--) {
+      BYFLI[i] = SLFL * INFRAC[i] * BYFRAC[i];
+      INFLI[i] = SLFL * INFRAC[i] * (1.0 - BYFRAC[i]);
+    }
+    VRFLI[N - 1] = V0[N - 1];
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = N - 1; i >= 0; i--) {
+      double MAXIN = (SWATMAX[i] - sw[i]) / DTI + VRFLI[i] + DSFLI[i] + TRANI[i];
+      if (i == 0) {
+        MAXIN = MAXIN + SLVP;
+        if (INFLI[0] > MAXIN) {
+          double too = INFLI[0] - MAXIN;
+          INFLI[0] = INFLI[0] - too;
+          BYFLI[0] = BYFLI[0] + too;
+        }
+      } else {
+        double vp = V0[i - 1];
+        if (vp + INFLI[i] > MAXIN) {
+          if (BYFRAC[i] > 0) {
+            if (vp < MAXIN) {
+              VRFLI[i - 1] = vp;
+              double too = INFLI[i] + vp - MAXIN;
+              INFLI[i] = INFLI[i] - too;
+              BYFLI[i] = BYFLI[i] + too;
+            } else {
+              VRFLI[i - 1] = MAXIN;
+              BYFLI[i] = BYFLI[i] + INFLI[i];
+              INFLI[i] = 0;
+            }
+          } else {
+            VRFLI[i - 1] = MAXIN - INFLI[i];
+          }
+        } else {
+          VRFLI[i - 1] = vp;
+        }
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Daily callback pieces.  These run once per member-day; they are compiled as separate
+// (non-inlined) functions so that their register footprint does not burden the stepping loop.
+// ---------------------------------------------------------------------------------------------
+
+// src/module_SUN.jl:194-207
+__device__ inline double hafday(double LAT, double DEC) {
+  if (fabs(LAT) >= p_PI / 2) LAT = (LAT > 0 ? 1.0 : (LAT < 0 ? -1.0 : 0.0)) * (p_PI / 2 - 0.01);
+  double ARG = -tan(DEC) * tan(LAT);
+  if (ARG >= 1) return 0;
+  else if (ARG <= -1) return p_PI;
+  return acos(ARG);
+}
+// src/module_SUN.jl:189-192
+__device__ inline double func3(double DEC, double L2, double L1, double a3, double a2) {
+  return (1.0 / (2.0 * p_PI)) * (sin(DEC) * sin(L1) * (a3 - a2) + cos(DEC) * cos(L1) * (sin(a3 + L2) - sin(a2 + L2)));
+}
+// SUNDS src/module_SUN.jl:140-187
+__device__ inline void sunds(double LAT, double SLOPE, double DOY, double L1, double L2, double& DAYLEN,
+                             double& I0HDAY, double& SLFDAY) {
+  double d = 1.0 - 0.0167 * cos(0.0172 * (DOY - 3));
+  double SCD = p_SC / (d * d);
+  double DEC = asin(.39785 * sin(4.868961 + 0.017203 * DOY + 0.033446 * sin(6.224111 + 0.017202 * DOY)));
+  double temp = hafday(LAT, DEC);
+  DAYLEN = jmax(0.0001, jmin(0.9999, temp / p_PI));
+  double ang1 = temp, ang0 = -temp;
+  temp = hafday(L1, DEC);
+  double ang7 = temp - L2, ang6 = -temp - L2;
+  double ang3 = jmin(ang1, ang7), ang2 = jmax(ang0, ang6);
+  double ang8 = 0, ang9 = 0, TWORIS;
+  if (ang3 < ang2) { ang2 = 0.; ang3 = 0.; }
+  ang6 = ang6 + 2.0 * p_PI;
+  if (ang6 < ang1) { ang8 = ang6; ang9 = ang1; }
+  ang7 = ang7 - 2.0 * p_PI;
+  if (ang7 > ang0) { ang8 = ang0; ang9 = ang7; TWORIS = 1.0; }
+  else TWORIS = 0.0;  // overwrites the first branch (reference quirk)
+  double I0SDAY;
+  if (TWORIS == 1.0)
+    I0SDAY = p_WTOMJ * SCD * (func3(DEC, L2, L1, ang3, ang2) + func3(DEC, L2, L1, ang9, ang8)) / cos(SLOPE);
+  else
+    I0SDAY = p_WTOMJ * SCD * func3(DEC, L2, L1, ang3, ang2) / cos(SLOPE);
+  I0HDAY = p_WTOMJ * SCD * func3(DEC, 0.0, LAT, ang1, ang0);
+  SLFDAY = (I0HDAY <= 0.0) ? 0.0 : I0SDAY / I0HDAY;
+}
+// AVAILEN src/module_SUN.jl:324-365
+__device__ inline void availen(double SLRAD, double ALBEDO, double C1, double C2, double C3, double TA, double EA,
+                               double RATIO, double SHEAT, double CR, double LAI, double SAI, double& AA,
+                               double& ASUBS) {
+  double SOLNET = (1 - ALBEDO) * SLRAD;
+  double EFFEM = 1.24 * pow(EA * 10 / (TA + 273.15), 1.0 / 7);
+  double NOVERN = (RATIO - C1) / C2;
+  if (NOVERN > 1) NOVERN = 1;
+  if (NOVERN < 0) NOVERN = 0;
+  double CLDCOR = C3 + (1 - C3) * NOVERN;
+  double tk = TA + 273.15;
+  double LNGNET = (EFFEM - 1) * CLDCOR * p_SIGMA * ((tk * tk) * (tk * tk));
+  double RN = SOLNET + LNGNET;
+  AA = RN - SHEAT;
+  ASUBS = RN * exp(-CR * (LAI + SAI)) - SHEAT;
+}
+// ESAT src/module_PET.jl:488-509
+__device__ inline void esat(double TA, double& ES, double& DELTA) {
+  ES = 0.61078 * exp(17.26939 * TA / (TA + 237.3));
+  DELTA = 4098 * ES / ((TA + 237.3) * (TA + 237.3));
+  if (TA < 0) {
+    ES = 0.61078 * exp(21.87456 * TA / (TA + 265.5));
+    DELTA = 5808 * ES / ((TA + 265.5) * (TA + 265.5));
+  }
+}
+// PM src/module_PET.jl:1102-1105
+__device__ inline double pm(double AA, double VPD, double DELTA, double RA, double RC) {
+  return (RA * DELTA * AA + p_CPRHO * VPD) / ((DELTA + p_GAMMA) * RA + p_GAMMA * RC);
+}
+// SWPE src/module_PET.jl:617-657
+__device__ inline void swpe(double AA, double ASUBS, double VPD, double RAA, double RAC, double RAS, double RSC,
+                            double RSS, double DELTA, double& PRATE, double& ERATE) {
+  double RS = (DELTA + p_GAMMA) * RAS + p_GAMMA * RSS;
+  double RC = (DELTA + p_GAMMA) * RAC + p_GAMMA * RSC;
+  double RA = (DELTA + p_GAMMA) * RAA;
+  double CCS = 1 / (1 + RS * RA / (RC * (RS + RA)));
+  double CCC = 1 / (1 + RC * RA / (RS * (RC + RA)));
+  double PMS = pm(AA, VPD - DELTA * RAS * (AA - ASUBS) / p_CPRHO, DELTA, RAA + RAS, RSS);
+  double PMC = pm(AA, VPD - DELTA * RAC * ASUBS / p_CPRHO, DELTA, RAA + RAC, RSC);
+  double LE = (CCC * PMC + CCS * PMS);
+  double D0 = VPD + RAA * (DELTA * AA - (DELTA + p_GAMMA) * LE) / p_CPRHO;
+  PRATE = p_ETOM * p_WTOMJ * pm(AA - ASUBS, D0, DELTA, RAC, RSC);
+  ERATE = p_ETOM * p_WTOMJ * pm(ASUBS, D0, DELTA, RAS, RSS);
+}
+// SWGE src/module_PET.jl:676-694
+__device__ inline double swge(double AA, double ASUBS, double VPD, double RAA, double RAS, double RSS, double DELTA,
+                              double ARATE) {
+  double LEC = ARATE / (p_ETOM * p_WTOMJ);
+  double RS = (DELTA + p_GAMMA) * RAS + p_GAMMA * RSS;
+  double RA = (DELTA + p_GAMMA) * RAA;
+  double LE = (RS / (RS + RA)) * LEC + (p_CPRHO * VPD + DELTA * RAS * ASUBS + DELTA * RAA * AA) / (RS + RA);
+  return p_ETOM * p_WTOMJ * (LE - LEC);
+}
+// SWGRA src/module_PET.jl:807-840
+__device__ inline void swgra(double UA, double ZA, double HEIGHT, double Z0, double DISP, double Z0C, double DISPC,
+                             double Z0GS, double LWIDTH, double RHOTP, double NN, double LAI, double SAI, double& RAA,
+                             double& RAC, double& RAS) {
+  double USTAR = p_K * UA / (log((ZA - DISP) / Z0));
+  double KH = p_K * USTAR * (HEIGHT - DISP);
+  RAS = (HEIGHT * exp(NN) / (NN * KH)) * (exp(-NN * Z0GS / HEIGHT) - exp(-NN * (Z0C + DISPC) / HEIGHT));
+  if (RAS < 1) RAS = 1.;
+  RAA = log((ZA - DISP) / (HEIGHT - DISP)) / (p_K * USTAR) +
+        (HEIGHT / (NN * KH)) * (-1 + exp(NN * (HEIGHT - DISPC - Z0C) / HEIGHT));
+  double UH = (USTAR / p_K) * log((HEIGHT - DISP) / Z0);
+  double RB = (100 * NN) * pow(LWIDTH / UH, 0.5) / (1 - exp(-NN / 2));
+  RAC = RB / (RHOTP * LAI + p_PI * SAI);
+}
+// SRSC src/module_PET.jl:1020-1066
+__device__ inline double srsc(double RAD, double TA, double VPD, double LAI, double SAI, double GLMIN, double GLMAX,
+                              double R5, double CVPD, double RM, double CR, double TL, double T1, double T2,
+                              double TH) {
+  double FS = (2 * LAI + SAI) / (2 * LAI);
+  double R0, FRINT;
+  if (RAD <= 1E-10) { R0 = 0; FRINT = 0; }
+  else {
+    R0 = RM * R5 / (RM - 2 * R5);
+    FRINT = ((RM + R0) / (RM * CR * FS)) * log((R0 + CR * RAD) / (R0 + CR * RAD * exp(-CR * FS * LAI)));
+  }
+  double FD = 1 / (1 + VPD / CVPD);
+  double FT;
+  if (TA <= TL) FT = 0;
+  else if (TA > TL && TA < T1) { double q = (T1 - TA) / (T1 - TL); FT = 1 - q * q; }
+  else if (TA >= T1 && TA <= T2) FT = 1;
+  else if (TA > T2 && TA < TH) { double q = (TA - T2) / (TH - T2); FT = 1 - q * q; }
+  else FT = 0;
+  double GSCc = FD * FT * FRINT * (GLMAX - GLMIN) + LAI * GLMIN;
+  return 1 / GSCc;
+}
+// WNDADJ src/module_PET.jl:543-549
+__device__ inline double wndadj(double ZA, double DISP, double Z0, double FETCH, double ZW, double Z0W) {
+  double HIBL = 0.334 * pow(FETCH, 0.875) * pow(Z0W, 0.125);
+  return log(HIBL / Z0W) * log((ZA - DISP) / Z0) / (log(HIBL / Z0) * log(ZW / Z0W));
+}
+// INTER24 src/module_EVP.jl:632-703 (24 hourly steps, storm centred on noon)
+__device__ inline void inter24(double RFAL, double PINT, double LAI, double SAI, double FRINTL, double FRINTS,
+                               double CINTRL, double CINTRS, int IHD, double INTR, double& RINT, double& IRVP) {
+  const double DTH = 1;
+  double INTRMX = CINTRL * LAI + CINTRS * SAI;
+  double cat = jmin(1, (FRINTL * LAI + FRINTS * SAI)) * RFAL / (2 * IHD);
+  double intr = INTR, s1 = 0, s2 = 0;
+#pragma unroll 1
+  for (int i = 0; i < 24; i++) {
+    double CATCH = (i < (12 - IHD) || i >= (12 + IHD)) ? 0.0 : cat;
+    double NEWINT = intr + (CATCH - PINT / 24) * DTH;
+    double ir, ri;
+    if (NEWINT > 0.0001) {
+      ir = PINT / 24;
+      ri = (NEWINT > INTRMX) ? ir + (INTRMX - intr) / DTH : CATCH;
+    } else {
+      ir = intr / DTH + CATCH;
+      ri = CATCH;
+    }
+    intr = intr + (ri - ir) * DTH;
+    s1 += ri * DTH;
+    s2 += ir * DTH;
+  }
+  RINT = s1;
+  IRVP = s2;
+}
+// SNOFRAC src/module_SNO.jl:98-107
+__device__ inline double snofrac(double TMAX, double TMIN, double RSTEMP) {
+  if (TMIN >= RSTEMP) return 0.0;
+  else if (TMAX < RSTEMP) return 1.0;
+  return 1.0 - (TMAX - RSTEMP) / (TMAX - TMIN);
+}
+// SNOWPACK src/module_SNO.jl:311-493
+__device__ inline void snowpack(double RTHR, double STHR, double PSNVP, double SNOEN, double& CC, double& SNOW,
+                                double& SNOWLQ, double DTP, double TA, double MAXLQF, double GRDMLT, double& RSNO,
+                                double& SNVP, double& SMLT) {
+  double u_CC = CC, u_SNOW = SNOW, u_SNOWLQ = SNOWLQ;
+  double aux_du_RSNO = 0, aux_du_SNVP, aux_du_SMLT;
+  u_SNOW = u_SNOW + STHR * DTP;
+  u_CC = u_CC + (p_CVICE * jmax(-TA, 0.) * STHR) * DTP;
+  if (u_CC > 0. && u_SNOWLQ > 0.) {
+    if (u_CC > u_SNOWLQ * p_LF) { u_CC = u_CC - u_SNOWLQ * p_LF; u_SNOWLQ = 0.; }
+    else { u_SNOWLQ = u_SNOWLQ - u_CC / p_LF; u_CC = 0.; }
+  }
+  double FRAC = (GRDMLT + PSNVP) * DTP / u_SNOW;
+  if (FRAC < 1) {
+    aux_du_SMLT = GRDMLT; aux_du_SNVP = PSNVP;
+    u_SNOW = u_SNOW * (1. - FRAC); u_SNOWLQ = u_SNOWLQ * (1. - FRAC); u_CC = u_CC * (1. - FRAC);
+  } else {
+    aux_du_SMLT = GRDMLT / FRAC; aux_du_SNVP = PSNVP / FRAC;
+    u_SNOW = 0.; u_SNOWLQ = 0.; u_CC = 0.;
+  }
+  if (u_SNOW == 0.) aux_du_RSNO = 0.;
+  if (u_SNOW > 0) {
+    double EQEN = DTP * (SNOEN + RTHR * jmax(TA, 0) * p_CVLQ) / p_LF;
+    if (EQEN <= 0) {
+      double NMLT = -EQEN;
+      if (NMLT < u_SNOWLQ) { u_CC = 0.; u_SNOWLQ = u_SNOWLQ - NMLT; }
+      else {
+        NMLT = NMLT - u_SNOWLQ; u_SNOWLQ = 0.;
+        u_CC = u_CC + NMLT * p_LF;
+        u_CC = jmin(u_CC, -TA * u_SNOW * p_CVICE);
+      }
+    } else {
+      if (EQEN * p_LF < u_CC || TA < 0) {
+        if (TA < 0) { u_CC = jmax(u_CC - EQEN * p_LF, -TA * u_SNOW * p_CVICE); u_SNOWLQ = 0.; }
+        else { u_CC = u_CC - EQEN * p_LF; u_SNOWLQ = 0.; }
+      } else {
+        EQEN = EQEN - u_CC / p_LF;
+        if (EQEN <= MAXLQF * u_SNOW - u_SNOWLQ) { u_SNOWLQ = u_SNOWLQ + EQEN; u_CC = 0.; }
+        else {
+          EQEN = EQEN - (MAXLQF * u_SNOW - u_SNOWLQ);
+          if (u_SNOW * (1. - MAXLQF) > EQEN) {
+            aux_du_SMLT = aux_du_SMLT + (EQEN / DTP) / (1. - MAXLQF);
+            u_SNOW = u_SNOW - EQEN / (1. - MAXLQF);
+            u_SNOWLQ = MAXLQF * u_SNOW; u_CC = 0.;
+          } else {
+            aux_du_SMLT = aux_du_SMLT + u_SNOW / DTP;
+            u_SNOW = 0.; u_SNOWLQ = 0.; u_CC = 0.;
+          }
+        }
+      }
+    }
+    if (RTHR == 0 || u_SNOW == 0) aux_du_RSNO = 0.;
+    else {
+      double RIN = RTHR * DTP;
+      if (u_CC > 0) {
+        if (u_CC > RIN * p_LF) { u_CC = u_CC - RIN * p_LF; aux_du_RSNO = RTHR; u_SNOW = u_SNOW + RIN; }
+        else {
+          u_SNOW = u_SNOW + u_CC / p_LF;
+          aux_du_RSNO = (u_CC / p_LF) / DTP;
+          u_CC = 0.;
+          RIN = RIN - aux_du_RSNO * DTP;
+          if (RIN < MAXLQF * u_SNOW / (1. - MAXLQF)) {
+            u_SNOWLQ = RIN; aux_du_RSNO = aux_du_RSNO + RIN / DTP; u_SNOW = u_SNOW + RIN;
+          } else {
+            u_SNOWLQ = MAXLQF * u_SNOW / (1. - MAXLQF);
+            aux_du_RSNO = aux_du_RSNO + u_SNOWLQ / DTP;
+            u_SNOW = u_SNOW + u_SNOWLQ;
+          }
+        }
+      } else {
+        if (u_SNOWLQ >= MAXLQF * u_SNOW) aux_du_RSNO = 0.;
+        else {
+          double ALQ = MAXLQF * u_SNOW - u_SNOWLQ;
+          if (RIN < ALQ) { aux_du_RSNO = RTHR; u_SNOWLQ = u_SNOWLQ + RIN; u_SNOW = u_SNOW + RIN; }
+          else {
+            aux_du_RSNO = (ALQ / (1. - MAXLQF)) / DTP;
+            u_SNOW = u_SNOW + aux_du_RSNO * DTP;
+            u_SNOWLQ = MAXLQF * u_SNOW;
+          }
+        }
+      }
+    }
+  }
+  CC = u_CC; SNOW = u_SNOW; SNOWLQ = u_SNOWLQ; RSNO = aux_du_RSNO; SNVP = aux_du_SNVP; SMLT = aux_du_SMLT;
+}
+
+// TBYLAYER src/module_EVP.jl:301-419.  FLAG kept as a bit mask (N <= 64).
+template <int NT>
+__device__ inline double tbylayer(int N, int J, double PTR, double DISPC, const double* ALPHA, const double* KK,
+                                  const double* RROOTI, double RXYLEM, const double* PSITI, double PSICR,
+                                  bool NOOUTF, double* ATRANI) {
+  constexpr int NMAX = NT > 0 ? NT : LWFB_MAX_LAYERS;
+  unsigned long long FLAG = 0ull;
+  double RI[NMAX];
+  for (int i = 0; i < N; i++) {
+    if (RROOTI[i] > 1E+15) FLAG |= (1ull << i);
+    else if (NOOUTF && PSITI[i] / 1000. <= PSICR) FLAG |= (1ull << i);
+    RI[i] = 0; ATRANI[i] = 0;
+  }
+  double ATR = 0.0;
+  for (;;) {
+    bool NEGFLAG = false;
+    double SUM = 0;
+    for (int i = 0; i < N; i++) {
+      if (!((FLAG >> i) & 1ull)) { RI[i] = RROOTI[i] + ALPHA[i] / KK[i]; SUM = SUM + 1.0 / RI[i]; }
+      else ATRANI[i] = 0.0;
+    }
+    if (SUM < 1E-20) { ATR = 0.; break; }
+    double RT = 1.0 / SUM;
+    double PSIT = 0;
+    for (int i = 0; i < N; i++)
+      if (!((FLAG >> i) & 1ull)) PSIT = PSIT + RT * PSITI[i] / RI[i];
+    double SUPPLY = (PSIT / 1000 - PSICR - p_RHOWG * DISPC) / (RT + RXYLEM);
+    if (J == 1) {
+      double R = (2 / p_PI) * (SUPPLY / PTR);
+      if (R <= 0) ATR = 0.;
+      else if (R < 1) ATR = PTR * (1 + R * acos(R) - sin(acos(R)));
+      else ATR = PTR;
+    } else {
+      if ((SUPPLY <= 0) || (PTR <= 0)) ATR = 0.;
+      else ATR = jmin(SUPPLY, PTR);
+    }
+    for (int i = 0; i < N; i++) {
+      if ((FLAG >> i) & 1ull) ATRANI[i] = 0;
+      else {
+        ATRANI[i] = ((PSITI[i] - PSIT) / 1000 + RT * ATR) / RI[i];
+        if (ATRANI[i] < -0.000001) NEGFLAG = true;
+      }
+    }
+    if (NOOUTF && NEGFLAG) {
+      int IDEL = -1;
+      double TRMIN = 0;
+      for (int i = 0; i < N; i++)
+        if (ATRANI[i] < TRMIN) { TRMIN = ATRANI[i]; IDEL = i; }
+      FLAG |= (1ull << IDEL);
+    } else break;
+  }
+  return ATR;
+}
+
+// day-constant part of a member's state that is not integrated by the ODE
+struct DayState {
+  double INTS, INTR, SNOW, CC, SNOWLQ;
+  double acc[LWFB_NACCUM];   // full accumulator block; the 8 integrated entries are mirrored here at day end
+};
+
+// LWFBrook90R_updateAmounts_INTS_INTR_SNOW_CC_SNOWLQ! src/func_DiffEq_definition_cb.jl:60-302 with
+// MSBSETVARS src/func_MSB_functions.jl:31-132, MSBDAYNIGHT :211-324, MSBDAYNIGHT_postprocess :338-364,
+// MSBPREINT :382-507, PLNTRES src/module_EVP.jl:144-190, CANOPY_* src/module_PET.jl:193-258,
+// ROUGH :325-366, WEATHER :429-480, SNOVAP src/module_SNO.jl:166-183, SNOENRGY :223-234, FRSS
+// src/module_PET.jl:873-888.
+template <int NT>
+__device__ __noinline__ void cb_amounts(Member<NT>& mb, const double* __restrict__ frow, double day, double* sw,
+                                        DayState& ds, double* TRANI_state, double& RWU_state) {
+  constexpr int NMAX = Member<NT>::NMAX;
+  const int N = mb.N;
+  double psim[NMAX], psiti[NMAX], kk[NMAX];
+  mb.swchek(sw);
+  for (int i = 0; i < N; i++) {
+    double W, th;
+    mb.soilvar1(i, sw[i], W, psim[i], th, kk[i]);
+    psiti[i] = psim[i] + mb.PSIG[i];
+  }
+  double u_INTS = ds.INTS, u_INTR = ds.INTR, u_SNOW = ds.SNOW, u_CC = ds.CC, u_SNOWLQ = ds.SNOWLQ;
+  double TMAX = __ldg(frow + LWFB_F_TMAX), TMIN = __ldg(frow + LWFB_F_TMIN), EA = __ldg(frow + LWFB_F_VAPPRES),
+         UW = __ldg(frow + LWFB_F_WIND), SOLRAD = __ldg(frow + LWFB_F_GLOBRAD), PREC = __ldg(frow + LWFB_F_PREC),
+         DOY = __ldg(frow + LWFB_F_DOY);
+  double DENSEF = __ldg(frow + LWFB_F_DENSEF_REL) * mb.S(LWFB_S_DENSEF_BASELINE);
+  double HEIGHT = __ldg(frow + LWFB_F_HEIGHT_REL) * mb.S(LWFB_S_HEIGHT_BASELINE);
+  double LAI = __ldg(frow + LWFB_F_LAI_REL) * mb.S(LWFB_S_MAXLAI);
+  double SAI = __ldg(frow + LWFB_F_SAI_REL) * mb.S(LWFB_S_SAI_BASELINE);
+  // relative root density of the day (HammelKennel_lateral_rootgrowth, src/func_DiffEq_definition_p.jl:606-628)
+  double RELDEN[NMAX];
+  if (mb.S(LWFB_S_RELDEN_CONST) != 0.0) {
+    for (int i = 0; i < N; i++) RELDEN[i] = mb.Lp(LWFB_L_TINI, i) > 1e19 ? 0.0 : mb.Lp(LWFB_L_RELDEN, i);
+  } else {
+    double t_y = mb.S(LWFB_S_AGE0) + day / 365, per = mb.S(LWFB_S_RGROPER), rl0 = mb.S(LWFB_S_RL0);
+    for (int i = 0; i < N; i++) {
+      double ts = mb.Lp(LWFB_L_TINI, i), fin = mb.Lp(LWFB_L_RELDEN, i);
+      if (t_y < ts) RELDEN[i] = 0.0;
+      else if (t_y <= ts + per) RELDEN[i] = rl0 * pow(fin / rl0, (t_y - ts) / per);
+      else RELDEN[i] = fin;
+    }
+  }
+  // ---- MSBSETVARS
+  double DAYLEN, I0HDAY, SLFDAY;
+  sunds(mb.S(LWFB_S_LAT), mb.S(LWFB_S_ESLOPE), DOY, mb.S(LWFB_S_L1), mb.S(LWFB_S_L2), DAYLEN, I0HDAY, SLFDAY);
+  double SAIeff = DENSEF * SAI;
+  double RTLENeff = DENSEF * mb.S(LWFB_S_MXRTLN);
+  double KPL = jmax(DENSEF * mb.S(LWFB_S_MXKPL), 1E-8);
+  double RPLANT = 1 / KPL;
+  double LAIeff0 = DENSEF * LAI;
+  double SNOFRC = snofrac(TMAX, TMIN, mb.S(LWFB_S_RSTEMP));
+  double RROOTI[NMAX], ALPHA[NMAX];
+  double RXYLEM = mb.S(LWFB_S_FXYLEM) * RPLANT;
+  {
+    double sumRD = 0;
+    for (int i = 0; i < N; i++) sumRD += RELDEN[i] * (mb.THICK[i] * (1 - mb.STONEF[i]));
+    double RTRAD = mb.S(LWFB_S_RTRAD);
+    for (int i = 0; i < N; i++) {
+      double D = mb.THICK[i] * (1 - mb.STONEF[i]);
+      double RTFRAC = RELDEN[i] * D / sumRD;
+      if (RELDEN[i] < 0.00001 || RTLENeff < 0.1) { RROOTI[i] = 1E+20; ALPHA[i] = 1E+20; }
+      else {
+        RROOTI[i] = (RPLANT - RXYLEM) / RTFRAC;
+        double RTDENI = RTFRAC * 0.001 * RTLENeff / D;
+        double DELT = p_PI * (RTRAD * RTRAD) * RTDENI;
+        double al = (1 / (8 * p_PI * RTDENI)) * (DELT - 3 - 2 * (log(DELT)) / (1 - DELT));
+        ALPHA[i] = al * 0.001 * p_RHOWG / D;
+      }
+    }
+  }
+  double SNODEP = 0.001 * u_SNOW / mb.S(LWFB_S_SNODEN);
+  double HSNO = jmax(HEIGHT - SNODEP, 0);
+  double RATIOc = HSNO / HEIGHT;
+  double HEIGHTeff = jmax(HSNO, 0.01);
+  double LAIeff = jmax(RATIOc * LAIeff0, 0.00001);
+  double Z0GS = (u_SNOW > 0) ? mb.S(LWFB_S_Z0S) : mb.S(LWFB_S_Z0G);
+  double Z0C, DISPC, Z0, DISP, ZA;
+  {
+    double HR = mb.S(LWFB_S_HR), HS = mb.S(LWFB_S_HS), CZR = mb.S(LWFB_S_CZR), CZS = mb.S(LWFB_S_CZS);
+    if (HEIGHTeff >= HR) Z0C = CZR * HEIGHTeff;
+    else if (HEIGHTeff <= HS) Z0C = CZS * HEIGHTeff;
+    else Z0C = CZS * HS + (CZR * HR - CZS * HS) * (HEIGHTeff - HS) / (HR - HS);
+    DISPC = HEIGHTeff - Z0C / 0.3;
+    if (Z0GS > Z0C) Z0GS = Z0C;
+    double RATIO = (LAIeff + SAIeff) / (mb.S(LWFB_S_LPC) + 0.035 * HEIGHTeff);
+    if (RATIO >= 1) { Z0 = Z0C; DISP = DISPC; }
+    else {
+      double e = -1 + exp(0.909 - 3.03 * Z0C / HEIGHTeff);
+      double XX = RATIO * ((e * e) * (e * e));
+      DISP = 1.1 * HEIGHTeff * log(1.0 + pow(XX, 0.25));
+      Z0 = jmin(0.3 * (HEIGHTeff - DISP), Z0GS + 0.3 * HEIGHTeff * pow(XX, 0.5));
+    }
+    ZA = HEIGHTeff + mb.S(LWFB_S_ZMINH);
+  }
+  const double SHEAT = 0.;
+  double SOLRADC, TA, TADTM, TANTM, UA, UADTM, UANTM;
+  {
+    if (SOLRAD < 0.001) SOLRADC = 0.550 * I0HDAY;
+    else if (SOLRAD > I0HDAY) SOLRADC = 0.99 * I0HDAY;
+    else SOLRADC = SOLRAD;
+    TA = (TMAX + TMIN) / 2;
+    TADTM = TA + ((TMAX - TMIN) / (2 * p_PI * DAYLEN)) * sin(p_PI * DAYLEN);
+    TANTM = TA - ((TMAX - TMIN) / (2 * p_PI * (1 - DAYLEN))) * sin(p_PI * DAYLEN);
+    double uw = UW;
+    if (uw == 0) uw = 3.0;
+    uw = jmax(uw, 0.2);
+    UA = uw * wndadj(ZA, DISP, Z0, mb.S(LWFB_S_FETCH), mb.S(LWFB_S_ZW), mb.S(LWFB_S_Z0W));
+    double WNDRAT = mb.S(LWFB_S_WNDRAT);
+    UADTM = UA / (DAYLEN + (1 - DAYLEN) * WNDRAT);
+    UANTM = WNDRAT * UADTM;
+  }
+  double LWIDTH = mb.S(LWFB_S_LWIDTH), RHOTP = mb.S(LWFB_S_RHOTP), NN = mb.S(LWFB_S_NN);
+  double TSNOW, PSNVP, ALBEDO;
+  if (u_SNOW > 0) {
+    TSNOW = -u_CC / (p_CVICE * u_SNOW);
+    double ESNOW, dummy;
+    if (TSNOW > -0.1) ESNOW = 0.61;
+    else esat(jmin(TA, TSNOW), ESNOW, dummy);
+    double RAA, RAC, RAS;
+    swgra(UA, ZA, HEIGHTeff, Z0, DISP, Z0C, DISPC, Z0GS, LWIDTH, RHOTP, NN, LAIeff, SAIeff, RAA, RAC, RAS);
+    PSNVP = (p_WTOMJ / p_LS) * (p_CPRHO / p_GAMMA) * (ESNOW - EA) / (RAA + RAS);
+    PSNVP = mb.S(LWFB_S_KSNVP) * PSNVP;
+    ALBEDO = mb.S(LWFB_S_ALBSN);
+  } else { TSNOW = 0.; PSNVP = 0.; ALBEDO = mb.S(LWFB_S_ALB); }
+  double SNOEN;
+  if (TA <= 0) SNOEN = mb.S(LWFB_S_CCFAC) * 2.0 * DAYLEN * (TA - TSNOW);
+  else
+    SNOEN = mb.S(LWFB_S_MELFAC) * 2.0 * DAYLEN * TA * exp(-mb.S(LWFB_S_SAIMLT) * SAIeff) *
+            exp(-mb.S(LWFB_S_LAIMLT) * LAIeff) * SLFDAY;
+  double RSS;
+  if (u_SNOW > 0) RSS = 0.;
+  else {
+    double RSSA = mb.S(LWFB_S_RSSA);
+    if (RSSA < 0.0001) RSS = 1e20;
+    else RSS = RSSA * pow(jmax(psim[0] / mb.Lp(LWFB_L_PSIF, 0), 1.0), mb.S(LWFB_S_RSSB));
+    if (RSS < 0.000001) mb.status = LWFB_ST_RSS;
+  }
+  // ---- MSBDAYNIGHT
+  double PTR[2], GER[2], PIR[2], GIR[2], PGER[2];
+  double ATRI0[NMAX], ATRI1[NMAX];
+  double C1 = mb.S(LWFB_S_C1), C2 = mb.S(LWFB_S_C2), C3 = mb.S(LWFB_S_C3), CR = mb.S(LWFB_S_CR);
+  double GLMIN = mb.S(LWFB_S_GLMIN), PSICR = mb.S(LWFB_S_PSICR);
+  bool NOOUTF = mb.S(LWFB_S_NOOUTF) != 0.0;
+#pragma unroll 1
+  for (int J = 1; J <= 2; J++) {
+    double SLRAD, TAJ, UAJ;
+    if (J == 1) { SLRAD = SLFDAY * SOLRADC / (p_WTOMJ * DAYLEN); TAJ = TADTM; UAJ = UADTM; }
+    else { SLRAD = 0; TAJ = TANTM; UAJ = UANTM; }
+    double cloud = SOLRADC / I0HDAY;
+    double AA, ASUBS, ES, DELTA, RAA, RAC, RAS, RSC, dmy;
+    availen(SLRAD, ALBEDO, C1, C2, C3, TAJ, EA, cloud, SHEAT, CR, LAIeff, SAIeff, AA, ASUBS);
+    esat(TAJ, ES, DELTA);
+    double VPD = ES - EA;
+    swgra(UAJ, ZA, HEIGHTeff, Z0, DISP, Z0C, DISPC, Z0GS, LWIDTH, RHOTP, NN, LAIeff, SAIeff, RAA, RAC, RAS);
+    if (J == 1)
+      RSC = srsc(SLRAD, TA, VPD, LAIeff, SAIeff, GLMIN, mb.S(LWFB_S_GLMAX), mb.S(LWFB_S_R5), mb.S(LWFB_S_CVPD),
+                 mb.S(LWFB_S_RM), CR, mb.S(LWFB_S_TL), mb.S(LWFB_S_T1), mb.S(LWFB_S_T2), mb.S(LWFB_S_TH));
+    else RSC = 1 / (GLMIN * LAIeff);
+    swpe(AA, ASUBS, VPD, RAA, RAC, RAS, RSC, RSS, DELTA, PTR[J - 1], GER[J - 1]);
+    swpe(AA, ASUBS, VPD, RAA, RAC, RAS, 0, RSS, DELTA, PIR[J - 1], GIR[J - 1]);
+    swpe(AA, ASUBS, VPD, RAA, RAC, RAS, RSC, 0, DELTA, dmy, PGER[J - 1]);
+    double* ATRI = (J == 1) ? ATRI0 : ATRI1;
+    if (PTR[J - 1] > 0.001) {
+      double ATR = tbylayer<NT>(N, J, PTR[J - 1], DISPC, ALPHA, kk, RROOTI, RXYLEM, psiti, PSICR, NOOUTF, ATRI);
+      if (ATR < PTR[J - 1]) GER[J - 1] = swge(AA, ASUBS, VPD, RAA, RAS, RSS, DELTA, ATR);
+    } else {
+      PTR[J - 1] = 0;
+      for (int i = 0; i < N; i++) ATRI[i] = 0;
+      GER[J - 1] = swge(AA, ASUBS, VPD, RAA, RAS, RSS, DELTA, 0);
+    }
+  }
+  double PTRAN = (PTR[0] * DAYLEN + PTR[1] * (1 - DAYLEN));
+  double GEVP = (GER[0] * DAYLEN + GER[1] * (1 - DAYLEN));
+  double PINT = (PIR[0] * DAYLEN + PIR[1] * (1 - DAYLEN));
+  double GIVP = (GIR[0] * DAYLEN + GIR[1] * (1 - DAYLEN));
+  for (int i = 0; i < N; i++) mb.TRANI[i] = (ATRI0[i] * DAYLEN + ATRI1[i] * (1 - DAYLEN));
+  // ---- MSBPREINT
+  const double DTP = 1.0;
+  double SFAL = SNOFRC * PREC, RFAL = PREC - SFAL;
+  int IHD = (int)__ldg(frow + LWFB_F_IHD);
+  double SINT, ISVP, RINT, IRVP;
+  inter24(SFAL, (PINT < 0 && TA > 0) ? 0.0 : PINT, LAIeff, SAIeff, mb.S(LWFB_S_FSINTL), mb.S(LWFB_S_FSINTS),
+          mb.S(LWFB_S_CINTSL), mb.S(LWFB_S_CINTSS), IHD, u_INTS, SINT, ISVP);
+  inter24(RFAL, PINT - ISVP, LAIeff, SAIeff, mb.S(LWFB_S_FRINTL), mb.S(LWFB_S_FRINTS), mb.S(LWFB_S_CINTRL),
+          mb.S(LWFB_S_CINTRS), IHD, u_INTR, RINT, IRVP);
+  double WETFR = jmin(1.0, (IRVP + ISVP) / PINT);
+  double RTHR = RFAL - RINT, STHR = SFAL - SINT;
+  PTRAN = (1.0 - WETFR) * PTRAN;
+  for (int i = 0; i < N; i++) mb.TRANI[i] = (1.0 - WETFR) * mb.TRANI[i];
+  double SLVP, RSNO, SNVP, SMLT;
+  if (u_SNOW <= 0 && STHR <= 0) SLVP = WETFR * GIVP + (1.0 - WETFR) * GEVP;
+  else SLVP = 0.0;
+  double nSNOW = u_SNOW, nCC = u_CC, nSNOWLQ = u_SNOWLQ;
+  if (u_SNOW <= 0 && STHR <= 0) { RSNO = 0.0; SNVP = 0.0; SMLT = 0.0; }
+  else {
+    if (u_SNOW <= 0 && STHR > 0) { nCC = 0.0; nSNOWLQ = 0.0; }
+    snowpack(RTHR, STHR, PSNVP, SNOEN, nCC, nSNOW, nSNOWLQ, DTP, TA, mb.S(LWFB_S_MAXLQF), mb.S(LWFB_S_GRDMLT), RSNO,
+             SNVP, SMLT);
+  }
+  double RNET = RTHR - RSNO;
+  mb.RNET = RNET; mb.SMLT = SMLT; mb.SLVP = SLVP; mb.TA = TA;
+  ds.INTS = u_INTS + (SINT - ISVP) * DTP;
+  ds.INTR = u_INTR + (RINT - IRVP) * DTP;
+  ds.SNOW = nSNOW; ds.CC = nCC; ds.SNOWLQ = nSNOWLQ;
+  double sumT = 0;
+  for (int i = 0; i < N; i++) sumT += mb.TRANI[i];
+  for (int i = 0; i < N; i++) TRANI_state[i] = DTP * mb.TRANI[i];
+  RWU_state = DTP * sumT;
+  double* a = ds.acc;
+  a[LWFB_A_CUM_D_PREC] = DTP * (RFAL + SFAL);
+  a[LWFB_A_CUM_D_RFAL] = DTP * RFAL;
+  a[LWFB_A_CUM_D_SFAL] = DTP * SFAL;
+  a[LWFB_A_CUM_D_RINT] = DTP * RINT;
+  a[LWFB_A_CUM_D_SINT] = DTP * SINT;
+  a[LWFB_A_CUM_D_RSNO] = DTP * RSNO;
+  a[LWFB_A_CUM_D_RNET] = DTP * (RFAL - RINT - RSNO);
+  a[LWFB_A_CUM_D_SMLT] = DTP * SMLT;
+  a[LWFB_A_CUM_D_EVAP] = DTP * (IRVP + ISVP + SNVP + SLVP + sumT);
+  a[LWFB_A_CUM_D_TRAN] = DTP * sumT;
+  a[LWFB_A_CUM_D_IRVP] = DTP * IRVP;
+  a[LWFB_A_CUM_D_ISVP] = DTP * ISVP;
+  a[LWFB_A_CUM_D_SLVP] = DTP * SLVP;
+  a[LWFB_A_CUM_D_SNVP] = DTP * SNVP;
+  a[LWFB_A_CUM_D_PINT] = DTP * PINT;
+  a[LWFB_A_CUM_D_PTRAN] = DTP * PTRAN;
+  a[LWFB_A_CUM_D_PSLVP] = DTP * (PGER[0] * DAYLEN + PGER[1] * (1 - DAYLEN));
+  a[LWFB_A_FLOW] = 0; a[LWFB_A_SEEP] = 0; a[LWFB_A_SRFL] = 0; a[LWFB_A_SLFL] = 0;
+  a[LWFB_A_BYFL] = 0; a[LWFB_A_DSFL] = 0; a[LWFB_A_GWFL] = 0; a[LWFB_A_VRFLN] = 0;
+  a[LWFB_A_CUM_D_RTHR] = DTP * (RFAL - RINT);
+  a[LWFB_A_CUM_D_STHR] = DTP * (SFAL - SINT);
+}
+
+// src/module_ISO.jl:36-37, :53-55
+__device__ constexpr double R18 = 2005.2e-6, R2H = 155.76e-6;
+__device__ __forceinline__ double d_to_x(double d, double R) { return 1 / (1 + 1 / (R * (d / 1000 + 1))); }
+__device__ __forceinline__ double x_to_d(double x, double R) { return (1 / (R * (1 / x - 1)) - 1) * 1000; }
+__device__ __forceinline__ double dxdt_to_dddt(double dxdt, double x, double R) {
+  return dxdt * 1 / R * 1 / ((x - 1) * (x - 1)) * 1000;
+}
+
+// isotope state carried between steps: delta of SWATI[N], GWAT, RWU, XYLEM for 18O and 2H
+template <int NT>
+struct IsoState {
+  static constexpr int NMAX = NT > 0 ? NT : LWFB_MAX_LAYERS;
+  double dS[2][NMAX];
+  double dG[2], dRWU[2], dXY[2];
+};
+
+// LWFBrook90R_updateIsotopes_GWAT_SWAT_AdvecDiff! src/func_DiffEq_definition_cb.jl:635-1250:
+// explicit Euler advection-dispersion of delta18O / delta2H after every accepted step, using the flux
+// caches of the last f call.  S1/G1: SWATI/GWAT of the new state; dprec: delta of precipitation at t.
+template <int NT>
+__device__ __forceinline__ void ade_step(const Member<NT>& mb, IsoState<NT>& is, const double* S1, double G1,
+                                         double dt, const double* dprec) {
+  constexpr int NMAX = Member<NT>::NMAX;
+  const int N = mb.N;
+  double th1[NMAX];
+#pragma unroll(NT > 0 ? NT : 1)
+  for (int i = 0; i < N; i++) {
+    double w = jmin(1.0, (mb.THSAT[i] * S1[i] / mb.SWATMAX[i] - mb.THR[i]) / (mb.THSAT[i] - mb.THR[i]));
+    th1[i] = w * (mb.THSAT[i] - mb.THR[i]) + mb.THR[i];
+  }
+  double Tk = mb.TA + 273.15;
+  double Lam = mb.S(LWFB_S_DISPERSIVITY);
+  double VXYLEM = mb.S(LWFB_S_VXYLEM);
+  double e = m_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
+  double sumT = 0;
+#pragma unroll(NT > 0 ? NT : 1)
+  for (int i = 0; i < N; i++) sumT += mb.TRANI[i];
+  double tauth[NMAX], aq[NMAX];
+#pragma unroll(NT > 0 ? NT : 1)
+  for (int i = 0; i < N; i++) {
+    tauth[i] = m_pow(th1[i], 7.0 / 3) / (mb.THSAT[i] * mb.THSAT[i]);
+    aq[i] = Lam * fabs(mb.VRFLI[i] / 1000);
+  }
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const double R = s == 0 ? R18 : R2H;
+    const double D0 = (s == 0 ? 0.96691 : 0.98331) * 1e-9 * e * 3600 * 24;
+    double* dk = is.dS[s];
+    double C[NMAX], Dd[NMAX], Ctr[NMAX], dd[NMAX];
+    double Cxy = d_to_x(is.dXY[s], R);
+    double Cinf = d_to_x(dprec[s], R);
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) {
+      Dd[i] = D0 * tauth[i] * th1[i] + aq[i];
+      C[i] = d_to_x(dk[i], R);
+      Ctr[i] = (mb.TRANI[i] < 0) ? Cxy : C[i];
+    }
+    double Cslvp = C[0];
+    const double dzpad = 1.0;
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) {
+      double diff_upp = (i == 0) ? 0.0 : ((Dd[i - 1] + Dd[i]) / 2) * ((C[i] - C[i - 1]) / mb.Lp(LWFB_L_DZ, i - 1));
+      double diff_low = (i == N - 1) ? 0.0 : ((Dd[i] + Dd[i + 1]) / 2) * ((C[i + 1] - C[i]) / mb.Lp(LWFB_L_DZ, i));
+      double qC_upp = (i == 0) ? 0.0 : mb.VRFLI[i - 1] * C[i - 1];
+      double qC_low = mb.VRFLI[i] * C[i];
+      double slv = (i == 0) ? Cslvp : 0.0;
+      double inner = -diff_upp * 1000 + diff_low * 1000 + qC_upp;
+      inner = inner - qC_low;
+      inner = inner + mb.INFLI[i] * Cinf;
+      inner = inner - mb.DSFLI[i] * C[i];
+      inner = inner - mb.SLVP * slv;
+      inner = inner - mb.TRANI[i] * Ctr[i];
+      double dC = -C[i] / S1[i] * mb.NTFLI[i] + 1 / S1[i] * inner;
+      dd[i] = dxdt_to_dddt(dC, C[i], R);
+    }
+    (void)dzpad;
+    double ddG;
+    double VN = mb.VRFLI[N - 1];
+    if ((G1 == 0) && (VN == 0)) ddG = NAN;
+    else if ((G1 == 0) && (VN > 0)) ddG = 0;
+    else {
+      double CG = d_to_x(is.dG[s], R);
+      double dCG = VN / G1 * (C[N - 1] - CG);
+      ddG = dxdt_to_dddt(dCG, CG, R);
+    }
+    is.dG[s] += dt * ddG;
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) dk[i] += dt * dd[i];
+    double sw = 0;
+#pragma unroll(NT > 0 ? NT : 1)
+    for (int i = 0; i < N; i++) sw += Ctr[i] * mb.TRANI[i];
+    double dRWU = x_to_d(sw / sumT, R);
+    is.dRWU[s] = dRWU;
+    double ddxy = (dRWU != dRWU) ? 0.0 : sumT / VXYLEM * (dRWU - is.dXY[s]);
+    is.dXY[s] += dt * ddxy;
+  }
+}
+
+// DiffEqBase.fastpow: Float32 log2 approximation + Float32 table exp2 (see oracle for provenance)
+__device__ __forceinline__ float fastlog2f(float x) {
+  const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+  uint32_t ux1i = __float_as_uint(x);
+  int32_t ex = (int32_t)((ux1i & 0x7F800000u) >> 23);
+  uint32_t greater = ux1i & 0x00400000u;
+  float signif, fexp;
+  if (greater != 0) {
+    signif = __uint_as_float((ux1i & 0x007FFFFFu) | 0x3f000000u);
+    fexp = __fsub_rn((float)ex, 126.0f);
+  } else {
+    signif = __uint_as_float((ux1i & 0x007FFFFFu) | 0x3f800000u);
+    fexp = __fsub_rn((float)ex, 127.0f);
+  }
+  signif = __fsub_rn(signif, 1.0f);
+  float num = __fmul_rn(signif, __fadd_rn(__fmul_rn(a, signif), b));
+  return __fadd_rn(fexp, __fdiv_rn(num, __fadd_rn(signif, c)));
+}
+__device__ __forceinline__ float exp2f_tbl(float x) {
+  const float tbl[16] = {0x1.6a09e667f3bcdp-1, 0x1.7a11473eb0187p-1, 0x1.8ace5422aa0dbp-1, 0x1.9c49182a3f090p-1,
+                         0x1.ae89f995ad3adp-1, 0x1.c199bdd85529cp-1, 0x1.d5818dcfba487p-1, 0x1.ea4afa2a490dap-1,
+                         0x1.0000000000000p+0, 0x1.0b5586cf9890fp+0, 0x1.172b83c7d517bp+0, 0x1.2387a6e756238p+0,
+                         0x1.306fe0a31b715p+0, 0x1.3dea64c123422p+0, 0x1.4bfdad5362a27p+0, 0x1.5ab07dd485429p+0};
+  const float redux = 786432.0f;  // 0x1.8p23 / 16
+  const float P1 = 0x1.62e430p-1f, P2 = 0x1.ebfbe0p-3f, P3 = 0x1.c6b348p-5f, P4 = 0x1.3b2c9cp-7f;
+  float t = __fadd_rn(x, redux);
+  uint32_t i0 = __float_as_uint(t);
+  i0 += 8u;
+  uint32_t k = (i0 >> 4) << 20;
+  i0 &= 15u;
+  t = __fsub_rn(t, redux);
+  float z = __fsub_rn(x, t);
+  float twopk = (float)__longlong_as_double((long long)(((unsigned long long)(0x3ff00000u + k)) << 32));
+  float tv = tbl[i0];
+  float u = __fmul_rn(tv, z);
+  // tv + u*(P1 + z*P2) + u*(z*z)*(P3 + z*P4), evaluated without contraction like the CPU code
+  float t1 = __fmul_rn(u, __fadd_rn(P1, __fmul_rn(z, P2)));
+  float t2 = __fmul_rn(__fmul_rn(u, __fmul_rn(z, z)), __fadd_rn(P3, __fmul_rn(z, P4)));
+  tv = __fadd_rn(__fadd_rn(tv, t1), t2);
+  return __fmul_rn(tv, twopk);
+}
+__device__ __forceinline__ double fastpow(double x, double y) {
+  if (x == 0.0) return 0.0;
+  return (double)exp2f_tbl(__fmul_rn((float)y, fastlog2f((float)x)));
+}
+
+__device__ __forceinline__ double eps_of(double x) {
+  x = fabs(x);
+  return __longlong_as_double(__double_as_longlong(x) + 1) - x;
+}
+
+}  // namespace lwfb

@@ -45,6 +45,8 @@ class DiscretizedSPAC:
     u0: np.ndarray            # [L]
     forcing: np.ndarray       # [n_rows, LWFB_F]
     p_soil: SoilPar
+    ILAYER: int = 0           # number of layers receiving infiltration (IDEPTH)
+    QLAYER: int = 0           # number of layers counted for source-area flow (QDEPTH)
     solution: Any = None      # filled by simulate_ (ODESolution-like object)
 
     @property
@@ -340,7 +342,8 @@ def setup(parametrizedSPAC: SPAC, *, requested_tspan=None, soil_output_depths_m=
         raise ValueError("the batched integrator needs whole-day tspan bounds (saveat = t0:1:t1)")
     return DiscretizedSPAC(parametrizedSPAC=spac, N=p_soil.NLAYER,
                            iso=bool(spac.solver_options["simulate_isotopes"]), tspan=tspan,
-                           scal=scal, lay=lay, u0=u0, forcing=forcing, p_soil=p_soil)
+                           scal=scal, lay=lay, u0=u0, forcing=forcing, p_soil=p_soil,
+                           ILAYER=IDEPTH_idx, QLAYER=QDEPTH_idx)
 
 
 _SHP_NAMES = {"ths_": "p_THSAT", "thr_": "p_thr", "Ksat_mmday": "p_KSAT", "alpha_per_m": "p_MvGalpha",
