@@ -232,6 +232,10 @@ int lwfb_scores_device(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_da
 int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, const double* gwat,
                   const double* frozen, const double* ntfli_prev, double* du);
 
+/* elementary functions of include/lwfb90_elem.h evaluated on the GPU (fn: 0 exp, 1 log, 2 pow, 3 sin,
+ * 4 cos, 5 tan, 6 asin, 7 acos, 8 DiffEqBase-style fastpow) - lets a host check device/host bit-equality */
+int lwfb_elem_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out);
+
 /* kernel launch statistics of the last lwfb_run: number of kernel launches, device ms */
 int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* device_ms);
 

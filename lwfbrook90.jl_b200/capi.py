@@ -13,7 +13,7 @@ import numpy as np
 from . import layout as lo
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblwfb90.so")
+LIB_PATH = os.environ.get("LWFB_LIB", os.path.join(_HERE, "liblwfb90.so"))
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -36,7 +36,7 @@ _lib = None
 # every symbol include/lwfb90.h declares
 SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error", "lwfb_set_sites",
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
-           "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats"]
+           "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval"]
 
 
 def lib():
@@ -64,8 +64,20 @@ def lib():
         L.lwfb_scores_device.restype = C.c_int
         L.lwfb_eval_rhs.argtypes = [vp, C.c_double, _dp, _dp, _dp, _dp, _dp]; L.lwfb_eval_rhs.restype = C.c_int
         L.lwfb_last_run_stats.argtypes = [vp, _ip, C.POINTER(C.c_float)]; L.lwfb_last_run_stats.restype = C.c_int
+        L.lwfb_elem_eval.argtypes = [C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp]; L.lwfb_elem_eval.restype = C.c_int
         _lib = L
     return _lib
+
+
+def elem_eval(fn: int, x, y=None, device: int = 0):
+    """Evaluate an elementary function of include/lwfb90_elem.h on the GPU."""
+    x = _f64(x).ravel()
+    y = np.zeros_like(x) if y is None else _f64(y).ravel()
+    out = np.empty_like(x)
+    rc = lib().lwfb_elem_eval(device, fn, x.size, _p(x), _p(y), _p(out))
+    if rc != 0:
+        raise LwfbError(f"lwfb_elem_eval failed with code {rc}")
+    return out
 
 
 def _p(a, t=_dp):

@@ -37,6 +37,15 @@ __device__ constexpr double bt1 = -0.00178001105222577714, bt2 = -0.000816434459
                             bt3 = 0.007880878010261995, bt4 = -0.1447110071732629, bt5 = 0.5823571654525552,
                             bt6 = -0.45808210592918697, bt7 = 0.015151515151515152;
 
+// a(s+1, l+1) for the stage loop (row s = stage s+1) and the stage times
+__device__ constexpr double kA[6][5] = {{0, 0, 0, 0, 0},
+                                        {a21, 0, 0, 0, 0},
+                                        {a31, a32, 0, 0, 0},
+                                        {a41, a42, a43, 0, 0},
+                                        {a51, a52, a53, a54, 0},
+                                        {a61, a62, a63, a64, a65}};
+__device__ constexpr double kC[6] = {0, c1, c2, c3, c4, 1.0};
+
 // position of the 8 integrated accumulators inside `accum`
 __device__ constexpr int kAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LWFB_A_SLFL,
                                        LWFB_A_BYFL, LWFB_A_DSFL, LWFB_A_GWFL, LWFB_A_VRFLN};
@@ -152,19 +161,23 @@ __global__ void __launch_bounds__(LWFB_BLOCK) integrate_kernel(DevData d) {
     { double dtmin_t = fmax(eps_of(t), dtmin_opt); if (dt < dtmin_t) dt = dtmin_t; }
     if (dt > tstop - t) dt = tstop - t;
     if (!(fabs(dt) > dtmin_opt)) { status = LWFB_ST_DTMIN; break; }
-    // perform_step! Tsit5; only SWATI and GWAT feed the RHS, the accumulators ride along
+    // perform_step! Tsit5; only SWATI and GWAT feed the RHS, the accumulators ride along.
+    // The stage loop is kept rolled so that the RHS is instantiated once.
     double tmp[NEMAX];
-    for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + (dt * a21) * k[0][j];
-    mb.rhs(tmp, tmp[N], t + c1 * dt, k[1]);
-    for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + dt * (a31 * k[0][j] + a32 * k[1][j]);
-    mb.rhs(tmp, tmp[N], t + c2 * dt, k[2]);
-    for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + dt * (a41 * k[0][j] + a42 * k[1][j] + a43 * k[2][j]);
-    mb.rhs(tmp, tmp[N], t + c3 * dt, k[3]);
-    for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + dt * (a51 * k[0][j] + a52 * k[1][j] + a53 * k[2][j] + a54 * k[3][j]);
-    mb.rhs(tmp, tmp[N], t + c4 * dt, k[4]);
-    for (int j = 0; j <= N; j++)
-      tmp[j] = yprev[j] + dt * (a61 * k[0][j] + a62 * k[1][j] + a63 * k[2][j] + a64 * k[3][j] + a65 * k[4][j]);
-    mb.rhs(tmp, tmp[N], t + dt, k[5]);
+#pragma unroll 1
+    for (int s = 1; s <= 5; s++) {
+      if (s == 1) {
+        const double a = dt * a21;
+        for (int j = 0; j <= N; j++) tmp[j] = yprev[j] + a * k[0][j];
+      } else {
+        for (int j = 0; j <= N; j++) {
+          double acc = kA[s][0] * k[0][j];
+          for (int l = 1; l < s; l++) acc = acc + kA[s][l] * k[l][j];
+          tmp[j] = yprev[j] + dt * acc;
+        }
+      }
+      mb.rhs(tmp, tmp[N], (s < 5) ? t + kC[s] * dt : t + dt, k[s]);
+    }
     for (int j = 0; j < NE; j++)
       y[j] = yprev[j] + dt * (a71 * k[0][j] + a72 * k[1][j] + a73 * k[2][j] + a74 * k[3][j] + a75 * k[4][j] + a76 * k[5][j]);
     mb.rhs(y, y[N], t + dt, k[6]);  // clamps the new SWATI in place
@@ -328,6 +341,27 @@ __global__ void score_kernel(DevData d, int n_obs_days, const int32_t* __restric
     res[2 * v] = rmse; res[2 * v + 1] = kge;
   }
   for (int s = 0; s < LWFB_NSCORES; s++) scores[m * LWFB_NSCORES + s] = res[s];
+}
+
+// elementary functions of include/lwfb90_elem.h evaluated on the device (host/device bit-equality tests)
+__global__ void elem_kernel(int fn, int64_t n, const double* __restrict__ x, const double* __restrict__ y,
+                            double* __restrict__ out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double r;
+  switch (fn) {
+    case 0: r = lwfb_exp(x[i]); break;
+    case 1: r = lwfb_log(x[i]); break;
+    case 2: r = lwfb_pow(x[i], y[i]); break;
+    case 3: r = lwfb_sin(x[i]); break;
+    case 4: r = lwfb_cos(x[i]); break;
+    case 5: r = lwfb_tan(x[i]); break;
+    case 6: r = lwfb_asin(x[i]); break;
+    case 7: r = lwfb_acos(x[i]); break;
+    case 8: r = fastpow(x[i], y[i]); break;
+    default: r = NAN;
+  }
+  out[i] = r;
 }
 
 // =============================================================================================
@@ -663,5 +697,32 @@ extern "C" int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, cons
   }
   CK(cudaGetLastError());
   CK(cudaMemcpy(du, d_du, n_du * sizeof(double), cudaMemcpyDeviceToHost));
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_elem_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out) {
+  if (n < 1 || !x || !y || !out) return LWFB_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return LWFB_ERR_CUDA;
+  double *dx = nullptr, *dy = nullptr, *dout = nullptr;
+  size_t b = (size_t)n * sizeof(double);
+  if (cudaMalloc(&dx, b) != cudaSuccess || cudaMalloc(&dy, b) != cudaSuccess || cudaMalloc(&dout, b) != cudaSuccess) {
+    cudaFree(dx); cudaFree(dy); cudaFree(dout);
+    return LWFB_ERR_NOMEM;
+  }
+  cudaMemcpy(dx, x, b, cudaMemcpyHostToDevice);
+  cudaMemcpy(dy, y, b, cudaMemcpyHostToDevice);
+  elem_kernel<<<(unsigned)((n + 255) / 256), 256>>>(fn, n, dx, dy, dout);
+  cudaError_t e = cudaMemcpy(out, dout, b, cudaMemcpyDeviceToHost);
+  cudaFree(dx); cudaFree(dy); cudaFree(dout);
+  return e == cudaSuccess ? LWFB_OK : LWFB_ERR_CUDA;
+}
+
+// debug/testing: raw device-layout copies of the member blocks ([field][member])
+extern "C" int lwfb_debug_get_block(lwfb_handle* h, int32_t which, double* out) {
+  if (!h || !out || h->M < 1) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  const double* src = which == 0 ? h->d_scal : (which == 1 ? h->d_lay : h->d_u0);
+  size_t n = (size_t)h->M * (which == 0 ? LWFB_PS : (which == 1 ? LWFB_PL * h->o.n_layers : h->L));
+  CK(cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost));
   return LWFB_OK;
 }

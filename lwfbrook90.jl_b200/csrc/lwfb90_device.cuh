@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "../../include/lwfb90.h"
+#include "../../include/lwfb90_elem.h"
 #include "lwfb90_math.cuh"
 
 namespace lwfb {
@@ -138,7 +139,7 @@ struct Member {
   // INFLOW! src/module_WAT.jl:313-457, ITER :459-571, VERT/KKMEAN :206-252, DSLOP! :178-198,
   // BYFLFR! :133-142, SRFLFR :144-150, GWATER :578-596.
   // du = (dSWATI[N], dGWAT, flow, seep, srfl, slfl, byfl, dsfl, gwfl, vrfln); sw is clamped in place.
-  __device__ void rhs(double* sw, double gwat, double t, double* du) {
+  __device__ __noinline__ void rhs(double* sw, double gwat, double t, double* du) {
     double W[NMAX], psim[NMAX], psiti[NMAX], theta[NMAX], kk[NMAX], BYFRAC[NMAX], V0[NMAX], BYFLI[NMAX];
     nf++;
     swchek(sw);
@@ -170,7 +171,7 @@ struct Member {
 #pragma unroll(NT > 0 ? NT : 1)
       for (int i = 0; i < N; i++) DSFLI[i] = 0;
     } else {
-      double cs = cos(DSLOPE), sn = sin(DSLOPE);
+      double cs = lwfb_cos(DSLOPE), sn = lwfb_sin(DSLOPE);
 #pragma unroll(NT > 0 ? NT : 1)
       for (int i = 0; i < N; i++) {
         double GRAD = cs * (psim[i] * 2 / (1000 * LENGTH_SLOPE)) + sn * p_RHOWG;
@@ -179,7 +180,7 @@ struct Member {
         DSFLI[i] = dd < 0 ? 0 : dd;
       }
     }
-    // first approximation of the vertical flow; log(K) is evaluated once per layer
+    // first approximation of the vertical flow; lwfb_log(K) is evaluated once per layer
     {
       double lk[NMAX];
 #pragma unroll(NT > 0 ? NT : 1)
@@ -296,21 +297,21 @@ struct Member {
 // src/module_SUN.jl:194-207
 __device__ inline double hafday(double LAT, double DEC) {
   if (fabs(LAT) >= p_PI / 2) LAT = (LAT > 0 ? 1.0 : (LAT < 0 ? -1.0 : 0.0)) * (p_PI / 2 - 0.01);
-  double ARG = -tan(DEC) * tan(LAT);
+  double ARG = -lwfb_tan(DEC) * lwfb_tan(LAT);
   if (ARG >= 1) return 0;
   else if (ARG <= -1) return p_PI;
-  return acos(ARG);
+  return lwfb_acos(ARG);
 }
 // src/module_SUN.jl:189-192
 __device__ inline double func3(double DEC, double L2, double L1, double a3, double a2) {
-  return (1.0 / (2.0 * p_PI)) * (sin(DEC) * sin(L1) * (a3 - a2) + cos(DEC) * cos(L1) * (sin(a3 + L2) - sin(a2 + L2)));
+  return (1.0 / (2.0 * p_PI)) * (lwfb_sin(DEC) * lwfb_sin(L1) * (a3 - a2) + lwfb_cos(DEC) * lwfb_cos(L1) * (lwfb_sin(a3 + L2) - lwfb_sin(a2 + L2)));
 }
 // SUNDS src/module_SUN.jl:140-187
 __device__ inline void sunds(double LAT, double SLOPE, double DOY, double L1, double L2, double& DAYLEN,
                              double& I0HDAY, double& SLFDAY) {
-  double d = 1.0 - 0.0167 * cos(0.0172 * (DOY - 3));
+  double d = 1.0 - 0.0167 * lwfb_cos(0.0172 * (DOY - 3));
   double SCD = p_SC / (d * d);
-  double DEC = asin(.39785 * sin(4.868961 + 0.017203 * DOY + 0.033446 * sin(6.224111 + 0.017202 * DOY)));
+  double DEC = lwfb_asin(.39785 * lwfb_sin(4.868961 + 0.017203 * DOY + 0.033446 * lwfb_sin(6.224111 + 0.017202 * DOY)));
   double temp = hafday(LAT, DEC);
   DAYLEN = jmax(0.0001, jmin(0.9999, temp / p_PI));
   double ang1 = temp, ang0 = -temp;
@@ -326,9 +327,9 @@ __device__ inline void sunds(double LAT, double SLOPE, double DOY, double L1, do
   else TWORIS = 0.0;  // overwrites the first branch (reference quirk)
   double I0SDAY;
   if (TWORIS == 1.0)
-    I0SDAY = p_WTOMJ * SCD * (func3(DEC, L2, L1, ang3, ang2) + func3(DEC, L2, L1, ang9, ang8)) / cos(SLOPE);
+    I0SDAY = p_WTOMJ * SCD * (func3(DEC, L2, L1, ang3, ang2) + func3(DEC, L2, L1, ang9, ang8)) / lwfb_cos(SLOPE);
   else
-    I0SDAY = p_WTOMJ * SCD * func3(DEC, L2, L1, ang3, ang2) / cos(SLOPE);
+    I0SDAY = p_WTOMJ * SCD * func3(DEC, L2, L1, ang3, ang2) / lwfb_cos(SLOPE);
   I0HDAY = p_WTOMJ * SCD * func3(DEC, 0.0, LAT, ang1, ang0);
   SLFDAY = (I0HDAY <= 0.0) ? 0.0 : I0SDAY / I0HDAY;
 }
@@ -337,7 +338,7 @@ __device__ inline void availen(double SLRAD, double ALBEDO, double C1, double C2
                                double RATIO, double SHEAT, double CR, double LAI, double SAI, double& AA,
                                double& ASUBS) {
   double SOLNET = (1 - ALBEDO) * SLRAD;
-  double EFFEM = 1.24 * pow(EA * 10 / (TA + 273.15), 1.0 / 7);
+  double EFFEM = 1.24 * lwfb_pow(EA * 10 / (TA + 273.15), 1.0 / 7);
   double NOVERN = (RATIO - C1) / C2;
   if (NOVERN > 1) NOVERN = 1;
   if (NOVERN < 0) NOVERN = 0;
@@ -346,14 +347,14 @@ __device__ inline void availen(double SLRAD, double ALBEDO, double C1, double C2
   double LNGNET = (EFFEM - 1) * CLDCOR * p_SIGMA * ((tk * tk) * (tk * tk));
   double RN = SOLNET + LNGNET;
   AA = RN - SHEAT;
-  ASUBS = RN * exp(-CR * (LAI + SAI)) - SHEAT;
+  ASUBS = RN * lwfb_exp(-CR * (LAI + SAI)) - SHEAT;
 }
 // ESAT src/module_PET.jl:488-509
 __device__ inline void esat(double TA, double& ES, double& DELTA) {
-  ES = 0.61078 * exp(17.26939 * TA / (TA + 237.3));
+  ES = 0.61078 * lwfb_exp(17.26939 * TA / (TA + 237.3));
   DELTA = 4098 * ES / ((TA + 237.3) * (TA + 237.3));
   if (TA < 0) {
-    ES = 0.61078 * exp(21.87456 * TA / (TA + 265.5));
+    ES = 0.61078 * lwfb_exp(21.87456 * TA / (TA + 265.5));
     DELTA = 5808 * ES / ((TA + 265.5) * (TA + 265.5));
   }
 }
@@ -389,14 +390,14 @@ __device__ inline double swge(double AA, double ASUBS, double VPD, double RAA, d
 __device__ inline void swgra(double UA, double ZA, double HEIGHT, double Z0, double DISP, double Z0C, double DISPC,
                              double Z0GS, double LWIDTH, double RHOTP, double NN, double LAI, double SAI, double& RAA,
                              double& RAC, double& RAS) {
-  double USTAR = p_K * UA / (log((ZA - DISP) / Z0));
+  double USTAR = p_K * UA / (lwfb_log((ZA - DISP) / Z0));
   double KH = p_K * USTAR * (HEIGHT - DISP);
-  RAS = (HEIGHT * exp(NN) / (NN * KH)) * (exp(-NN * Z0GS / HEIGHT) - exp(-NN * (Z0C + DISPC) / HEIGHT));
+  RAS = (HEIGHT * lwfb_exp(NN) / (NN * KH)) * (lwfb_exp(-NN * Z0GS / HEIGHT) - lwfb_exp(-NN * (Z0C + DISPC) / HEIGHT));
   if (RAS < 1) RAS = 1.;
-  RAA = log((ZA - DISP) / (HEIGHT - DISP)) / (p_K * USTAR) +
-        (HEIGHT / (NN * KH)) * (-1 + exp(NN * (HEIGHT - DISPC - Z0C) / HEIGHT));
-  double UH = (USTAR / p_K) * log((HEIGHT - DISP) / Z0);
-  double RB = (100 * NN) * pow(LWIDTH / UH, 0.5) / (1 - exp(-NN / 2));
+  RAA = lwfb_log((ZA - DISP) / (HEIGHT - DISP)) / (p_K * USTAR) +
+        (HEIGHT / (NN * KH)) * (-1 + lwfb_exp(NN * (HEIGHT - DISPC - Z0C) / HEIGHT));
+  double UH = (USTAR / p_K) * lwfb_log((HEIGHT - DISP) / Z0);
+  double RB = (100 * NN) * lwfb_pow(LWIDTH / UH, 0.5) / (1 - lwfb_exp(-NN / 2));
   RAC = RB / (RHOTP * LAI + p_PI * SAI);
 }
 // SRSC src/module_PET.jl:1020-1066
@@ -408,7 +409,7 @@ __device__ inline double srsc(double RAD, double TA, double VPD, double LAI, dou
   if (RAD <= 1E-10) { R0 = 0; FRINT = 0; }
   else {
     R0 = RM * R5 / (RM - 2 * R5);
-    FRINT = ((RM + R0) / (RM * CR * FS)) * log((R0 + CR * RAD) / (R0 + CR * RAD * exp(-CR * FS * LAI)));
+    FRINT = ((RM + R0) / (RM * CR * FS)) * lwfb_log((R0 + CR * RAD) / (R0 + CR * RAD * lwfb_exp(-CR * FS * LAI)));
   }
   double FD = 1 / (1 + VPD / CVPD);
   double FT;
@@ -422,8 +423,8 @@ __device__ inline double srsc(double RAD, double TA, double VPD, double LAI, dou
 }
 // WNDADJ src/module_PET.jl:543-549
 __device__ inline double wndadj(double ZA, double DISP, double Z0, double FETCH, double ZW, double Z0W) {
-  double HIBL = 0.334 * pow(FETCH, 0.875) * pow(Z0W, 0.125);
-  return log(HIBL / Z0W) * log((ZA - DISP) / Z0) / (log(HIBL / Z0) * log(ZW / Z0W));
+  double HIBL = 0.334 * lwfb_pow(FETCH, 0.875) * lwfb_pow(Z0W, 0.125);
+  return lwfb_log(HIBL / Z0W) * lwfb_log((ZA - DISP) / Z0) / (lwfb_log(HIBL / Z0) * lwfb_log(ZW / Z0W));
 }
 // INTER24 src/module_EVP.jl:632-703 (24 hourly steps, storm centred on noon)
 __device__ inline void inter24(double RFAL, double PINT, double LAI, double SAI, double FRINTL, double FRINTS,
@@ -573,7 +574,7 @@ __device__ inline double tbylayer(int N, int J, double PTR, double DISPC, const 
     if (J == 1) {
       double R = (2 / p_PI) * (SUPPLY / PTR);
       if (R <= 0) ATR = 0.;
-      else if (R < 1) ATR = PTR * (1 + R * acos(R) - sin(acos(R)));
+      else if (R < 1) ATR = PTR * (1 + R * lwfb_acos(R) - lwfb_sin(lwfb_acos(R)));
       else ATR = PTR;
     } else {
       if ((SUPPLY <= 0) || (PTR <= 0)) ATR = 0.;
@@ -609,7 +610,7 @@ struct DayState {
 // ROUGH :325-366, WEATHER :429-480, SNOVAP src/module_SNO.jl:166-183, SNOENRGY :223-234, FRSS
 // src/module_PET.jl:873-888.
 template <int NT>
-__device__ __noinline__ void cb_amounts(Member<NT>& mb, const double* __restrict__ frow, double day, double* sw,
+__device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restrict__ frow, double day, double* sw,
                                         DayState& ds, double* TRANI_state, double& RWU_state) {
   constexpr int NMAX = Member<NT>::NMAX;
   const int N = mb.N;
@@ -637,7 +638,7 @@ __device__ __noinline__ void cb_amounts(Member<NT>& mb, const double* __restrict
     for (int i = 0; i < N; i++) {
       double ts = mb.Lp(LWFB_L_TINI, i), fin = mb.Lp(LWFB_L_RELDEN, i);
       if (t_y < ts) RELDEN[i] = 0.0;
-      else if (t_y <= ts + per) RELDEN[i] = rl0 * pow(fin / rl0, (t_y - ts) / per);
+      else if (t_y <= ts + per) RELDEN[i] = rl0 * lwfb_pow(fin / rl0, (t_y - ts) / per);
       else RELDEN[i] = fin;
     }
   }
@@ -664,7 +665,7 @@ __device__ __noinline__ void cb_amounts(Member<NT>& mb, const double* __restrict
         RROOTI[i] = (RPLANT - RXYLEM) / RTFRAC;
         double RTDENI = RTFRAC * 0.001 * RTLENeff / D;
         double DELT = p_PI * (RTRAD * RTRAD) * RTDENI;
-        double al = (1 / (8 * p_PI * RTDENI)) * (DELT - 3 - 2 * (log(DELT)) / (1 - DELT));
+        double al = (1 / (8 * p_PI * RTDENI)) * (DELT - 3 - 2 * (lwfb_log(DELT)) / (1 - DELT));
         ALPHA[i] = al * 0.001 * p_RHOWG / D;
       }
     }
@@ -686,10 +687,10 @@ __device__ __noinline__ void cb_amounts(Member<NT>& mb, const double* __restrict
     double RATIO = (LAIeff + SAIeff) / (mb.S(LWFB_S_LPC) + 0.035 * HEIGHTeff);
     if (RATIO >= 1) { Z0 = Z0C; DISP = DISPC; }
     else {
-      double e = -1 + exp(0.909 - 3.03 * Z0C / HEIGHTeff);
+      double e = -1 + lwfb_exp(0.909 - 3.03 * Z0C / HEIGHTeff);
       double XX = RATIO * ((e * e) * (e * e));
-      DISP = 1.1 * HEIGHTeff * log(1.0 + pow(XX, 0.25));
-      Z0 = jmin(0.3 * (HEIGHTeff - DISP), Z0GS + 0.3 * HEIGHTeff * pow(XX, 0.5));
+      DISP = 1.1 * HEIGHTeff * lwfb_log(1.0 + lwfb_pow(XX, 0.25));
+      Z0 = jmin(0.3 * (HEIGHTeff - DISP), Z0GS + 0.3 * HEIGHTeff * lwfb_pow(XX, 0.5));
     }
     ZA = HEIGHTeff + mb.S(LWFB_S_ZMINH);
   }
@@ -700,8 +701,8 @@ __device__ __noinline__ void cb_amounts(Member<NT>& mb, const double* __restrict
     else if (SOLRAD > I0HDAY) SOLRADC = 0.99 * I0HDAY;
     else SOLRADC = SOLRAD;
     TA = (TMAX + TMIN) / 2;
-    TADTM = TA + ((TMAX - TMIN) / (2 * p_PI * DAYLEN)) * sin(p_PI * DAYLEN);
-    TANTM = TA - ((TMAX - TMIN) / (2 * p_PI * (1 - DAYLEN))) * sin(p_PI * DAYLEN);
+    TADTM = TA + ((TMAX - TMIN) / (2 * p_PI * DAYLEN)) * lwfb_sin(p_PI * DAYLEN);
+    TANTM = TA - ((TMAX - TMIN) / (2 * p_PI * (1 - DAYLEN))) * lwfb_sin(p_PI * DAYLEN);
     double uw = UW;
     if (uw == 0) uw = 3.0;
     uw = jmax(uw, 0.2);
@@ -726,14 +727,14 @@ __device__ __noinline__ void cb_amounts(Member<NT>& mb, const double* __restrict
   double SNOEN;
   if (TA <= 0) SNOEN = mb.S(LWFB_S_CCFAC) * 2.0 * DAYLEN * (TA - TSNOW);
   else
-    SNOEN = mb.S(LWFB_S_MELFAC) * 2.0 * DAYLEN * TA * exp(-mb.S(LWFB_S_SAIMLT) * SAIeff) *
-            exp(-mb.S(LWFB_S_LAIMLT) * LAIeff) * SLFDAY;
+    SNOEN = mb.S(LWFB_S_MELFAC) * 2.0 * DAYLEN * TA * lwfb_exp(-mb.S(LWFB_S_SAIMLT) * SAIeff) *
+            lwfb_exp(-mb.S(LWFB_S_LAIMLT) * LAIeff) * SLFDAY;
   double RSS;
   if (u_SNOW > 0) RSS = 0.;
   else {
     double RSSA = mb.S(LWFB_S_RSSA);
     if (RSSA < 0.0001) RSS = 1e20;
-    else RSS = RSSA * pow(jmax(psim[0] / mb.Lp(LWFB_L_PSIF, 0), 1.0), mb.S(LWFB_S_RSSB));
+    else RSS = RSSA * lwfb_pow(jmax(psim[0] / mb.Lp(LWFB_L_PSIF, 0), 1.0), mb.S(LWFB_S_RSSB));
     if (RSS < 0.000001) mb.status = LWFB_ST_RSS;
   }
   // ---- MSBDAYNIGHT

@@ -1,25 +1,19 @@
-// lwfb90_math.cuh — FP64 transcendental helpers of the hot loop.
+// lwfb90_math.cuh — transcendental call sites of the hot loop.
 //
-// The RHS spends most of its FP64 instructions in pow/exp/log (5 live pow + 2 log + 1 exp per
-// layer).  All call sites go through these wrappers so that the implementation can be specialised for
-// the argument ranges that actually occur (0 < a <= 1, moderate exponents) without touching the model
-// code.  LWFB_EXACT_MATH selects the plain CUDA math library (used for the tightest parity runs).
+// All pow/exp/log of the RHS and of the isotope step go through these wrappers.  They map onto the
+// portable elementary functions of include/lwfb90_elem.h (bit-identical on host and device), which
+// are specialised for what the model needs: one log(a) per layer is shared by the three powers of
+// the wetness a (a^(-1/m), a^(n/(n-1)), a^l), and log(K) is evaluated once per layer for both
+// interfaces that use it.
 #pragma once
-#include <math.h>
+#include "../../include/lwfb90_elem.h"
 
 namespace lwfb {
-
-#ifdef LWFB_EXACT_MATH
-__device__ __forceinline__ double m_log(double x) { return log(x); }
-__device__ __forceinline__ double m_exp(double x) { return exp(x); }
-__device__ __forceinline__ double m_pow(double x, double y) { return pow(x, y); }
-// a^e where la = log(a) is already known
-__device__ __forceinline__ double m_exp_of_scaled_log(double e, double la, double a) { (void)la; return pow(a, e); }
-#else
-__device__ __forceinline__ double m_log(double x) { return log(x); }
-__device__ __forceinline__ double m_exp(double x) { return exp(x); }
-__device__ __forceinline__ double m_pow(double x, double y) { return pow(x, y); }
-__device__ __forceinline__ double m_exp_of_scaled_log(double e, double la, double a) { (void)la; return pow(a, e); }
-#endif
-
+__device__ __forceinline__ double m_log(double x) { return lwfb_log(x); }
+__device__ __forceinline__ double m_exp(double x) { return lwfb_exp(x); }
+__device__ __forceinline__ double m_pow(double x, double y) { return lwfb_pow(x, y); }
+// a^e where la = m_log(a) is already known
+__device__ __forceinline__ double m_exp_of_scaled_log(double e, double la, double a) {
+  return lwfb_pow_from_log(a, la, e);
+}
 }  // namespace lwfb

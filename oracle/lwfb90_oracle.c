@@ -19,11 +19,27 @@
  * reference root.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../include/lwfb90.h"
+
+/* Build mode B (-DLWFB_ORACLE_ELEM): identical code, but the elementary functions are the portable
+ * routines the CUDA kernels use (include/lwfb90_elem.h), so that GPU results can be compared
+ * BIT-EXACTLY.  Mode A (default) uses the host libm and is the one pinned against the goldens. */
+#ifdef LWFB_ORACLE_ELEM
+#include "../include/lwfb90_elem.h"
+#define exp lwfb_exp
+#define log lwfb_log
+#define pow lwfb_pow
+#define sin lwfb_sin
+#define cos lwfb_cos
+#define tan lwfb_tan
+#define asin lwfb_asin
+#define acos lwfb_acos
+#endif
 
 #define MAXN 512
 
@@ -310,7 +326,7 @@ static void availen(double SLRAD, double ALBEDO, double C1, double C2, double C3
   if (NOVERN < 0) NOVERN = 0;
   double CLDCOR = C3 + (1 - C3) * NOVERN;
   double tk = TA + 273.15;
-  double LNGNET = (EFFEM - 1) * CLDCOR * p_SIGMA * pow(tk, 4);
+  double LNGNET = (EFFEM - 1) * CLDCOR * p_SIGMA * ((tk * tk) * (tk * tk)); /* x^4 by squaring */
   double RN = SOLNET + LNGNET;
   *AA = RN - SHEAT;
   *ASUBS = RN * exp(-CR * (LAI + SAI)) - SHEAT;
@@ -696,7 +712,7 @@ static void cb_amounts(model_t* m, double* u, const sidx_t* ix, int day) {
     if (RATIO >= 1) { Z0 = Z0C; DISP = DISPC; }
     else {
       double e = -1 + exp(0.909 - 3.03 * Z0C / HEIGHTeff);
-      double XX = RATIO * pow(e, 4);
+      double XX = RATIO * ((e * e) * (e * e));
       DISP = 1.1 * HEIGHTeff * log(1.0 + pow(XX, 0.25));
       Z0 = jmin(0.3 * (HEIGHTeff - DISP), Z0GS + 0.3 * HEIGHTeff * pow(XX, 0.5));
     }
@@ -1295,3 +1311,17 @@ double lwfb_oracle_kkmean(double K1, double K2, double T1, double T2) {
 void lwfb_oracle_esat(double TA, double* ES, double* DELTA) { esat(TA, ES, DELTA); }
 double lwfb_oracle_pm(double AA, double VPD, double DELTA, double RA, double RC) { return pm(AA, VPD, DELTA, RA, RC); }
 double lwfb_oracle_fastpow(double x, double y) { return fastpow(x, y); }
+/* elementary functions as compiled into this build (libm in mode A, lwfb90_elem.h in mode B) */
+double lwfb_oracle_elem(int fn, double x, double y) {
+  switch (fn) {
+    case 0: return exp(x);
+    case 1: return log(x);
+    case 2: return pow(x, y);
+    case 3: return sin(x);
+    case 4: return cos(x);
+    case 5: return tan(x);
+    case 6: return asin(x);
+    case 7: return acos(x);
+    default: return NAN;
+  }
+}

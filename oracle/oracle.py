@@ -13,7 +13,19 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liblwfb90_oracle.so")
+_SO_ELEM = os.path.join(_HERE, "_build", "liblwfb90_oracle_elem.so")
 _lib = None
+_libs = {}
+_mode = "libm"
+
+
+def use(mode: str):
+    """Select the oracle build: "libm" (mode A, independent, pinned to goldens) or "elem"
+    (mode B, elementary functions of include/lwfb90_elem.h = bit-exact replay of the GPU)."""
+    global _mode, _lib
+    assert mode in ("libm", "elem")
+    _mode = mode
+    _lib = _libs.get(mode)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -21,10 +33,11 @@ _lp = C.POINTER(C.c_int64)
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "lwfb90_oracle.c")
-    hdr = os.path.join(os.path.dirname(_HERE), "include", "lwfb90.h")
-    if (force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src)
-            or os.path.getmtime(_SO) < os.path.getmtime(hdr)):
+    src = [os.path.join(_HERE, "lwfb90_oracle.c"), os.path.join(os.path.dirname(_HERE), "include", "lwfb90.h"),
+           os.path.join(os.path.dirname(_HERE), "include", "lwfb90_elem.h")]
+    stale = any(not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in src)
+                for so in (_SO, _SO_ELEM))
+    if force or stale:
         subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
     return _SO
 
@@ -33,7 +46,8 @@ def lib():
     global _lib
     if _lib is None:
         build()
-        _lib = C.CDLL(_SO)
+        _lib = C.CDLL(_SO if _mode == "libm" else _SO_ELEM)
+        _libs[_mode] = _lib
         _lib.lwfb_oracle_run.restype = C.c_int
         _lib.lwfb_oracle_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp,
                                          C.c_int64, _ip, _dp, _dp, _dp, C.c_double, C.c_double,
@@ -52,6 +66,8 @@ def lib():
         _lib.lwfb_oracle_esat.argtypes = [C.c_double, _dp, _dp]
         _lib.lwfb_oracle_fastpow.restype = C.c_double
         _lib.lwfb_oracle_fastpow.argtypes = [C.c_double, C.c_double]
+        _lib.lwfb_oracle_elem.restype = C.c_double
+        _lib.lwfb_oracle_elem.argtypes = [C.c_int, C.c_double, C.c_double]
     return _lib
 
 
@@ -115,3 +131,13 @@ def eval_rhs(N, scal, lay, t, swati, gwat, frozen, ntfli_prev):
                                _p(np.ascontiguousarray(frozen, dtype=np.float64)),
                                _p(np.ascontiguousarray(ntfli_prev, dtype=np.float64)), _p(du))
     return du, sw
+
+
+def elem(fn: int, x, y=None):
+    """Elementary function as compiled into the selected oracle build."""
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    y = np.zeros_like(x) if y is None else np.ascontiguousarray(y, dtype=np.float64).ravel()
+    L = lib()
+    if fn == 8:
+        return np.array([L.lwfb_oracle_fastpow(a, b) for a, b in zip(x, y)])
+    return np.array([L.lwfb_oracle_elem(fn, a, b) for a, b in zip(x, y)])

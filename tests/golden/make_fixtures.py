@@ -54,6 +54,16 @@ def main():
         for f in sorted(os.listdir(os.path.join(REF, rel))):
             if f.endswith(".csv") and "oldFormat" not in f:
                 shutil.copy(os.path.join(REF, rel, f), os.path.join(dst, f))
+    # examples/isoBEA2016-reset-FALSE-input/*_param.csv is in a pre-0.9 format: it lacks 7 keys that
+    # read_path_param (src/func_read_inputData.jl:978-1059) requires, so the reference itself cannot load
+    # it.  The fixture takes the missing rows from the BEA2016-reset-FALSE param file (same site, same year).
+    iso_p = os.path.join(HERE, "inputs", "isoBEA2016-reset-FALSE-input", "isoBEA2016-reset-FALSE_param.csv")
+    bea_p = os.path.join(HERE, "inputs", "BEA2016-reset-FALSE-input", "BEA2016-reset-FALSE_param.csv")
+    have = {l.split(",")[0].strip() for l in open(iso_p)}
+    extra = [l for l in open(bea_p) if l.split(",")[0].strip() not in have and not l.startswith("###")]
+    lines = open(iso_p).read().rstrip("\n").split("\n")
+    with open(iso_p, "w") as fh:
+        fh.write("\n".join(lines) + "\n" + "### rows added from BEA2016-reset-FALSE_param.csv (see make_fixtures.py),NA\n" + "".join(extra))
     os.makedirs(os.path.join(HERE, "outputs"), exist_ok=True)
     for rel in GOLDEN_OUTPUTS:
         shutil.copy(os.path.join(REF, rel), os.path.join(HERE, "outputs", os.path.basename(rel)))
