@@ -236,6 +236,13 @@ int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, const double* g
  * 4 cos, 5 tan, 6 asin, 7 acos, 8 DiffEqBase-style fastpow) - lets a host check device/host bit-equality */
 int lwfb_elem_eval(int32_t device, int32_t fn, int64_t n, const double* x, const double* y, double* out);
 
+/* measured FP64 (DFMA) peak of the device in TFLOP/s: the roofline denominator of this path (the
+ * driver-written MEASURED_PEAKS.json has HBM and bf16 tensor figures only) */
+int lwfb_fp64_peak(int32_t device, int32_t reps, double* tflops);
+
+/* testing aid: raw device-layout copy ([field][member]) of the member blocks; which = 0 scal, 1 lay, 2 u0 */
+int lwfb_debug_get_block(lwfb_handle* h, int32_t which, double* out);
+
 /* kernel launch statistics of the last lwfb_run: number of kernel launches, device ms */
 int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* device_ms);
 

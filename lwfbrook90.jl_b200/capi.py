@@ -36,7 +36,8 @@ _lib = None
 # every symbol include/lwfb90.h declares
 SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error", "lwfb_set_sites",
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
-           "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval"]
+           "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
+           "lwfb_fp64_peak", "lwfb_debug_get_block"]
 
 
 def lib():
@@ -67,6 +68,18 @@ def lib():
         L.lwfb_elem_eval.argtypes = [C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp]; L.lwfb_elem_eval.restype = C.c_int
         _lib = L
     return _lib
+
+
+def fp64_peak(device: int = 0, reps: int = 5) -> float:
+    """Measured DFMA peak of the device in TFLOP/s."""
+    out = C.c_double()
+    L = lib()
+    L.lwfb_fp64_peak.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    L.lwfb_fp64_peak.restype = C.c_int
+    rc = L.lwfb_fp64_peak(device, reps, C.byref(out))
+    if rc != 0:
+        raise LwfbError(f"lwfb_fp64_peak failed with code {rc}")
+    return float(out.value)
 
 
 def elem_eval(fn: int, x, y=None, device: int = 0):

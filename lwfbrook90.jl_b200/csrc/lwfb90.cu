@@ -364,6 +364,21 @@ __global__ void elem_kernel(int fn, int64_t n, const double* __restrict__ x, con
   out[i] = r;
 }
 
+// FP64 pipe peak: 16 independent DFMA chains per thread, no memory traffic
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) x[i] = (double)(threadIdx.x + i) * 1e-3;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = fma(x[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += x[i];
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // =============================================================================================
 // host side
 // =============================================================================================
@@ -725,4 +740,32 @@ extern "C" int lwfb_debug_get_block(lwfb_handle* h, int32_t which, double* out) 
   size_t n = (size_t)h->M * (which == 0 ? LWFB_PS : (which == 1 ? LWFB_PL * h->o.n_layers : h->L));
   CK(cudaMemcpy(out, src, n * sizeof(double), cudaMemcpyDeviceToHost));
   return LWFB_OK;
+}
+
+// measured FP64 (DFMA) peak of the device in TFLOP/s (2 flop per DFMA); best of `reps` launches
+extern "C" int lwfb_fp64_peak(int32_t device, int32_t reps, double* tflops) {
+  if (!tflops) return LWFB_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return LWFB_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LWFB_ERR_CUDA;
+  double* d_out = nullptr;
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+  if (cudaMalloc(&d_out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return LWFB_ERR_NOMEM;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int r = 0; r < reps + 1; r++) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<blocks, threads>>>(d_out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    double tf = 2.0 * 16.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (r > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = best;
+  return cudaGetLastError() == cudaSuccess ? LWFB_OK : LWFB_ERR_CUDA;
 }

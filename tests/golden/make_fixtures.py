@@ -21,6 +21,8 @@ INPUT_SETS = {
     "isoBEA2016-reset-FALSE-input": "examples/isoBEA2016-reset-FALSE-input",
     "infiltrationSaturationINFEXP1": "examples/infiltrationSaturationINFEXP1",
 }
+# only the files of one prefix are taken from this directory (root-model unit tests, test/01-unit-tests.jl:384-421)
+HAMMEL = ("test/test-assets/Hammel-2001/input-files-ISO", "Hammel_loam-NLayer-27-RESET=FALSE")
 GOLDEN_OUTPUTS = [
     "examples/DAV2020-full_u_sol_referenceu_mm.csv",
     "examples/DAV2020-full_u_sol_referenceu_δ.csv",
@@ -54,6 +56,11 @@ def main():
         for f in sorted(os.listdir(os.path.join(REF, rel))):
             if f.endswith(".csv") and "oldFormat" not in f:
                 shutil.copy(os.path.join(REF, rel, f), os.path.join(dst, f))
+    dst = os.path.join(HERE, "inputs", "Hammel-2001")
+    os.makedirs(dst, exist_ok=True)
+    for f in sorted(os.listdir(os.path.join(REF, HAMMEL[0]))):
+        if f.startswith(HAMMEL[1]) and f.endswith(".csv"):
+            shutil.copy(os.path.join(REF, HAMMEL[0], f), os.path.join(dst, f))
     # examples/isoBEA2016-reset-FALSE-input/*_param.csv is in a pre-0.9 format: it lacks 7 keys that
     # read_path_param (src/func_read_inputData.jl:978-1059) requires, so the reference itself cannot load
     # it.  The fixture takes the missing rows from the BEA2016-reset-FALSE param file (same site, same year).

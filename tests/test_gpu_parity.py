@@ -1,0 +1,319 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/lwfb90.h), against the CPU
+oracle on the same inputs.
+
+Two comparisons:
+  * oracle mode B (elementary functions of include/lwfb90_elem.h): the GPU record must be BIT-IDENTICAL
+    for every member, every day, every state entry, including status and step counters;
+  * oracle mode A (host libm, the build that is pinned to the reference's goldens): within the
+    north-star tolerance (storage / theta 1e-6 relative, delta 1e-4 permil) wherever the reference
+    algorithm itself is reproducible, which is established per member by re-running the oracle with a
+    1e-15 relative perturbation of KSAT (see DESIGN.md "Parity").
+"""
+import numpy as np
+import pytest
+
+from conftest import inputs, outputs, read_table
+
+import oracle as orc
+from lwfbrook90.jl_b200 import api, capi, ensemble as en, layout as lo
+
+pytestmark = pytest.mark.gpu
+
+TOL_STORAGE = 1e-6      # relative, daily soil-water storage and layer theta (BASELINE.json north_star)
+TOL_DELTA = 1e-4        # permil, delta18O / delta2H
+
+
+def gpu_run(ens, n_days=None, members=None, record=True):
+    sub = ens if members is None else ens.subset(members)
+    nd = ens.n_days if n_days is None else n_days
+    h = capi.Handle(ens.N, ens.iso, ens.t0_day, nd, record_daily=record)
+    h.set_sites(ens.forcing)
+    h.set_members(sub.site_of_member, sub.scal, sub.lay, sub.u0)
+    h.run()
+    return h, sub, nd
+
+
+def oracle_run(sub, nd, mode, lay=None):
+    orc.use(mode)
+    return orc.run(sub.N, sub.iso, sub.t0_day, nd, sub.forcing, sub.site_of_member, sub.scal,
+                   sub.lay if lay is None else lay, sub.u0, n_threads=8)
+
+
+def assert_bit_identical(h, sub, nd):
+    gpu = h.get_daily()
+    st, cnt = h.get_status()
+    ref, st_o, cnt_o = oracle_run(sub, nd, "elem")
+    assert np.array_equal(st, st_o)
+    assert np.array_equal(cnt, cnt_o), "accepted / rejected / RHS-evaluation counters differ"
+    same = (gpu == ref) | (np.isnan(gpu) & np.isnan(ref))
+    assert same.all(), f"{(~same).any(axis=(1, 2)).sum()} of {sub.M} members differ from the oracle"
+    return gpu
+
+
+# ------------------------------------------------------------------------------ building blocks
+def test_elementary_functions_bit_equal_on_device():
+    rng = np.random.default_rng(0)
+    orc.use("elem")
+    n = 4000
+    cases = {0: rng.uniform(-700, 700, n), 1: 10 ** rng.uniform(-300, 300, n), 3: rng.uniform(-50, 50, n),
+             4: rng.uniform(-50, 50, n), 5: rng.uniform(-1.5, 1.5, n), 6: rng.uniform(-1, 1, n), 7: rng.uniform(-1, 1, n)}
+    for fn, x in cases.items():
+        g, c = capi.elem_eval(fn, x), orc.elem(fn, x)
+        assert np.array_equal(g, c, equal_nan=True), fn
+    x, y = 10 ** rng.uniform(-6, 0, n), rng.uniform(-25, 25, n)
+    assert np.array_equal(capi.elem_eval(2, x, y), orc.elem(2, x, y))
+    # DiffEqBase-style fastpow of the step-size controller (Float32 arithmetic)
+    x, y = 10 ** rng.uniform(-8, 3, n), np.where(rng.random(n) < 0.5, 0.14, 0.08)
+    assert np.array_equal(capi.elem_eval(8, x, y), orc.elem(8, x, y))
+    # edge cases: 0^y, x^0, log 0, exp of huge arguments, acos at the ends
+    assert capi.elem_eval(2, [0.0, 0.0, 3.0, 0.0], [0.5, 0.0, 0.0, -1.0]).tolist() == [0.0, 1.0, 1.0, np.inf]
+    assert capi.elem_eval(1, [0.0])[0] == -np.inf and capi.elem_eval(0, [-1e9, 1e9]).tolist() == [0.0, np.inf]
+    assert np.isnan(capi.elem_eval(1, [-1.0])[0]) and capi.elem_eval(7, [1.0])[0] == 0.0
+
+
+@pytest.mark.parametrize("which", ["dav_full", "bea", "infexp1"])
+def test_rhs_bit_identical(which, request):
+    """One evaluation of f(u,p,t) (lwfb_eval_rhs) for perturbed states, incl. clamped and saturated layers."""
+    sim = request.getfixturevalue(which)
+    ens = en.make_ensemble(sim, 64) if which != "infexp1" else en.batched_setup(sim, params={"DRAIN": np.linspace(0.1, 1, 64)})
+    N, M = ens.N, ens.M
+    rng = np.random.default_rng(5)
+    ix = lo.StateIndex(N, ens.iso)
+    smax = ens.lay[:, lo.L.SWATMAX]
+    swati = ens.u0[:, ix.SWATI_mm] * rng.uniform(0.5, 1.3, (M, N))
+    swati[::7] = smax[::7] * 1.01            # above saturation: SWCHEK clamps
+    swati[3::11, 0] = -0.1                   # negative storage: clamped to 0
+    gwat = rng.uniform(0, 5, M); gwat[::5] = 0.0
+    frozen = np.concatenate([rng.uniform(0, 30, (M, 1)), rng.uniform(0, 2, (M, 1)), rng.uniform(0, 1, (M, 1)),
+                             rng.uniform(-0.01, 0.5, (M, N))], axis=1)
+    ntfli = rng.normal(0, 20, (M, N)); ntfli[::9] = np.nan      # first call of a fresh problem sees NaN
+    h = capi.Handle(N, ens.iso, 0, 1)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    orc.use("elem")
+    for t in (0.0, 0.3712, 10.999999):
+        du = h.eval_rhs(t, swati, gwat, frozen, ntfli)
+        for m in range(M):
+            ref, _ = orc.eval_rhs(N, ens.scal[m], ens.lay[m], t, swati[m], gwat[m], frozen[m], ntfli[m])
+            assert np.array_equal(du[m], ref, equal_nan=True), (t, m)
+    h.close()
+
+
+# ------------------------------------------------------------------------------ full runs, bit-exact
+def test_dav2020_full_single_member_vs_golden_G1(lw):
+    """Member 0 = the reference's run_example(): GPU against the reference's own golden CSVs."""
+    sim = lw.setup(lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True), requested_tspan=(0, 300))
+    api.simulate_(sim)
+    sol, ix = sim.solution, sim.solution.ix
+    assert sol.retcode == "Success" and 24 * 300 <= sol.destats.naccept < 26 * 300
+    h, a = read_table(outputs("DAV2020-full_u_sol_referenceu_belowground.csv"))
+    days = a[:, 0]
+    sw = np.array([sol.record_at(d)[ix.SWATI_mm] for d in days])
+    assert np.max(np.abs(sw - a[:, 1:6]) / a[:, 1:6]) < TOL_STORAGE
+    t = api.get_soil_(["θ", "ψ", "δ18O", "δ2H"], sim, days_to_read_out_d=days)
+    th = np.stack([t[f"θ_Lay{i}"] for i in range(1, 6)], axis=1)
+    assert np.max(np.abs(th - a[:, 16:21]) / a[:, 16:21]) < TOL_STORAGE
+    d18 = np.stack([t[f"δ18O_Lay{i}"] for i in range(1, 6)], axis=1)
+    d2 = np.stack([t[f"δ2H_Lay{i}"] for i in range(1, 6)], axis=1)
+    assert np.max(np.abs(d18 - a[:, 6:11])) < TOL_DELTA and np.max(np.abs(d2 - a[:, 11:16])) < TOL_DELTA
+    h, a = read_table(outputs("DAV2020-full_u_sol_referenceu_δ.csv"))
+    d = api.get_delta(sim, days_to_read_out_d=a[:, 0])
+    for j, name in enumerate(h[1:], start=1):
+        assert np.array_equal(np.isnan(d[name]), np.isnan(a[:, j])), name
+        assert np.nanmax(np.abs(d[name] - a[:, j])) < TOL_DELTA, name
+    h, a = read_table(outputs("DAV2020-full_u_sol_referenceu_mm.csv"))
+    am = api.get_amounts(sim, days_to_read_out_d=a[:, 0])
+    for j, name in zip(range(1, 7), ["GWAT_mm", "INTS_mm", "INTR_mm", "SNOW_mm", "CC_MJm2", "SNOWLQ_mm"]):
+        assert np.max(np.abs(am[name] - a[:, j])) <= 1e-9 + TOL_STORAGE * np.max(np.abs(a[:, j]))
+
+
+@pytest.mark.parametrize("which,M,nd", [("dav_full", 96, None), ("bea", 48, None), ("isobea", 48, None)])
+def test_ensemble_bit_identical_to_oracle(which, M, nd, request):
+    sim = request.getfixturevalue(which)
+    ens = en.make_ensemble(sim, M)
+    h, sub, nd = gpu_run(ens, nd)
+    gpu = assert_bit_identical(h, sub, nd)
+    # get_final returns the last record
+    assert np.array_equal(h.get_final(), gpu[:, -1], equal_nan=True)
+    h.close()
+
+
+def test_generic_layer_count_kernels_bit_identical(lw, infexp1):
+    """N = 42 (INFEXP1, saturation/bypass regime incl.) and N = 13 (DAV2020-bare-minimum) go through the
+    runtime-N kernel."""
+    e = en.batched_setup(infexp1, params={"DRAIN": np.array([1.0, 0.6, 0.3])})
+    h, sub, nd = gpu_run(e, 260)
+    assert_bit_identical(h, sub, nd)
+    h.close()
+    m = lw.loadSPAC(inputs("DAV2020-bare-minimum"), "DAV2020-minimal", simulate_isotopes=False, Δz_thickness_m=[0.1] * 11,
+                    root_distribution=dict(beta=0.77, z_rootMax_m=-0.5), IC_soil=dict(PSIM_init_kPa=-7.0),
+                    canopy_evolution=dict(DENSEF_rel=100, HEIGHT_rel=100, SAI_rel=100,
+                                          LAI_rel=dict(DOY_Bstart=120, Bduration=21, DOY_Cstart=270, Cduration=60,
+                                                       LAI_perc_BtoC=95, LAI_perc_CtoB=70)),
+                    storm_durations_h=[5.44] * 12,
+                    IC_scalar=dict(amount=dict(u_GWAT_init_mm=1., u_INTS_init_mm=13.7, u_INTR_init_mm=0., u_SNOW_init_mm=22.222,
+                                               u_CC_init_MJ_per_m2=0.101010, u_SNOWLQ_init_mm=0.),
+                                   d18O=dict(u_GWAT_init_permil=-11.111, u_INTS_init_permil=-12.222, u_INTR_init_permil=-13.333, u_SNOW_init_permil=-14.444),
+                                   d2H=dict(u_GWAT_init_permil=-95.111, u_INTS_init_permil=-95.222, u_INTR_init_permil=-95.333, u_SNOW_init_permil=-95.444)))
+    s = lw.setup(m)
+    assert s.N == 13 and not s.iso
+    e = en.make_ensemble(s, 8)
+    h, sub, nd = gpu_run(e)
+    assert_bit_identical(h, sub, nd)
+    h.close()
+
+
+def test_nonzero_start_day_and_short_span(dav_full):
+    """tspan not starting at 0 (initial conditions applied at t0, forcing taken from the right rows)."""
+    e = en.make_ensemble(dav_full, 16)
+    e.t0_day, e.n_days = 120, 45
+    h, sub, nd = gpu_run(e)
+    assert_bit_identical(h, sub, nd)
+    h.close()
+
+
+# ------------------------------------------------------------------------------ against the libm oracle
+def test_tolerance_vs_libm_oracle_with_conditioning(dav_full):
+    """GPU vs the golden-pinned oracle build.  A member counts as reproducible if the oracle itself
+    stays within tolerance under a 1e-15 relative perturbation of KSAT; every reproducible member must
+    meet the north-star tolerance, and the GPU deviation may never exceed the oracle's own spread by
+    more than a small factor."""
+    ens = en.make_ensemble(dav_full, 64)
+    h, sub, nd = gpu_run(ens)
+    gpu = h.get_daily()
+    h.close()
+    ref = oracle_run(sub, nd, "libm")[0]
+    lay_p = sub.lay.copy(); lay_p[:, lo.L.KSAT] *= (1 + 1e-15)
+    ref_p = oracle_run(sub, nd, "libm", lay=lay_p)[0]
+    ix = lo.StateIndex(sub.N, True)
+
+    def errs(a, b):
+        sw = np.abs(a[:, :, ix.SWATI_mm] - b[:, :, ix.SWATI_mm]) / np.abs(b[:, :, ix.SWATI_mm])
+        st = np.abs(a[:, :, ix.acc("StorageSWAT")] - b[:, :, ix.acc("StorageSWAT")]) / b[:, :, ix.acc("StorageSWAT")]
+        d = np.maximum(np.nan_to_num(np.abs(a[:, :, ix.SWATI_d18O] - b[:, :, ix.SWATI_d18O])),
+                       np.nan_to_num(np.abs(a[:, :, ix.SWATI_d2H] - b[:, :, ix.SWATI_d2H])))
+        return np.maximum(sw.max(axis=(1, 2)), st.max(axis=1)), d.max(axis=(1, 2))
+    e_sw, e_d = errs(gpu, ref)
+    s_sw, s_d = errs(ref_p, ref)
+    reproducible = (s_sw < TOL_STORAGE / 10) & (s_d < TOL_DELTA / 10)
+    assert reproducible[0], "the unmodified site definition must be well conditioned"
+    assert reproducible.mean() > 0.5
+    assert np.all(e_sw[reproducible] < TOL_STORAGE) and np.all(e_d[reproducible] < TOL_DELTA)
+    assert np.median(e_sw) < 1e-9
+    # chaotic members: the GPU is no further from the oracle than the oracle is from its perturbed self (x100)
+    assert np.all(e_sw[~reproducible] < 100 * np.maximum(s_sw[~reproducible], TOL_STORAGE))
+
+
+# ------------------------------------------------------------------------------ size-independent properties
+def test_properties_at_scale(dav_full):
+    """20k members (beyond what the oracle finishes in seconds): determinism, permutation invariance,
+    sub-sampled bit-exact check, physical invariants."""
+    M = 20000
+    ens = en.make_ensemble(dav_full, M)
+    nd = 60
+    h, _, _ = gpu_run(ens, nd)
+    st, cnt = h.get_status()
+    assert np.all(st == 0)
+    fin = h.get_final()
+    ix = lo.StateIndex(ens.N, True)
+    # run again: bitwise deterministic
+    h.run()
+    assert np.array_equal(h.get_final(), fin, equal_nan=True)
+    # permutation of members does not change any member's result (no cross-member coupling)
+    perm = np.random.default_rng(1).permutation(M)
+    h2, _, _ = gpu_run(ens, nd, members=perm)
+    assert np.array_equal(h2.get_final(), fin[perm], equal_nan=True)
+    h2.close()
+    # physical invariants of the final state
+    sw = fin[:, ix.SWATI_mm]
+    assert np.all(sw >= 0) and np.all(sw <= ens.lay[:, lo.L.SWATMAX])
+    assert np.all(fin[:, ix.GWAT_mm] >= 0) and np.all(fin[:, ix.SNOW_mm] >= 0) and np.all(fin[:, ix.INTS_mm] >= -1e-12)
+    assert np.all(fin[:, ix.aux_theta] == 0) and np.all(fin[:, ix.XYLEM_mm] == 5.0)
+    assert np.all(cnt[:, 0] >= 24 * nd) and np.all(cnt[:, 2] >= 6 * cnt[:, 0])
+    # daily water balance of the last day closes unless SWCHEK clamped
+    assert np.median(np.abs(fin[:, ix.acc("BALERD_SWAT")])) < 1e-9
+    # a random sub-sample is bit-identical to the oracle
+    pick = np.sort(np.random.default_rng(2).choice(M, 24, replace=False))
+    sub = ens.subset(pick)
+    ref, st_o, cnt_o = oracle_run(sub, nd, "elem")
+    assert np.array_equal(np.stack([h.get_daily(int(i), 1)[0] for i in pick]), ref, equal_nan=True)
+    assert np.array_equal(cnt[pick], cnt_o)
+    h.close()
+
+
+def test_bad_member_does_not_disturb_the_batch(dav_full):
+    ens = en.make_ensemble(dav_full, 40)
+    bad = ens.subset(np.arange(40))
+    ix = lo.StateIndex(ens.N, True)
+    bad.u0[5, ix.SWATI_mm.start + 1] = np.nan          # NaN state -> unstable_check
+    bad.lay[9, lo.L.KSAT] = np.nan                      # NaN parameter
+    h, _, nd = gpu_run(bad, 20)
+    st, cnt = h.get_status()
+    assert st[5] == 1 and st[9] == 1 and np.all(np.delete(st, [5, 9]) == 0)
+    g = h.get_daily()
+    h.close()
+    h0, _, _ = gpu_run(ens, 20)
+    g0 = h0.get_daily()
+    h0.close()
+    keep = np.delete(np.arange(40), [5, 9])
+    assert np.array_equal(g[keep], g0[keep], equal_nan=True)
+    assert np.all(np.isnan(g[5, 1:])) and np.all(np.isnan(g[9, 1:]))     # records never reached are NaN
+    # the oracle reports the same status words
+    ref, st_o, _ = oracle_run(bad, 20, "elem")
+    assert np.array_equal(st, st_o)
+
+
+def test_scores_against_numpy(isobea):
+    ens = en.make_ensemble(isobea, 32)
+    nd = 90
+    h, sub, _ = gpu_run(ens, nd)
+    rec = h.get_daily()
+    ix = lo.StateIndex(ens.N, True)
+    obs_day = np.arange(5, nd, 7).astype(np.int32)
+    obs_layer = np.array([0, 2, 4], dtype=np.int32)
+    # synthetic observations = member 3 + noise, with gaps
+    rng = np.random.default_rng(7)
+    sw = rec[3][obs_day][:, obs_layer]
+    ths, thr, smax = (ens.lay[3, k][obs_layer] for k in (lo.L.THSAT, lo.L.THR, lo.L.SWATMAX))
+    th_obs = np.minimum(1.0, (ths * sw / smax - thr) / (ths - thr)) * (ths - thr) + thr + rng.normal(0, 0.005, sw.shape)
+    d_obs = rec[3][obs_day][:, ix.SWATI_d18O][:, obs_layer] + rng.normal(0, 0.1, sw.shape)
+    th_obs[2, 1] = np.nan; d_obs[4, 0] = np.nan
+    sc = h.scores(obs_day, obs_layer, th_obs, d_obs)
+    for m in range(ens.M):
+        swm = rec[m][obs_day][:, obs_layer]
+        thsm, thrm, smaxm = (ens.lay[m, k][obs_layer] for k in (lo.L.THSAT, lo.L.THR, lo.L.SWATMAX))
+        sim_th = np.minimum(1.0, (thsm * swm / smaxm - thrm) / (thsm - thrm)) * (thsm - thrm) + thrm
+        sim_d = rec[m][obs_day][:, ix.SWATI_d18O][:, obs_layer]
+        for v, (sim, obs) in enumerate(((sim_th, th_obs), (sim_d, d_obs))):
+            ok = ~np.isnan(obs)
+            s_, o_ = sim[ok], obs[ok]
+            rmse = np.sqrt(np.mean((s_ - o_) ** 2))
+            r = np.corrcoef(s_, o_)[0, 1]
+            kge = 1 - np.sqrt((r - 1) ** 2 + (s_.std() / o_.std() - 1) ** 2 + (s_.mean() / o_.mean() - 1) ** 2)
+            assert np.isclose(sc[m, 2 * v], rmse, rtol=1e-9) and np.isclose(sc[m, 2 * v + 1], kge, rtol=1e-6, atol=1e-9)
+    assert np.argmin(sc[:, 0]) == 3 and np.argmin(sc[:, 2]) == 3     # the generating member scores best
+    h.close()
+
+
+def test_abi_error_handling(dav_full):
+    ens = en.make_ensemble(dav_full, 4)
+    h = capi.Handle(ens.N, ens.iso, 0, 10)
+    with pytest.raises(capi.LwfbError, match="set_sites"):
+        h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    with pytest.raises(capi.LwfbError, match="shorter"):
+        h.set_sites(ens.forcing[:, :5])
+    h.set_sites(ens.forcing)
+    with pytest.raises(capi.LwfbError, match="site index"):
+        h.set_members(np.full(4, 3), ens.scal, ens.lay, ens.u0)
+    h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    with pytest.raises(capi.LwfbError):
+        h.get_daily()                               # not run yet
+    h.run()
+    with pytest.raises(capi.LwfbError):
+        h.get_daily(2, 10)                          # out of range
+    h.close()
+    h = capi.Handle(ens.N, ens.iso, 0, 10, record_daily=False)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0); h.run()
+    with pytest.raises(capi.LwfbError, match="record_daily"):
+        h.get_daily()
+    assert h.get_final().shape == (4, ens.u0.shape[1])
+    h.close()
