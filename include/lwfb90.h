@@ -243,6 +243,10 @@ int lwfb_fp64_peak(int32_t device, int32_t reps, double* tflops);
 /* testing aid: raw device-layout copy ([field][member]) of the member blocks; which = 0 scal, 1 lay, 2 u0 */
 int lwfb_debug_get_block(lwfb_handle* h, int32_t which, double* out);
 
+/* testing aid: run the thread-per-member kernel (a second, independently written CUDA implementation that
+ * is otherwise used only for N < 3 or N > 32 layers) instead of the lane-per-layer production kernel */
+int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on);
+
 /* kernel launch statistics of the last lwfb_run: number of kernel launches, device ms */
 int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* device_ms);
 

@@ -37,7 +37,7 @@ _lib = None
 SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error", "lwfb_set_sites",
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
            "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
-           "lwfb_fp64_peak", "lwfb_debug_get_block"]
+           "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy"]
 
 
 def lib():
@@ -209,6 +209,11 @@ class Handle:
         du = np.empty((self.M, self.N + 9))
         self._ck(self._L.lwfb_eval_rhs(self._h, float(t), _p(sw), _p(gw), _p(fr), _p(nt), _p(du)))
         return du
+
+    def force_legacy(self, on: bool = True):
+        """Testing aid: use the thread-per-member kernel instead of the lane-per-layer kernel."""
+        self._L.lwfb_debug_force_legacy.argtypes = [C.c_void_p, C.c_int32]
+        self._ck(self._L.lwfb_debug_force_legacy(self._h, int(on)))
 
     def last_run_stats(self):
         n = C.c_int32()

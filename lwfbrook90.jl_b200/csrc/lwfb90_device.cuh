@@ -9,7 +9,7 @@
 // reference root) is cited next to it.  The arithmetic follows the reference formulas; the time
 // stepping restates OrdinaryDiffEq's Tsit5 + PI controller + callback ordering.
 #pragma once
-#include <cuda_runtime.h>
+#include "lwfb90_simt.h"
 #include <math.h>
 #include <stdint.h>
 
@@ -545,11 +545,10 @@ __device__ inline void snowpack(double RTHR, double STHR, double PSNVP, double S
 }
 
 // TBYLAYER src/module_EVP.jl:301-419.  FLAG kept as a bit mask (N <= 64).
-template <int NT>
+template <int NMAX>
 __device__ inline double tbylayer(int N, int J, double PTR, double DISPC, const double* ALPHA, const double* KK,
                                   const double* RROOTI, double RXYLEM, const double* PSITI, double PSICR,
                                   bool NOOUTF, double* ATRANI) {
-  constexpr int NMAX = NT > 0 ? NT : LWFB_MAX_LAYERS;
   unsigned long long FLAG = 0ull;
   double RI[NMAX];
   for (int i = 0; i < N; i++) {
@@ -609,34 +608,44 @@ struct DayState {
 // MSBPREINT :382-507, PLNTRES src/module_EVP.jl:144-190, CANOPY_* src/module_PET.jl:193-258,
 // ROUGH :325-366, WEATHER :429-480, SNOVAP src/module_SNO.jl:166-183, SNOENRGY :223-234, FRSS
 // src/module_PET.jl:873-888.
-template <int NT>
-__device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restrict__ frow, double day, double* sw,
-                                        DayState& ds, double* TRANI_state, double& RWU_state) {
-  constexpr int NMAX = Member<NT>::NMAX;
-  const int N = mb.N;
-  double psim[NMAX], psiti[NMAX], kk[NMAX];
-  mb.swchek(sw);
-  for (int i = 0; i < N; i++) {
-    double W, th;
-    mb.soilvar1(i, sw[i], W, psim[i], th, kk[i]);
-    psiti[i] = psim[i] + mb.PSIG[i];
-  }
+// read-only view of one member's parameter blocks ([field][member] layout)
+struct ParamView {
+  int N;
+  int64_t m, M;
+  const double* __restrict__ scal;
+  const double* __restrict__ lay;
+  __device__ __forceinline__ double S(int k) const { return __ldg(scal + (int64_t)k * M + m); }
+  __device__ __forceinline__ double Lp(int k, int i) const { return __ldg(lay + ((int64_t)k * N + i) * M + m); }
+};
+
+// Core of the daily callback: everything after the soil state (psim of the top layer, psiti[], kk[]) is
+// known.  Outputs: the daily-frozen fluxes (RNET, SMLT, SLVP, TRANI[]), TA, the updated day-constant
+// states in `ds`, u.TRANI.mmday / u.RWU.mmday and the per-member status.
+#ifndef LWFB_CB_INLINE
+#define LWFB_CB_INLINE __forceinline__
+#endif
+template <int NMAX>
+__device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __restrict__ frow, double day, double psim0,
+                                        const double* psiti, const double* kk, DayState& ds, double* TRANI,
+                                        double& o_RNET, double& o_SMLT, double& o_SLVP, double& o_TA,
+                                        double* TRANI_state, double& RWU_state, int& status) {
+  const int N = pv.N;
   double u_INTS = ds.INTS, u_INTR = ds.INTR, u_SNOW = ds.SNOW, u_CC = ds.CC, u_SNOWLQ = ds.SNOWLQ;
   double TMAX = __ldg(frow + LWFB_F_TMAX), TMIN = __ldg(frow + LWFB_F_TMIN), EA = __ldg(frow + LWFB_F_VAPPRES),
          UW = __ldg(frow + LWFB_F_WIND), SOLRAD = __ldg(frow + LWFB_F_GLOBRAD), PREC = __ldg(frow + LWFB_F_PREC),
          DOY = __ldg(frow + LWFB_F_DOY);
-  double DENSEF = __ldg(frow + LWFB_F_DENSEF_REL) * mb.S(LWFB_S_DENSEF_BASELINE);
-  double HEIGHT = __ldg(frow + LWFB_F_HEIGHT_REL) * mb.S(LWFB_S_HEIGHT_BASELINE);
-  double LAI = __ldg(frow + LWFB_F_LAI_REL) * mb.S(LWFB_S_MAXLAI);
-  double SAI = __ldg(frow + LWFB_F_SAI_REL) * mb.S(LWFB_S_SAI_BASELINE);
+  double DENSEF = __ldg(frow + LWFB_F_DENSEF_REL) * pv.S(LWFB_S_DENSEF_BASELINE);
+  double HEIGHT = __ldg(frow + LWFB_F_HEIGHT_REL) * pv.S(LWFB_S_HEIGHT_BASELINE);
+  double LAI = __ldg(frow + LWFB_F_LAI_REL) * pv.S(LWFB_S_MAXLAI);
+  double SAI = __ldg(frow + LWFB_F_SAI_REL) * pv.S(LWFB_S_SAI_BASELINE);
   // relative root density of the day (HammelKennel_lateral_rootgrowth, src/func_DiffEq_definition_p.jl:606-628)
   double RELDEN[NMAX];
-  if (mb.S(LWFB_S_RELDEN_CONST) != 0.0) {
-    for (int i = 0; i < N; i++) RELDEN[i] = mb.Lp(LWFB_L_TINI, i) > 1e19 ? 0.0 : mb.Lp(LWFB_L_RELDEN, i);
+  if (pv.S(LWFB_S_RELDEN_CONST) != 0.0) {
+    for (int i = 0; i < N; i++) RELDEN[i] = pv.Lp(LWFB_L_TINI, i) > 1e19 ? 0.0 : pv.Lp(LWFB_L_RELDEN, i);
   } else {
-    double t_y = mb.S(LWFB_S_AGE0) + day / 365, per = mb.S(LWFB_S_RGROPER), rl0 = mb.S(LWFB_S_RL0);
+    double t_y = pv.S(LWFB_S_AGE0) + day / 365, per = pv.S(LWFB_S_RGROPER), rl0 = pv.S(LWFB_S_RL0);
     for (int i = 0; i < N; i++) {
-      double ts = mb.Lp(LWFB_L_TINI, i), fin = mb.Lp(LWFB_L_RELDEN, i);
+      double ts = pv.Lp(LWFB_L_TINI, i), fin = pv.Lp(LWFB_L_RELDEN, i);
       if (t_y < ts) RELDEN[i] = 0.0;
       else if (t_y <= ts + per) RELDEN[i] = rl0 * lwfb_pow(fin / rl0, (t_y - ts) / per);
       else RELDEN[i] = fin;
@@ -644,21 +653,21 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
   }
   // ---- MSBSETVARS
   double DAYLEN, I0HDAY, SLFDAY;
-  sunds(mb.S(LWFB_S_LAT), mb.S(LWFB_S_ESLOPE), DOY, mb.S(LWFB_S_L1), mb.S(LWFB_S_L2), DAYLEN, I0HDAY, SLFDAY);
+  sunds(pv.S(LWFB_S_LAT), pv.S(LWFB_S_ESLOPE), DOY, pv.S(LWFB_S_L1), pv.S(LWFB_S_L2), DAYLEN, I0HDAY, SLFDAY);
   double SAIeff = DENSEF * SAI;
-  double RTLENeff = DENSEF * mb.S(LWFB_S_MXRTLN);
-  double KPL = jmax(DENSEF * mb.S(LWFB_S_MXKPL), 1E-8);
+  double RTLENeff = DENSEF * pv.S(LWFB_S_MXRTLN);
+  double KPL = jmax(DENSEF * pv.S(LWFB_S_MXKPL), 1E-8);
   double RPLANT = 1 / KPL;
   double LAIeff0 = DENSEF * LAI;
-  double SNOFRC = snofrac(TMAX, TMIN, mb.S(LWFB_S_RSTEMP));
+  double SNOFRC = snofrac(TMAX, TMIN, pv.S(LWFB_S_RSTEMP));
   double RROOTI[NMAX], ALPHA[NMAX];
-  double RXYLEM = mb.S(LWFB_S_FXYLEM) * RPLANT;
+  double RXYLEM = pv.S(LWFB_S_FXYLEM) * RPLANT;
   {
     double sumRD = 0;
-    for (int i = 0; i < N; i++) sumRD += RELDEN[i] * (mb.THICK[i] * (1 - mb.STONEF[i]));
-    double RTRAD = mb.S(LWFB_S_RTRAD);
+    for (int i = 0; i < N; i++) sumRD += RELDEN[i] * (pv.Lp(LWFB_L_THICK, i) * (1 - pv.Lp(LWFB_L_STONEF, i)));
+    double RTRAD = pv.S(LWFB_S_RTRAD);
     for (int i = 0; i < N; i++) {
-      double D = mb.THICK[i] * (1 - mb.STONEF[i]);
+      double D = pv.Lp(LWFB_L_THICK, i) * (1 - pv.Lp(LWFB_L_STONEF, i));
       double RTFRAC = RELDEN[i] * D / sumRD;
       if (RELDEN[i] < 0.00001 || RTLENeff < 0.1) { RROOTI[i] = 1E+20; ALPHA[i] = 1E+20; }
       else {
@@ -670,21 +679,21 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
       }
     }
   }
-  double SNODEP = 0.001 * u_SNOW / mb.S(LWFB_S_SNODEN);
+  double SNODEP = 0.001 * u_SNOW / pv.S(LWFB_S_SNODEN);
   double HSNO = jmax(HEIGHT - SNODEP, 0);
   double RATIOc = HSNO / HEIGHT;
   double HEIGHTeff = jmax(HSNO, 0.01);
   double LAIeff = jmax(RATIOc * LAIeff0, 0.00001);
-  double Z0GS = (u_SNOW > 0) ? mb.S(LWFB_S_Z0S) : mb.S(LWFB_S_Z0G);
+  double Z0GS = (u_SNOW > 0) ? pv.S(LWFB_S_Z0S) : pv.S(LWFB_S_Z0G);
   double Z0C, DISPC, Z0, DISP, ZA;
   {
-    double HR = mb.S(LWFB_S_HR), HS = mb.S(LWFB_S_HS), CZR = mb.S(LWFB_S_CZR), CZS = mb.S(LWFB_S_CZS);
+    double HR = pv.S(LWFB_S_HR), HS = pv.S(LWFB_S_HS), CZR = pv.S(LWFB_S_CZR), CZS = pv.S(LWFB_S_CZS);
     if (HEIGHTeff >= HR) Z0C = CZR * HEIGHTeff;
     else if (HEIGHTeff <= HS) Z0C = CZS * HEIGHTeff;
     else Z0C = CZS * HS + (CZR * HR - CZS * HS) * (HEIGHTeff - HS) / (HR - HS);
     DISPC = HEIGHTeff - Z0C / 0.3;
     if (Z0GS > Z0C) Z0GS = Z0C;
-    double RATIO = (LAIeff + SAIeff) / (mb.S(LWFB_S_LPC) + 0.035 * HEIGHTeff);
+    double RATIO = (LAIeff + SAIeff) / (pv.S(LWFB_S_LPC) + 0.035 * HEIGHTeff);
     if (RATIO >= 1) { Z0 = Z0C; DISP = DISPC; }
     else {
       double e = -1 + lwfb_exp(0.909 - 3.03 * Z0C / HEIGHTeff);
@@ -692,7 +701,7 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
       DISP = 1.1 * HEIGHTeff * lwfb_log(1.0 + lwfb_pow(XX, 0.25));
       Z0 = jmin(0.3 * (HEIGHTeff - DISP), Z0GS + 0.3 * HEIGHTeff * lwfb_pow(XX, 0.5));
     }
-    ZA = HEIGHTeff + mb.S(LWFB_S_ZMINH);
+    ZA = HEIGHTeff + pv.S(LWFB_S_ZMINH);
   }
   const double SHEAT = 0.;
   double SOLRADC, TA, TADTM, TANTM, UA, UADTM, UANTM;
@@ -706,12 +715,12 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
     double uw = UW;
     if (uw == 0) uw = 3.0;
     uw = jmax(uw, 0.2);
-    UA = uw * wndadj(ZA, DISP, Z0, mb.S(LWFB_S_FETCH), mb.S(LWFB_S_ZW), mb.S(LWFB_S_Z0W));
-    double WNDRAT = mb.S(LWFB_S_WNDRAT);
+    UA = uw * wndadj(ZA, DISP, Z0, pv.S(LWFB_S_FETCH), pv.S(LWFB_S_ZW), pv.S(LWFB_S_Z0W));
+    double WNDRAT = pv.S(LWFB_S_WNDRAT);
     UADTM = UA / (DAYLEN + (1 - DAYLEN) * WNDRAT);
     UANTM = WNDRAT * UADTM;
   }
-  double LWIDTH = mb.S(LWFB_S_LWIDTH), RHOTP = mb.S(LWFB_S_RHOTP), NN = mb.S(LWFB_S_NN);
+  double LWIDTH = pv.S(LWFB_S_LWIDTH), RHOTP = pv.S(LWFB_S_RHOTP), NN = pv.S(LWFB_S_NN);
   double TSNOW, PSNVP, ALBEDO;
   if (u_SNOW > 0) {
     TSNOW = -u_CC / (p_CVICE * u_SNOW);
@@ -721,28 +730,28 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
     double RAA, RAC, RAS;
     swgra(UA, ZA, HEIGHTeff, Z0, DISP, Z0C, DISPC, Z0GS, LWIDTH, RHOTP, NN, LAIeff, SAIeff, RAA, RAC, RAS);
     PSNVP = (p_WTOMJ / p_LS) * (p_CPRHO / p_GAMMA) * (ESNOW - EA) / (RAA + RAS);
-    PSNVP = mb.S(LWFB_S_KSNVP) * PSNVP;
-    ALBEDO = mb.S(LWFB_S_ALBSN);
-  } else { TSNOW = 0.; PSNVP = 0.; ALBEDO = mb.S(LWFB_S_ALB); }
+    PSNVP = pv.S(LWFB_S_KSNVP) * PSNVP;
+    ALBEDO = pv.S(LWFB_S_ALBSN);
+  } else { TSNOW = 0.; PSNVP = 0.; ALBEDO = pv.S(LWFB_S_ALB); }
   double SNOEN;
-  if (TA <= 0) SNOEN = mb.S(LWFB_S_CCFAC) * 2.0 * DAYLEN * (TA - TSNOW);
+  if (TA <= 0) SNOEN = pv.S(LWFB_S_CCFAC) * 2.0 * DAYLEN * (TA - TSNOW);
   else
-    SNOEN = mb.S(LWFB_S_MELFAC) * 2.0 * DAYLEN * TA * lwfb_exp(-mb.S(LWFB_S_SAIMLT) * SAIeff) *
-            lwfb_exp(-mb.S(LWFB_S_LAIMLT) * LAIeff) * SLFDAY;
+    SNOEN = pv.S(LWFB_S_MELFAC) * 2.0 * DAYLEN * TA * lwfb_exp(-pv.S(LWFB_S_SAIMLT) * SAIeff) *
+            lwfb_exp(-pv.S(LWFB_S_LAIMLT) * LAIeff) * SLFDAY;
   double RSS;
   if (u_SNOW > 0) RSS = 0.;
   else {
-    double RSSA = mb.S(LWFB_S_RSSA);
+    double RSSA = pv.S(LWFB_S_RSSA);
     if (RSSA < 0.0001) RSS = 1e20;
-    else RSS = RSSA * lwfb_pow(jmax(psim[0] / mb.Lp(LWFB_L_PSIF, 0), 1.0), mb.S(LWFB_S_RSSB));
-    if (RSS < 0.000001) mb.status = LWFB_ST_RSS;
+    else RSS = RSSA * lwfb_pow(jmax(psim0 / pv.Lp(LWFB_L_PSIF, 0), 1.0), pv.S(LWFB_S_RSSB));
+    if (RSS < 0.000001) status = LWFB_ST_RSS;
   }
   // ---- MSBDAYNIGHT
   double PTR[2], GER[2], PIR[2], GIR[2], PGER[2];
   double ATRI0[NMAX], ATRI1[NMAX];
-  double C1 = mb.S(LWFB_S_C1), C2 = mb.S(LWFB_S_C2), C3 = mb.S(LWFB_S_C3), CR = mb.S(LWFB_S_CR);
-  double GLMIN = mb.S(LWFB_S_GLMIN), PSICR = mb.S(LWFB_S_PSICR);
-  bool NOOUTF = mb.S(LWFB_S_NOOUTF) != 0.0;
+  double C1 = pv.S(LWFB_S_C1), C2 = pv.S(LWFB_S_C2), C3 = pv.S(LWFB_S_C3), CR = pv.S(LWFB_S_CR);
+  double GLMIN = pv.S(LWFB_S_GLMIN), PSICR = pv.S(LWFB_S_PSICR);
+  bool NOOUTF = pv.S(LWFB_S_NOOUTF) != 0.0;
 #pragma unroll 1
   for (int J = 1; J <= 2; J++) {
     double SLRAD, TAJ, UAJ;
@@ -755,15 +764,15 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
     double VPD = ES - EA;
     swgra(UAJ, ZA, HEIGHTeff, Z0, DISP, Z0C, DISPC, Z0GS, LWIDTH, RHOTP, NN, LAIeff, SAIeff, RAA, RAC, RAS);
     if (J == 1)
-      RSC = srsc(SLRAD, TA, VPD, LAIeff, SAIeff, GLMIN, mb.S(LWFB_S_GLMAX), mb.S(LWFB_S_R5), mb.S(LWFB_S_CVPD),
-                 mb.S(LWFB_S_RM), CR, mb.S(LWFB_S_TL), mb.S(LWFB_S_T1), mb.S(LWFB_S_T2), mb.S(LWFB_S_TH));
+      RSC = srsc(SLRAD, TA, VPD, LAIeff, SAIeff, GLMIN, pv.S(LWFB_S_GLMAX), pv.S(LWFB_S_R5), pv.S(LWFB_S_CVPD),
+                 pv.S(LWFB_S_RM), CR, pv.S(LWFB_S_TL), pv.S(LWFB_S_T1), pv.S(LWFB_S_T2), pv.S(LWFB_S_TH));
     else RSC = 1 / (GLMIN * LAIeff);
     swpe(AA, ASUBS, VPD, RAA, RAC, RAS, RSC, RSS, DELTA, PTR[J - 1], GER[J - 1]);
     swpe(AA, ASUBS, VPD, RAA, RAC, RAS, 0, RSS, DELTA, PIR[J - 1], GIR[J - 1]);
     swpe(AA, ASUBS, VPD, RAA, RAC, RAS, RSC, 0, DELTA, dmy, PGER[J - 1]);
     double* ATRI = (J == 1) ? ATRI0 : ATRI1;
     if (PTR[J - 1] > 0.001) {
-      double ATR = tbylayer<NT>(N, J, PTR[J - 1], DISPC, ALPHA, kk, RROOTI, RXYLEM, psiti, PSICR, NOOUTF, ATRI);
+      double ATR = tbylayer<NMAX>(N, J, PTR[J - 1], DISPC, ALPHA, kk, RROOTI, RXYLEM, psiti, PSICR, NOOUTF, ATRI);
       if (ATR < PTR[J - 1]) GER[J - 1] = swge(AA, ASUBS, VPD, RAA, RAS, RSS, DELTA, ATR);
     } else {
       PTR[J - 1] = 0;
@@ -775,20 +784,20 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
   double GEVP = (GER[0] * DAYLEN + GER[1] * (1 - DAYLEN));
   double PINT = (PIR[0] * DAYLEN + PIR[1] * (1 - DAYLEN));
   double GIVP = (GIR[0] * DAYLEN + GIR[1] * (1 - DAYLEN));
-  for (int i = 0; i < N; i++) mb.TRANI[i] = (ATRI0[i] * DAYLEN + ATRI1[i] * (1 - DAYLEN));
+  for (int i = 0; i < N; i++) TRANI[i] = (ATRI0[i] * DAYLEN + ATRI1[i] * (1 - DAYLEN));
   // ---- MSBPREINT
   const double DTP = 1.0;
   double SFAL = SNOFRC * PREC, RFAL = PREC - SFAL;
   int IHD = (int)__ldg(frow + LWFB_F_IHD);
   double SINT, ISVP, RINT, IRVP;
-  inter24(SFAL, (PINT < 0 && TA > 0) ? 0.0 : PINT, LAIeff, SAIeff, mb.S(LWFB_S_FSINTL), mb.S(LWFB_S_FSINTS),
-          mb.S(LWFB_S_CINTSL), mb.S(LWFB_S_CINTSS), IHD, u_INTS, SINT, ISVP);
-  inter24(RFAL, PINT - ISVP, LAIeff, SAIeff, mb.S(LWFB_S_FRINTL), mb.S(LWFB_S_FRINTS), mb.S(LWFB_S_CINTRL),
-          mb.S(LWFB_S_CINTRS), IHD, u_INTR, RINT, IRVP);
+  inter24(SFAL, (PINT < 0 && TA > 0) ? 0.0 : PINT, LAIeff, SAIeff, pv.S(LWFB_S_FSINTL), pv.S(LWFB_S_FSINTS),
+          pv.S(LWFB_S_CINTSL), pv.S(LWFB_S_CINTSS), IHD, u_INTS, SINT, ISVP);
+  inter24(RFAL, PINT - ISVP, LAIeff, SAIeff, pv.S(LWFB_S_FRINTL), pv.S(LWFB_S_FRINTS), pv.S(LWFB_S_CINTRL),
+          pv.S(LWFB_S_CINTRS), IHD, u_INTR, RINT, IRVP);
   double WETFR = jmin(1.0, (IRVP + ISVP) / PINT);
   double RTHR = RFAL - RINT, STHR = SFAL - SINT;
   PTRAN = (1.0 - WETFR) * PTRAN;
-  for (int i = 0; i < N; i++) mb.TRANI[i] = (1.0 - WETFR) * mb.TRANI[i];
+  for (int i = 0; i < N; i++) TRANI[i] = (1.0 - WETFR) * TRANI[i];
   double SLVP, RSNO, SNVP, SMLT;
   if (u_SNOW <= 0 && STHR <= 0) SLVP = WETFR * GIVP + (1.0 - WETFR) * GEVP;
   else SLVP = 0.0;
@@ -796,17 +805,17 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
   if (u_SNOW <= 0 && STHR <= 0) { RSNO = 0.0; SNVP = 0.0; SMLT = 0.0; }
   else {
     if (u_SNOW <= 0 && STHR > 0) { nCC = 0.0; nSNOWLQ = 0.0; }
-    snowpack(RTHR, STHR, PSNVP, SNOEN, nCC, nSNOW, nSNOWLQ, DTP, TA, mb.S(LWFB_S_MAXLQF), mb.S(LWFB_S_GRDMLT), RSNO,
+    snowpack(RTHR, STHR, PSNVP, SNOEN, nCC, nSNOW, nSNOWLQ, DTP, TA, pv.S(LWFB_S_MAXLQF), pv.S(LWFB_S_GRDMLT), RSNO,
              SNVP, SMLT);
   }
   double RNET = RTHR - RSNO;
-  mb.RNET = RNET; mb.SMLT = SMLT; mb.SLVP = SLVP; mb.TA = TA;
+  o_RNET = RNET; o_SMLT = SMLT; o_SLVP = SLVP; o_TA = TA;
   ds.INTS = u_INTS + (SINT - ISVP) * DTP;
   ds.INTR = u_INTR + (RINT - IRVP) * DTP;
   ds.SNOW = nSNOW; ds.CC = nCC; ds.SNOWLQ = nSNOWLQ;
   double sumT = 0;
-  for (int i = 0; i < N; i++) sumT += mb.TRANI[i];
-  for (int i = 0; i < N; i++) TRANI_state[i] = DTP * mb.TRANI[i];
+  for (int i = 0; i < N; i++) sumT += TRANI[i];
+  for (int i = 0; i < N; i++) TRANI_state[i] = DTP * TRANI[i];
   RWU_state = DTP * sumT;
   double* a = ds.acc;
   a[LWFB_A_CUM_D_PREC] = DTP * (RFAL + SFAL);
@@ -830,6 +839,24 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
   a[LWFB_A_BYFL] = 0; a[LWFB_A_DSFL] = 0; a[LWFB_A_GWFL] = 0; a[LWFB_A_VRFLN] = 0;
   a[LWFB_A_CUM_D_RTHR] = DTP * (RFAL - RINT);
   a[LWFB_A_CUM_D_STHR] = DTP * (SFAL - SINT);
+}
+
+// daily callback of the thread-per-member kernels: soil state of all layers, then the core
+template <int NT>
+__device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restrict__ frow, double day, double* sw,
+                                        DayState& ds, double* TRANI_state, double& RWU_state) {
+  constexpr int NMAX = Member<NT>::NMAX;
+  const int N = mb.N;
+  double psim[NMAX], psiti[NMAX], kk[NMAX];
+  mb.swchek(sw);
+  for (int i = 0; i < N; i++) {
+    double W, th;
+    mb.soilvar1(i, sw[i], W, psim[i], th, kk[i]);
+    psiti[i] = psim[i] + mb.PSIG[i];
+  }
+  ParamView pv{N, mb.m, mb.M, mb.scal, mb.lay};
+  cb_core<NMAX>(pv, frow, day, psim[0], psiti, kk, ds, mb.TRANI, mb.RNET, mb.SMLT, mb.SLVP, mb.TA, TRANI_state, RWU_state,
+                mb.status);
 }
 
 // src/module_ISO.jl:36-37, :53-55

@@ -1122,7 +1122,8 @@ int lwfb_oracle_run_member(int N, int iso, int t0_day, int n_days, int n_rows, c
   double tstop = t0 + 1.0;
   if (tstop > tend) tstop = tend;
   int rec = 1;
-  while (t < tend) {
+  status = m->status;   /* a failing initial callback (RSS error) stops the member before its first step */
+  while (status == LWFB_ST_OK && t < tend) {
     /* loopheader! */
     if (iter > 0) {
       if (accept) {

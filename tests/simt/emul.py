@@ -1,0 +1,76 @@
+"""ctypes wrapper of the lock-step warp emulator (tests/simt/simt_emul.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Runs the *kernel text* of lwfbrook90.jl_b200/csrc on the host with SIMT semantics so that the non-GPU
+test suite can compare it bit-for-bit with the CPU oracle.  Never imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_SO = os.path.join(_HERE, "_build", "libsimt_emul.so")
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_lp = C.POINTER(C.c_int64)
+
+LANES, MEMBER = 0, 1
+
+
+def build(force: bool = False) -> str:
+    deps = [os.path.join(_HERE, "simt_emul.cpp")] + glob.glob(os.path.join(_ROOT, "lwfbrook90.jl_b200", "csrc", "*.cuh")) \
+        + glob.glob(os.path.join(_ROOT, "lwfbrook90.jl_b200", "csrc", "*.h")) + glob.glob(os.path.join(_ROOT, "include", "*.h"))
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(f) for f in deps):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read().split() else []
+        subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", *fma, "-fPIC", "-shared",
+                               "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"), "-lpthread"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.lwfb_emul_run.restype = C.c_int
+        _lib.lwfb_emul_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int64, _ip,
+                                       _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int,
+                                       _dp, _ip, _lp]
+    return _lib
+
+
+def _p(a, t=_dp):
+    return a.ctypes.data_as(t)
+
+
+def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, *, reltol=1e-5, abstol=1e-6,
+        dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000, n_threads=8):
+    """Same shapes and return values as oracle.run."""
+    forcing = np.ascontiguousarray(forcing, dtype=np.float64)
+    if forcing.ndim == 2:
+        forcing = forcing[None]
+    n_sites, n_rows, _ = forcing.shape
+    scal = np.ascontiguousarray(scal, dtype=np.float64)
+    lay = np.ascontiguousarray(lay, dtype=np.float64)
+    u0 = np.ascontiguousarray(u0, dtype=np.float64)
+    M = scal.shape[0]
+    L = 9 * N + 51 if iso else 5 * N + 39
+    assert u0.shape == (M, L) and lay.shape[0] == M and lay.shape[2] == N
+    som = np.ascontiguousarray(site_of_member, dtype=np.int32)
+    out = np.empty((M, n_days + 1, L))
+    status = np.zeros(M, dtype=np.int32)
+    counters = np.zeros((M, 3), dtype=np.int64)
+    rc = lib().lwfb_emul_run(int(kernel), N, int(iso), int(t0_day), int(n_days), n_sites, n_rows, _p(forcing), M, _p(som, _ip),
+                             _p(scal), _p(lay), _p(u0), reltol, abstol, dt_init, dtmax, maxiters, int(n_threads), _p(out),
+                             _p(status, _ip), _p(counters, _lp))
+    if rc != 0:
+        raise RuntimeError(f"lwfb_emul_run failed ({rc})")
+    return out, status, counters

@@ -1,0 +1,199 @@
+// simt_emul.cpp — lock-step warp emulator for the liblwfb90 kernels.  TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the kernel headers of lwfbrook90.jl_b200/csrc with a host compiler (-DLWFB_SIMT_EMUL, see
+// csrc/lwfb90_simt.h) and runs them with the semantics the hardware gives warp-synchronous code: the
+// 32 lanes of a warp are coroutines (ucontext) that advance round-robin from one warp primitive to the
+// next; a primitive returns when all lanes have reached it.  Every primitive carries its source line;
+// lanes meeting at different lines abort the run (that would be undefined behaviour on the GPU).
+//
+// Purpose: the container that builds this repository has no GPU.  The emulator lets the non-GPU test
+// suite check the kernels' arithmetic, shuffle choreography and control flow bit-for-bit against the
+// CPU oracle (tests/test_simt_emulation.py).  It is never linked into liblwfb90.so and is not a
+// fallback: the product path needs the CUDA library and a GPU.
+#define LWFB_SIMT_EMUL 1
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <ucontext.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../lwfbrook90.jl_b200/csrc/lwfb90_simt.h"
+#include "../../lwfbrook90.jl_b200/csrc/lwfb90_device.cuh"
+#include "../../lwfbrook90.jl_b200/csrc/lwfb90_lanes.cuh"
+#include "../../lwfbrook90.jl_b200/csrc/lwfb90_member.cuh"
+
+namespace {
+constexpr int WARP = 32;
+constexpr size_t STACK_BYTES = 1u << 20;
+
+struct Warp {
+  ucontext_t main_ctx, ctx[WARP];
+  char* stacks = nullptr;
+  bool done[WARP];
+  uint64_t slot[2][WARP];
+  int opid[2][WARP];
+  unsigned long counter[WARP];
+  int cur = 0;
+  void (*body)(void* arg, int lane) = nullptr;
+  void* arg = nullptr;
+  long n_ops = 0;
+};
+thread_local Warp* W = nullptr;
+
+int next_alive(int l) {
+  for (int s = 1; s <= WARP; s++) {
+    int n = (l + s) % WARP;
+    if (!W->done[n]) return n;
+  }
+  return -1;
+}
+
+void trampoline(int lane) {
+  W->body(W->arg, lane);
+  W->done[lane] = true;
+  int n = next_alive(lane);
+  if (n < 0) setcontext(&W->main_ctx);
+  W->cur = n;
+  setcontext(&W->ctx[n]);
+}
+
+// deposit a value, let every other lane run up to the same primitive, return the parity of the slot
+int rendezvous(uint64_t v, int op_id) {
+  const int l = W->cur;
+  const unsigned long my_op = W->counter[l]++;
+  const int par = (int)(my_op & 1ul);
+  W->slot[par][l] = v;
+  W->opid[par][l] = op_id;
+  const int n = next_alive(l);
+  if (n >= 0 && n != l) {
+    W->cur = n;
+    swapcontext(&W->ctx[l], &W->ctx[n]);
+  }
+  for (int i = 0; i < WARP; i++) {
+    if (W->done[i] && W->counter[i] <= my_op) { fprintf(stderr, "simt_emul: lane %d exited before the warp primitive at line %d\n", i, op_id); abort(); }
+    if (W->opid[par][i] != op_id) {
+      fprintf(stderr, "simt_emul: divergent warp primitive: lane %d at line %d, lane %d at line %d\n", l, op_id, i, W->opid[par][i]);
+      abort();
+    }
+  }
+  if (l == 0) W->n_ops++;
+  return par;
+}
+
+void run_warp(void (*body)(void*, int), void* arg) {
+  Warp w;
+  w.stacks = (char*)malloc(STACK_BYTES * WARP);
+  w.body = body; w.arg = arg;
+  W = &w;
+  for (int l = 0; l < WARP; l++) {
+    w.done[l] = false; w.counter[l] = 0;
+    w.opid[0][l] = w.opid[1][l] = -1;
+    getcontext(&w.ctx[l]);
+    w.ctx[l].uc_stack.ss_sp = w.stacks + (size_t)l * STACK_BYTES;
+    w.ctx[l].uc_stack.ss_size = STACK_BYTES;
+    w.ctx[l].uc_link = nullptr;
+    makecontext(&w.ctx[l], (void (*)())trampoline, 1, l);
+  }
+  w.cur = 0;
+  swapcontext(&w.main_ctx, &w.ctx[0]);
+  free(w.stacks);
+  W = nullptr;
+}
+}  // namespace
+
+namespace simt {
+uint64_t exchange(uint64_t v, int src_lane, int op_id) {
+  const int l = W->cur;
+  const int par = rendezvous(v, op_id);
+  return (src_lane >= 0 && src_lane < WARP) ? W->slot[par][src_lane] : W->slot[par][l];
+}
+unsigned vote(bool p, int op_id) {
+  const int par = rendezvous(p ? 1u : 0u, op_id);
+  unsigned m = 0;
+  for (int i = 0; i < WARP; i++) m |= (W->slot[par][i] ? 1u : 0u) << i;
+  return m;
+}
+int lane_id() { return W->cur; }
+}  // namespace simt
+
+// ----------------------------------------------------------------------------------------------
+// harness: same argument meaning as lwfb_oracle_run (member-major blocks in, member-major record out)
+// ----------------------------------------------------------------------------------------------
+namespace {
+struct Job {
+  lwfb::DevData d;
+  int kernel;                 // 0 lanes, 1 thread-per-member
+  std::atomic<int64_t> next{0};
+  int64_t n_units = 0;        // warps (lanes kernel) or members
+  std::atomic<long> ops{0};
+};
+
+struct WarpArg { const lwfb::DevData* d; int64_t warp_g; };
+
+void lanes_entry(void* a, int lane) {
+  const WarpArg* wa = (const WarpArg*)a;
+  const lwfb::DevData& d = *wa->d;
+  if (d.N <= 4) lwfb::lanes_body<8, 3>(d, lane, wa->warp_g);
+  else if (d.N <= 8) lwfb::lanes_body<8, 2>(d, lane, wa->warp_g);
+  else lwfb::lanes_body<32, 1>(d, lane, wa->warp_g);
+}
+
+void* worker(void* p) {
+  Job* j = (Job*)p;
+  for (;;) {
+    int64_t u = j->next.fetch_add(1);
+    if (u >= j->n_units) break;
+    if (j->kernel == 0) {
+      WarpArg wa{&j->d, u};
+      run_warp(lanes_entry, &wa);
+    } else {
+      lwfb::integrate_member<0>(j->d, u);
+    }
+  }
+  return nullptr;
+}
+
+template <typename T>
+void to_soa(const T* src, T* dst, int64_t M, int64_t K) {   // [M][K] -> [K][M]
+  for (int64_t m = 0; m < M; m++)
+    for (int64_t k = 0; k < K; k++) dst[k * M + m] = src[m * K + k];
+}
+}  // namespace
+
+extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days, int n_sites, int n_rows,
+                             const double* forcing, int64_t M, const int32_t* site_of_member, const double* scal,
+                             const double* lay, const double* u0, double reltol, double abstol, double dt_init,
+                             double dtmax, int64_t maxiters, int n_threads, double* out_daily, int32_t* status,
+                             int64_t* counters) {
+  (void)n_sites;
+  const int L = LWFB_STATE_LEN(N, iso);
+  if (kernel == 0 && (N < 3 || N > 32)) return -1;
+  std::vector<double> s_scal((size_t)M * LWFB_PS), s_lay((size_t)M * LWFB_PL * N), s_u0((size_t)M * L);
+  std::vector<double> rec((size_t)M * L * (n_days + 1)), fin((size_t)M * L);
+  std::vector<long long> cnt((size_t)M * LWFB_NCOUNTERS);
+  to_soa(scal, s_scal.data(), M, (int64_t)LWFB_PS);
+  to_soa(lay, s_lay.data(), M, (int64_t)LWFB_PL * N);
+  to_soa(u0, s_u0.data(), M, (int64_t)L);
+  Job job;
+  lwfb::DevData& d = job.d;
+  d.M = M; d.N = N; d.iso = iso; d.t0_day = t0_day; d.n_days = n_days; d.n_rows = n_rows; d.L = L;
+  d.scal = s_scal.data(); d.lay = s_lay.data(); d.forc = forcing; d.site = site_of_member; d.u0 = s_u0.data();
+  d.rec = rec.data(); d.fin = fin.data(); d.status = status; d.counters = cnt.data();
+  d.reltol = reltol; d.abstol = abstol; d.dt_init = dt_init; d.dtmax = dtmax; d.maxiters = maxiters;
+  job.kernel = kernel;
+  if (kernel == 0) { const int mpw = 32 / N; job.n_units = (M + mpw - 1) / mpw; }
+  else job.n_units = M;
+  if (n_threads < 1) n_threads = 1;
+  std::vector<pthread_t> th(n_threads);
+  for (int i = 0; i < n_threads; i++) pthread_create(&th[i], nullptr, worker, &job);
+  for (int i = 0; i < n_threads; i++) pthread_join(th[i], nullptr);
+  // [day][L][M] -> [M][day][L]
+  const int64_t K = (int64_t)(n_days + 1) * L;
+  for (int64_t m = 0; m < M; m++)
+    for (int64_t k = 0; k < K; k++) out_daily[m * K + k] = rec[(size_t)k * M + m];
+  for (int64_t m = 0; m < M; m++)
+    for (int c = 0; c < LWFB_NCOUNTERS; c++) counters[m * LWFB_NCOUNTERS + c] = cnt[(size_t)c * M + m];
+  return 0;
+}

@@ -162,6 +162,33 @@ def test_generic_layer_count_kernels_bit_identical(lw, infexp1):
     h.close()
 
 
+def test_thread_per_member_kernel_agrees_with_lane_per_layer_kernel(dav_full, bea):
+    """The library holds two independently written CUDA implementations (lane-per-layer production kernel,
+    thread-per-member kernel for N < 3 or N > 32); both must reproduce the oracle bit-for-bit."""
+    for sim, M in ((dav_full, 24), (bea, 12)):
+        ens = en.make_ensemble(sim, M)
+        h = capi.Handle(ens.N, ens.iso, ens.t0_day, 120)
+        h.force_legacy(True)
+        h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0); h.run()
+        assert_bit_identical(h, ens, 120)
+        h.close()
+
+
+@pytest.mark.parametrize("N", [3, 4, 6, 8, 9, 16, 22, 32])
+def test_lane_kernel_all_group_sizes(lw, N):
+    """Every lanes-per-member geometry (32/N members per warp, idle lanes, 1..3 extra components per lane)."""
+    m = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=[1.1 / N] * N,
+                    root_distribution=dict(beta=0.97, z_rootMax_m=None),
+                    IC_soil=dict(PSIM_init_kPa=-6.0, delta18O_init_permil=-12.0, delta2H_init_permil=-90.0))
+    s = lw.setup(m, ε=0.001 if N > 16 else 0.01, requested_tspan=(100, 130))
+    if s.N > 32:
+        pytest.skip("refinement pushed N above 32")
+    e = en.make_ensemble(s, 11)
+    h, sub, nd = gpu_run(e)
+    assert_bit_identical(h, sub, nd)
+    h.close()
+
+
 def test_nonzero_start_day_and_short_span(dav_full):
     """tspan not starting at 0 (initial conditions applied at t0, forcing taken from the right rows)."""
     e = en.make_ensemble(dav_full, 16)
