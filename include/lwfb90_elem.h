@@ -58,13 +58,14 @@ LWFB_ELEM double lwfb_i2d(int64_t i) {
 #define LWFB_PIO2_LO2 -0x1.f1976b7ed8fbcp-110
 #define LWFB_2OPI 0x1.45f306dc9c883p-1
 
-/* e^x: k = rint(x/ln2), Cody-Waite reduction with fma, degree-14 Taylor polynomial on |r| <= ln2/2 */
+/* e^x: k = rint(x/ln2), Cody-Waite reduction with fma, degree-14 Taylor polynomial on |r| <= ln2/2.
+ * Written without branches (selects only) so that several independent calls can be interleaved by the
+ * instruction scheduler: the polynomial runs on the argument clamped to [-746, 710] and the special
+ * results (NaN, overflow, underflow) are selected at the end. */
 LWFB_ELEM double lwfb_exp(double x) {
-  if (x != x) return x;
-  if (x > 709.782712893384) return INFINITY;
-  if (x < -745.1332191019412) return 0.0;
-  double kf = rint(x * LWFB_INVLN2);
-  double r = fma(-kf, LWFB_LN2_HI, x);
+  double xs = fmin(fmax(x, -746.0), 710.0);   /* fmin/fmax drop a NaN argument: xs is always finite */
+  double kf = rint(xs * LWFB_INVLN2);
+  double r = fma(-kf, LWFB_LN2_HI, xs);
   r = fma(-kf, LWFB_LN2_LO, r);
   double q = 1.0 / 87178291200.0;           /* 1/14! */
   q = fma(q, r, 1.0 / 6227020800.0);        /* 1/13! */
@@ -81,25 +82,30 @@ LWFB_ELEM double lwfb_exp(double x) {
   q = fma(q, r, 0.5);
   double res = 1.0 + fma(r * r, q, r);
   int k = (int)kf;
-  if (k > 1023) { res *= 0x1p1023; k -= 1023; }
-  else if (k < -1021) { res *= 0x1p-1000; k += 1000; }
-  return res * lwfb_i2d((int64_t)(k + 1023) << 52);
+  /* two-step scaling outside the normal exponent range; adj = 0 multiplies by 1.0 (exact) */
+  int adj = k > 1023 ? 1023 : (k < -1021 ? -1000 : 0);
+  res = res * lwfb_i2d((int64_t)(adj + 1023) << 52);
+  k -= adj;
+  res = res * lwfb_i2d((int64_t)(k + 1023) << 52);
+  res = x > 709.782712893384 ? INFINITY : res;
+  res = x < -745.1332191019412 ? 0.0 : res;
+  return x != x ? x : res;
 }
 
 /* log(x): x = 2^e * m, m in (sqrt(1/2), sqrt(2)]; log(m) = 2 atanh(s), s = (m-1)/(m+1), evaluated as
- * f - (f^2/2 - s*(f^2/2 + R(s^2))) to avoid the rounding error of the division near m = 1 */
+ * f - (f^2/2 - s*(f^2/2 + R(s^2))) to avoid the rounding error of the division near m = 1.
+ * Branch-free like lwfb_exp: special arguments (NaN, negative, 0, inf) are selected at the end. */
 LWFB_ELEM double lwfb_log(double x) {
-  if (x != x) return x;
-  if (x < 0.0) return NAN;
-  if (x == 0.0) return -INFINITY;
-  if (x == INFINITY) return x;
-  int e = 0;
-  if (x < 0x1p-1022) { x *= 0x1p54; e = -54; }
-  int64_t ix = lwfb_d2i(x);
+  int sub = x < 0x1p-1022;
+  double xs = sub ? x * 0x1p54 : x;
+  int e = sub ? -54 : 0;
+  int64_t ix = lwfb_d2i(xs);
   e += (int)((ix >> 52) & 0x7ff) - 1023;
   ix = (ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
   double m = lwfb_i2d(ix);
-  if (m > 0x1.6a09e667f3bcdp+0) { m *= 0.5; e += 1; }
+  int big = m > 0x1.6a09e667f3bcdp+0;
+  m = big ? m * 0.5 : m;
+  e += big;
   double f = m - 1.0;
   double s = f / (2.0 + f);
   double z = s * s;
@@ -118,22 +124,24 @@ LWFB_ELEM double lwfb_log(double x) {
   R = R * z;
   double hfsq = 0.5 * f * f;
   double dk = (double)e;
-  return dk * LWFB_LN2_HI - ((hfsq - (s * (hfsq + R) + dk * LWFB_LN2_LO)) - f);
+  double res = dk * LWFB_LN2_HI - ((hfsq - (s * (hfsq + R) + dk * LWFB_LN2_LO)) - f);
+  res = x == INFINITY ? x : res;
+  res = x == 0.0 ? -INFINITY : res;
+  res = x < 0.0 ? NAN : res;
+  return x != x ? x : res;
 }
 
-/* x^y for x >= 0 (x < 0 gives NaN; the reference would throw a DomainError there) */
+/* x^y for x >= 0 (x < 0 gives NaN; the reference would throw a DomainError there).
+ * exp(y*log(x)) already yields NaN for NaN arguments and for x < 0; only y == 0 needs a select. */
 LWFB_ELEM double lwfb_pow(double x, double y) {
-  if (y == 0.0) return 1.0;
-  if (x != x || y != y) return NAN;
-  if (x < 0.0) return NAN;
-  return lwfb_exp(y * lwfb_log(x));
+  double r = lwfb_exp(y * lwfb_log(x));
+  return y == 0.0 ? 1.0 : r;
 }
 /* x^y when lx = lwfb_log(x) is already known (bit-identical to lwfb_pow) */
 LWFB_ELEM double lwfb_pow_from_log(double x, double lx, double y) {
-  if (y == 0.0) return 1.0;
-  if (x != x || y != y) return NAN;
-  if (x < 0.0) return NAN;
-  return lwfb_exp(y * lx);
+  (void)x;
+  double r = lwfb_exp(y * lx);
+  return y == 0.0 ? 1.0 : r;
 }
 
 /* sin and cos kernels on |r| <= pi/4 (Taylor, exact coefficients 1/n!) */

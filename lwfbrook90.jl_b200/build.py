@@ -1,21 +1,28 @@
 """In-tree build of liblwfb90.so (hand-written CUDA for sm_100a, C ABI of include/lwfb90.h)."""
 from __future__ import annotations
 
+import glob
 import os
 import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(_HERE, "csrc", "lwfb90.cu")
+_CSRC = os.path.join(_HERE, "csrc")
 OUT = os.path.join(_HERE, "liblwfb90.so")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "lwfb90_device.cuh"), os.path.join(_HERE, "csrc", "lwfb90_math.cuh"),
-        os.path.join(os.path.dirname(_HERE), "include", "lwfb90.h"),
-        os.path.join(os.path.dirname(_HERE), "include", "lwfb90_elem.h")]
+_OBJ = os.path.join(_HERE, "_obj")
 
 # -fmad=false: no implicit FMA contraction, so that the arithmetic is reproducible bit-for-bit by the
 # host replay (oracle mode B); the elementary functions use explicit fma().
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC"]
+# translation units: (source, extra flags).  lwfb90_member.cu (fallback kernels, not on the measured path) is
+# compiled with NVVM -O1, see the note at the top of that file.
+UNITS = [("lwfb90.cu", []), ("lwfb90_member.cu", ["-Xcicc", "-O1"])]
+
+
+def _deps():
+    return (glob.glob(os.path.join(_CSRC, "*.cu")) + glob.glob(os.path.join(_CSRC, "*.cuh")) + glob.glob(os.path.join(_CSRC, "*.h"))
+            + glob.glob(os.path.join(os.path.dirname(_HERE), "include", "*.h")) + [os.path.abspath(__file__)])
 
 
 def nvcc_path() -> str:
@@ -26,11 +33,21 @@ def nvcc_path() -> str:
 
 
 def stale() -> bool:
-    return (not os.path.exists(OUT)) or any(os.path.getmtime(OUT) < os.path.getmtime(d) for d in DEPS)
+    return (not os.path.exists(OUT)) or any(os.path.getmtime(OUT) < os.path.getmtime(d) for d in _deps())
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, extra=()) -> str:
     if force or stale():
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
-        subprocess.check_call(cmd, cwd=os.path.dirname(SRC))
+        os.makedirs(_OBJ, exist_ok=True)
+        nvcc = nvcc_path()
+        procs, objs = [], []
+        for src, flags in UNITS:
+            obj = os.path.join(_OBJ, src.replace(".cu", ".o"))
+            objs.append(obj)
+            cmd = [nvcc] + NVCC_FLAGS + list(flags) + list(extra) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            procs.append((cmd, subprocess.Popen(cmd, cwd=_CSRC)))
+        for cmd, p in procs:
+            if p.wait() != 0:
+                raise subprocess.CalledProcessError(p.returncode, cmd)
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs, cwd=_CSRC)
     return OUT

@@ -18,39 +18,9 @@
 
 #include "lwfb90_device.cuh"
 #include "lwfb90_lanes.cuh"
-#include "lwfb90_member.cuh"
+#include "lwfb90_launch.h"
 
 using namespace lwfb;
-
-#ifndef LWFB_BLOCK
-#define LWFB_BLOCK 128
-#endif
-
-template <int NT>
-__global__ void __launch_bounds__(LWFB_BLOCK) integrate_kernel(DevData d) {
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= d.M) return;
-  integrate_member<NT>(d, m);
-}
-
-// one RHS evaluation per member (parity tests)
-template <int NT>
-__global__ void rhs_kernel(DevData d, double t, const double* __restrict__ swati, const double* __restrict__ gwat,
-                           const double* __restrict__ frozen, const double* __restrict__ ntfli_prev,
-                           double* __restrict__ du) {
-  constexpr int NMAX = Member<NT>::NMAX;
-  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= d.M) return;
-  Member<NT> mb;
-  mb.load(d, m);
-  const int N = mb.N;
-  double sw[NMAX], out[NMAX + 9];
-  for (int i = 0; i < N; i++) sw[i] = swati[m * N + i];
-  mb.RNET = frozen[m * (N + 3) + 0]; mb.SMLT = frozen[m * (N + 3) + 1]; mb.SLVP = frozen[m * (N + 3) + 2];
-  for (int i = 0; i < N; i++) { mb.TRANI[i] = frozen[m * (N + 3) + 3 + i]; mb.NTFLI[i] = ntfli_prev[m * N + i]; }
-  mb.rhs(sw, gwat[m], t, out);
-  for (int j = 0; j < N + 9; j++) du[m * (N + 9) + j] = out[j];
-}
 
 // [K][M] rows k in [0,K) of members [m_first, m_first+cnt) -> [cnt][K]
 __global__ void soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, int64_t M, int64_t m_first,
@@ -335,18 +305,20 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
   CK(cudaSetDevice(h->o.device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   DevData d = make_dev(h);
-  unsigned grid = (unsigned)((h->M + LWFB_BLOCK - 1) / LWFB_BLOCK);
   CK(cudaEventRecord(h->ev0, st));
   if (d.N >= 3 && d.N <= 32 && !h->force_legacy) {
-    // production path: one lane per soil layer, 32/N members per warp
+    // production path: one lane per soil layer, 32/N members per warp; per-thread constants in shared memory
     const int mpw = 32 / d.N;
     const int64_t warps = (d.M + mpw - 1) / mpw;
-    const unsigned lgrid = (unsigned)((warps + 3) / 4);
-    if (d.N <= 4) integrate_lanes<8, 3><<<lgrid, 128, 0, st>>>(d);
-    else if (d.N <= 8) integrate_lanes<8, 2><<<lgrid, 128, 0, st>>>(d);
-    else integrate_lanes<32, 1><<<lgrid, 128, 0, st>>>(d);
+    const int wpb = LWFB_LANES_BLOCK / 32;
+    const unsigned lgrid = (unsigned)((warps + wpb - 1) / wpb);
+    const size_t smem = (size_t)KC_COUNT * LWFB_LANES_BLOCK * sizeof(double);
+    if (d.N == 3) integrate_lanes<8, 3><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
+    else if (d.N < 8) integrate_lanes<8, 2><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
+    else if (d.N == 8) integrate_lanes<8, 1><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
+    else integrate_lanes<32, 1><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
   } else {
-    integrate_kernel<0><<<grid, LWFB_BLOCK, 0, st>>>(d);   // thread-per-member, runtime layer count (N < 3 or N > 32)
+    launch_member_integrate(d, st);   // thread-per-member, runtime layer count (N < 3 or N > 32)
   }
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, st));
@@ -487,12 +459,7 @@ extern "C" int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, cons
   CK(cudaMemcpy(d_fr, frozen, n_fr * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_nt, ntfli_prev, n_sw * sizeof(double), cudaMemcpyHostToDevice));
   DevData d = make_dev(h);
-  unsigned grid = (unsigned)((M + 127) / 128);
-  switch (N) {
-    case 5: rhs_kernel<5><<<grid, 128>>>(d, t, d_sw, d_gw, d_fr, d_nt, d_du); break;
-    case 7: rhs_kernel<7><<<grid, 128>>>(d, t, d_sw, d_gw, d_fr, d_nt, d_du); break;
-    default: rhs_kernel<0><<<grid, 128>>>(d, t, d_sw, d_gw, d_fr, d_nt, d_du); break;
-  }
+  launch_member_rhs(d, t, d_sw, d_gw, d_fr, d_nt, d_du);
   CK(cudaGetLastError());
   CK(cudaMemcpy(du, d_du, n_du * sizeof(double), cudaMemcpyDeviceToHost));
   return LWFB_OK;

@@ -1,27 +1,31 @@
 // lwfb90_lanes.cuh — the production integrator: one LANE per soil layer.
 //
 // Mapping: a member with N layers (3 <= N <= 32) occupies N consecutive lanes of a warp ("group");
-// a warp holds floor(32/N) members, the remaining lanes idle.  Lane i of a group owns layer i:
-// its 14 hydraulic constants, its SWATI component with the Runge-Kutta bookkeeping, its delta18O /
-// delta2H, and up to EMAX of the 9 member-level ODE components (GWAT and the 8 integrated flow
-// accumulators are dealt round-robin to the lanes of the group).  Everything lives in registers; there
-// is no shared memory and no per-thread stack in the stepping loop.
+// a warp holds floor(32/N) members, the remaining lanes shadow lane 0 and never commit.  Lane i of a
+// group owns layer i: its hydraulic constants (one column of shared memory per thread, ~40 doubles),
+// its SWATI component with the Runge-Kutta bookkeeping, its delta18O / delta2H, and up to EQ of the 8
+// integrated flow accumulators (pure quadratures, dealt round-robin to the lanes of the group).  GWAT
+// and the step-size controller are member-level scalars replicated in the lanes of the group; they
+// evolve identically because every input is a broadcast value.
 //
-// Why this mapping (see profiles/r01_*): with one member per THREAD the layer loops must be unrolled
-// to keep per-layer arrays in registers, the inlined exp/log/pow bodies then make one RHS ~9000
-// instructions (~140 KB of SASS), far beyond the instruction cache, and with 255 registers only 8 warps
-// per SM are resident: ncu showed the warps stalled on instruction fetch ~10 cycles per issued
-// instruction and the FP64 pipe 6 % busy.  One lane per layer makes the code naturally rolled (the
-// per-layer body exists once), needs ~1/5 of the registers, and turns cross-layer couplings into warp
-// shuffles:
-//   * Darcy flux needs psi_t and log K of the layer below          -> __shfl_down
-//   * ITER's min-chain, the bypass/downslope sums, the error norm   -> N-step broadcast chains, evaluated
-//     in exactly the oracle's order so that results stay bit-identical
-//   * INFLOW's bottom-up oversaturation limiter                     -> skipped by a warp vote when no layer
+// Everything that changes only once per day (interception / snow states, the 23 non-integrated
+// accumulator entries, RWU, delta of INTS/INTR/SNOW) lives in global memory in `fin`, the member's full
+// state vector in the reference's order; the daily record is a snapshot copy of it.
+//
+// Why this mapping (see profiles/r01_*): with one member per THREAD the per-layer arrays only stay in
+// registers if the layer loops are unrolled; one RHS is then ~9000 instructions, the kernel needs 255
+// registers (8 warps per SM) and ncu showed the warps waiting ~10 cycles per issued instruction on
+// instruction fetch, FP64 pipe 6 % busy.  One lane per layer keeps the per-layer body once in the code,
+// divides the register need by N, and turns cross-layer couplings into warp shuffles:
+//   * Darcy flux needs psi_t and log K of the layer below           -> __shfl_down
+//   * ITER's min-chain, bypass / downslope sums, the error norm      -> broadcast chains evaluated in
+//     exactly the oracle's order so that results stay bit-identical; ITER takes a plain min when no
+//     clamp / NaN is in play (warp vote), the sums are skipped when every term is zero
+//   * INFLOW's bottom-up oversaturation limiter                      -> skipped by a warp vote when no layer
 //     limits (the common case), otherwise an N-step chain
-// Member-level scalars (t, dt, controller state, frozen daily fluxes) are replicated in the lanes of a
-// group; they evolve identically because every input is a broadcast value.  The daily callback runs
-// warp-synchronously (lanes wait at the day boundary for the slowest member of the warp).
+// The daily callback runs warp-synchronously (lanes wait at the day boundary for the slowest member of
+// the warp).  The elementary functions (include/lwfb90_elem.h) are branch-free so that the independent
+// pow/exp/log of one layer interleave in the FP64 pipe.
 #pragma once
 #include "lwfb90_device.cuh"
 
@@ -36,6 +40,8 @@ __device__ constexpr double lCQ[7][5] = {
     {-0.09249506636175525, -0.071584973281401, 1.379008574103742, 0, 0},                                      // k4 -> stages 5..7
     {-0.028269050394068383, -3.290069515436081, 0, 0, 0},                                                     // k5 -> stages 6..7
     {2.324710524099774, 0, 0, 0, 0}};                                                                         // k6 -> stage 7
+__device__ constexpr double lB7[8] = {0, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742,
+                                      -3.290069515436081, 2.324710524099774, 0};                              // a(7, ks)
 __device__ constexpr double lBT[8] = {0, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
                                       -0.1447110071732629, 0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
 __device__ constexpr double lC[7] = {0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};   // time of the stage evaluated at s
@@ -43,10 +49,25 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
                                        LWFB_A_BYFL, LWFB_A_DSFL, LWFB_A_GWFL, LWFB_A_VRFLN};
 
 #define LFULL 0xffffffffu
+#define LWFB_LANES_BLOCK 128        // threads per block = stride of the shared-memory constant columns
+#ifndef LWFB_LANES_MINBLOCKS
+#define LWFB_LANES_MINBLOCKS 4      // resident blocks per SM the register allocation is sized for
+#endif
 
-template <int NMAX, int EMAX>
-__device__ void lanes_body(const DevData& d, const int lane, const int64_t warp_g) {
-  constexpr int NC = 1 + EMAX;                       // ODE components per lane
+// per-thread constant column (shared memory): element k of this thread is cst[k * LWFB_LANES_BLOCK]
+enum {
+  KC_THSAT = 0, KC_THR, KC_DTH, KC_SWATMAX, KC_E1, KC_E2, KC_E3, KC_E4, KC_TORT, KC_CPSI, KC_KSAT, KC_PSIG,
+  KC_THICK, KC_OMS, KC_INFRAC, KC_THICK_DN, KC_KSAT_DN, KC_TSUM, KC_THALF, KC_STFAC, KC_CITER, KC_WETF,
+  KC_DZ_UP, KC_DZ_DN, KC_THS2, KC_ARATIO,
+  // member-level
+  KC_DPSIMAX, KC_DTIMAX, KC_DRAIN, KC_GSC, KC_GSP, KC_IMPERV, KC_QFFC, KC_QFPAR, KC_SWATQF, KC_SWATQX,
+  KC_CS, KC_SNRHO, KC_LEN1000, KC_LAM, KC_VXYLEM,
+  KC_COUNT
+};
+#define LC(k) (*(const volatile double*)(cst + (k) * LWFB_LANES_BLOCK))
+
+template <int NMAX, int EQ>
+__device__ __forceinline__ void lanes_body(const DevData& d, const int lane, const int64_t warp_g, double* cst) {
   const int N = d.N;
   const int mpw = 32 / N;                            // members per warp
   const int64_t M = d.M;
@@ -64,104 +85,88 @@ __device__ void lanes_body(const DevData& d, const int lane, const int64_t warp_
   const SIdx ix(N, d.iso);
   const ParamView pv{N, m, M, d.scal, d.lay};
   const double* __restrict__ forc = d.forc + (int64_t)__ldg(d.site + m) * d.n_rows * LWFB_F;
+  double* const fin = d.fin;
   auto U0 = [&](int j) { return __ldg(d.u0 + (int64_t)j * M + m); };
+  auto FIN = [&](int j) -> double& { return fin[(int64_t)j * M + m]; };
   auto bcast = [&](double v, int layer) { return __shfl_sync(LFULL, v, base + layer); };
 
-  // ---- per-lane constants (own layer i, and what the flux to the layer below needs)
-  const double THSAT = pv.Lp(LWFB_L_THSAT, i), SWATMAX = pv.Lp(LWFB_L_SWATMAX, i), THR = pv.Lp(LWFB_L_THR, i);
-  const double NPAR = pv.Lp(LWFB_L_NPAR, i), MPAR = pv.Lp(LWFB_L_MPAR, i);
-  const double E1 = -1.0 / MPAR, E2 = 1.0 / NPAR, E3 = NPAR / (NPAR - 1.0);
-  const double TORT = pv.Lp(LWFB_L_TORT, i), CPSI = 9.81 * (-1.0 / pv.Lp(LWFB_L_ALPHA, i));
-  const double KSAT = pv.Lp(LWFB_L_KSAT, i), PSIG = pv.Lp(LWFB_L_PSIG, i), THICK = pv.Lp(LWFB_L_THICK, i);
-  const double STONEF = pv.Lp(LWFB_L_STONEF, i), INFRAC = pv.Lp(LWFB_L_INFRAC, i);
-  const int idn = bot ? i : i + 1;
-  const double THICK_dn = pv.Lp(LWFB_L_THICK, idn), KSAT_dn = pv.Lp(LWFB_L_KSAT, idn), STONEF_dn = pv.Lp(LWFB_L_STONEF, idn);
-  const double DSWMAX = pv.S(LWFB_S_DSWMAX);
-  const double CITER = 0.01 * DSWMAX * THICK * THSAT * (1 - STONEF);
-  const double DPSIMAX = pv.S(LWFB_S_DPSIMAX), DTIMAX = pv.S(LWFB_S_DTIMAX), DRAIN = pv.S(LWFB_S_DRAIN),
-               GSC = pv.S(LWFB_S_GSC), GSP = pv.S(LWFB_S_GSP), IMPERV = pv.S(LWFB_S_IMPERV);
-  const bool BYPAR = pv.S(LWFB_S_BYPAR) == 1.0;
-  const int QLAYER = (int)pv.S(LWFB_S_QLAYER);
-  const bool SLOPE = !(pv.S(LWFB_S_LENGTH_SLOPE) == 0 || pv.S(LWFB_S_DSLOPE) == 0);
-  const double WETF = BYPAR ? pv.Lp(LWFB_L_WETF, i) : 0.0;
-  const double DZ_up = top ? 1.0 : pv.Lp(LWFB_L_DZ, i - 1), DZ_dn = bot ? 1.0 : pv.Lp(LWFB_L_DZ, i);
+  // ---- per-lane constants -> shared-memory column
+  bool BYPAR, SLOPE;
+  int QLAYER;
+  {
+    auto SETC = [&](int k, double v) { cst[k * LWFB_LANES_BLOCK] = v; };
+    const double THSAT = pv.Lp(LWFB_L_THSAT, i), SWATMAX = pv.Lp(LWFB_L_SWATMAX, i), THR = pv.Lp(LWFB_L_THR, i);
+    const double NPAR = pv.Lp(LWFB_L_NPAR, i), MPAR = pv.Lp(LWFB_L_MPAR, i);
+    const double E2 = 1.0 / NPAR;
+    const double THICK = pv.Lp(LWFB_L_THICK, i), STONEF = pv.Lp(LWFB_L_STONEF, i);
+    const int idn = bot ? i : i + 1;
+    const double THICK_dn = pv.Lp(LWFB_L_THICK, idn), STONEF_dn = pv.Lp(LWFB_L_STONEF, idn);
+    SETC(KC_THSAT, THSAT); SETC(KC_THR, THR); SETC(KC_DTH, THSAT - THR); SETC(KC_SWATMAX, SWATMAX);
+    SETC(KC_E1, -1.0 / MPAR); SETC(KC_E2, E2); SETC(KC_E3, NPAR / (NPAR - 1.0)); SETC(KC_E4, 1.0 - E2);
+    SETC(KC_TORT, pv.Lp(LWFB_L_TORT, i)); SETC(KC_CPSI, 9.81 * (-1.0 / pv.Lp(LWFB_L_ALPHA, i)));
+    SETC(KC_KSAT, pv.Lp(LWFB_L_KSAT, i)); SETC(KC_PSIG, pv.Lp(LWFB_L_PSIG, i));
+    SETC(KC_THICK, THICK); SETC(KC_OMS, 1 - STONEF); SETC(KC_INFRAC, pv.Lp(LWFB_L_INFRAC, i));
+    SETC(KC_THICK_DN, THICK_dn); SETC(KC_KSAT_DN, pv.Lp(LWFB_L_KSAT, idn));
+    SETC(KC_TSUM, THICK + THICK_dn); SETC(KC_THALF, (THICK + THICK_dn) / 2.0);
+    SETC(KC_STFAC, 1.0 - (STONEF + STONEF_dn) / 2.0);
+    SETC(KC_CITER, 0.01 * pv.S(LWFB_S_DSWMAX) * THICK * THSAT * (1 - STONEF));
+    BYPAR = pv.S(LWFB_S_BYPAR) == 1.0;
+    SETC(KC_WETF, BYPAR ? pv.Lp(LWFB_L_WETF, i) : 0.0);
+    SETC(KC_DZ_UP, top ? 1.0 : pv.Lp(LWFB_L_DZ, i - 1)); SETC(KC_DZ_DN, bot ? 1.0 : pv.Lp(LWFB_L_DZ, i));
+    SETC(KC_THS2, THSAT * THSAT);
+    SETC(KC_DPSIMAX, pv.S(LWFB_S_DPSIMAX)); SETC(KC_DTIMAX, pv.S(LWFB_S_DTIMAX)); SETC(KC_DRAIN, pv.S(LWFB_S_DRAIN));
+    SETC(KC_GSC, pv.S(LWFB_S_GSC)); SETC(KC_GSP, pv.S(LWFB_S_GSP)); SETC(KC_IMPERV, pv.S(LWFB_S_IMPERV));
+    SETC(KC_QFFC, pv.S(LWFB_S_QFFC)); SETC(KC_QFPAR, pv.S(LWFB_S_QFPAR));
+    SETC(KC_SWATQF, pv.S(LWFB_S_SWATQF)); SETC(KC_SWATQX, pv.S(LWFB_S_SWATQX));
+    QLAYER = (int)pv.S(LWFB_S_QLAYER);
+    const double DSLOPE = pv.S(LWFB_S_DSLOPE), LEN = pv.S(LWFB_S_LENGTH_SLOPE);
+    SLOPE = !(LEN == 0 || DSLOPE == 0);
+    const double cs = SLOPE ? lwfb_cos(DSLOPE) : 1.0, sn = SLOPE ? lwfb_sin(DSLOPE) : 0.0;   // DSLOPE used as radians (reference quirk)
+    SETC(KC_CS, cs); SETC(KC_SNRHO, sn * p_RHOWG); SETC(KC_LEN1000, 1000 * LEN);
+    SETC(KC_ARATIO, SLOPE ? THICK * (1 - STONEF) * cs / (1000 * LEN) : 0.0);
+    SETC(KC_LAM, pv.S(LWFB_S_DISPERSIVITY)); SETC(KC_VXYLEM, pv.S(LWFB_S_VXYLEM));
+  }
+  const unsigned grpmask = (N == 32) ? LFULL : (((1u << N) - 1u) << base);
 
-  // ---- ODE components of this lane: c = 0 own SWATI; c >= 1: member-level component e = i + (c-1)*N
-  //      (e = 0 GWAT, 1..8 the integrated accumulators flow, seep, srfl, slfl, byfl, dsfl, gwfl, vrfln)
-  double y[NC], yprev[NC], k1[NC], kk_[NC];
-  bool cvalid[NC];
-  int cext[NC];
+  // ---- live state: fin := u0 (then kept current at day boundaries); registers for what evolves per step
+  if (live) for (int j = i; j < L; j += N) FIN(j) = U0(j);
+  double y = U0(ix.SWATI + i), G = U0(ix.GWAT);
+  double Q[EQ], kFQ[EQ];
+  int qe[EQ];                                        // accumulator held in slot j (>= 8: none)
 #pragma unroll
-  for (int c = 0; c < NC; c++) {
-    cext[c] = (c == 0) ? -1 : i + (c - 1) * N;
-    cvalid[c] = (c == 0) || (cext[c] < 9);
-    k1[c] = 0; kk_[c] = 0; yprev[c] = 0;
+  for (int j = 0; j < EQ; j++) {
+    qe[j] = i + j * N;
+    Q[j] = qe[j] < 8 ? U0(ix.ACC + lAccPos[qe[j] & 7]) : 0.0;
+    kFQ[j] = 0;
   }
-  DayState ds;
-  for (int a = 0; a < LWFB_NACCUM; a++) ds.acc[a] = U0(ix.ACC + a);
-  y[0] = U0(ix.SWATI + i);
-#pragma unroll
-  for (int c = 1; c < NC; c++) {
-    const int e = cext[c];
-    y[c] = !cvalid[c] ? 0.0 : (e == 0 ? U0(ix.GWAT) : ds.acc[lAccPos[(e - 1) & 7]]);
-  }
-  ds.INTS = U0(ix.INTS); ds.INTR = U0(ix.INTR); ds.SNOW = U0(ix.SNOW); ds.CC = U0(ix.CC); ds.SNOWLQ = U0(ix.SNOWLQ);
-  double TRANIst = U0(ix.TRANI + i), RWUst = U0(ix.RWU), XYmm = U0(ix.XYLEM);
-  double dS[2] = {0, 0}, dG[2] = {0, 0}, dRWU[2] = {0, 0}, dXY[2] = {0, 0}, dISN[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+  double kFy = 0, kFG = 0;                           // FSAL derivative of SWATI / GWAT
+  double dS[2] = {0, 0}, dG[2] = {0, 0}, dXY[2] = {0, 0};
   if (iso) {
 #pragma unroll
-    for (int s = 0; s < 2; s++) {
-      dS[s] = U0(ix.SWATI + (s + 1) * N + i);
-      dG[s] = U0(ix.GWAT + 1 + s); dRWU[s] = U0(ix.RWU + 1 + s); dXY[s] = U0(ix.XYLEM + 1 + s);
-      dISN[0][s] = U0(ix.INTS + 1 + s); dISN[1][s] = U0(ix.INTR + 1 + s); dISN[2][s] = U0(ix.SNOW + 1 + s);
-    }
+    for (int s = 0; s < 2; s++) { dS[s] = U0(ix.SWATI + (s + 1) * N + i); dG[s] = U0(ix.GWAT + 1 + s); dXY[s] = U0(ix.XYLEM + 1 + s); }
   }
-  double TRANI = NAN, ntfli = NAN;          // frozen uptake of the layer; du_NTFLI of the previous RHS call
+  double TRANI = NAN, ntfli = NAN;                   // frozen uptake of the layer; du_NTFLI of the previous RHS call
   double RNET = NAN, SMLT = NAN, SLVP = NAN, TA = NAN;
+  double VV = 0, INFLI = 0, DSFLI = 0;               // flux caches of the last RHS (isotope step)
 
-  // value of member-level component e (held by lane e % N in slot 1 + e / N), broadcast to the group
-  auto ext_bcast = [&](const double* v, int e) {
-    const int slot = 1 + e / N;
-    double mine = v[1];
+  // value of accumulator e (held by lane e % N in slot e / N), broadcast to the group
+  auto q_bcast = [&](const double* v, int e) {
+    const int slot = e / N;
+    double mine = v[0];
 #pragma unroll
-    for (int c = 2; c < NC; c++) mine = (slot == c) ? v[c] : mine;
+    for (int j = 1; j < EQ; j++) mine = (slot == j) ? v[j] : mine;
     return bcast(mine, e % N);
   };
-
-  // full state record in the reference's order; lane i writes the entries of layer i, lane 0 the scalars
-  auto write_record = [&](double* __restrict__ dst) {
+  // registers -> fin for everything that evolves per step
+  auto flush_state = [&]() {
     if (!live) return;
-    auto W = [&](int j, double v) { dst[(int64_t)j * M + m] = v; };
-    W(ix.SWATI + i, y[0]);
-    W(ix.TRANI + i, TRANIst);
-    if (iso) {
+    FIN(ix.SWATI + i) = y;
+    if (iso) { FIN(ix.SWATI + N + i) = dS[0]; FIN(ix.SWATI + 2 * N + i) = dS[1]; }
 #pragma unroll
-      for (int s = 0; s < 2; s++) {
-        W(ix.SWATI + (s + 1) * N + i, dS[s]);
-        W(ix.TRANI + (s + 1) * N + i, U0(ix.TRANI + (s + 1) * N + i));
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < 3; q++) W(ix.AUX + q * N + i, U0(ix.AUX + q * N + i));
-#pragma unroll
-    for (int c = 1; c < NC; c++)
-      if (cvalid[c]) W(cext[c] == 0 ? ix.GWAT : ix.ACC + lAccPos[(cext[c] - 1) & 7], y[c]);
+    for (int j = 0; j < EQ; j++) if (qe[j] < 8) FIN(ix.ACC + lAccPos[qe[j] & 7]) = Q[j];
     if (top) {
-      W(ix.INTS, ds.INTS); W(ix.INTR, ds.INTR); W(ix.SNOW, ds.SNOW);
-      W(ix.RWU, RWUst); W(ix.XYLEM, XYmm); W(ix.CC, ds.CC); W(ix.SNOWLQ, ds.SNOWLQ);
-      if (iso) {
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-          W(ix.GWAT + 1 + s, dG[s]); W(ix.RWU + 1 + s, dRWU[s]); W(ix.XYLEM + 1 + s, dXY[s]);
-          W(ix.INTS + 1 + s, dISN[0][s]); W(ix.INTR + 1 + s, dISN[1][s]); W(ix.SNOW + 1 + s, dISN[2][s]);
-        }
-      }
-      for (int a = 0; a < LWFB_NACCUM; a++) {
-        bool integrated = false;
-#pragma unroll
-        for (int q = 0; q < 8; q++) integrated |= (a == lAccPos[q]);
-        if (!integrated) W(ix.ACC + a, ds.acc[a]);
-      }
+      FIN(ix.GWAT) = G;
+      if (iso) { FIN(ix.GWAT + 1) = dG[0]; FIN(ix.GWAT + 2) = dG[1]; FIN(ix.XYLEM + 1) = dXY[0]; FIN(ix.XYLEM + 2) = dXY[1]; }
     }
   };
   auto prec_delta = [&](double t, double* dp) {
@@ -173,203 +178,212 @@ __device__ void lanes_body(const DevData& d, const int lane, const int64_t warp_
 
   const double qmin = 0.2, qmax = 10.0, gamma = 0.9, beta1 = 0.14, beta2 = 0.08, qoldinit = 1e-4;
   const double t0 = (double)d.t0_day, tend = (double)(d.t0_day + d.n_days);
-  double t = t0, tprev = t0, dt = d.dt_init, dtpropose = d.dt_init, qold = qoldinit, q11 = 1.0;
+  double t = t0, dt = d.dt_init, qold = qoldinit, tstop = t0;
   const double dtmin_opt = fmax(eps_of(tend), eps_of(t0));
-  long long naccept = 0, nreject = 0, iter = 0, nf = 0;
-  bool accept = false, reeval = false;
+  const unsigned maxiters = d.maxiters > 0x7fffffffLL ? 0x7fffffffu : (unsigned)d.maxiters;
+  unsigned naccept = 0, nreject = 0, iter = 0, nf = 0;
+  bool reeval = false, at_boundary = true, cand_nan = (y != y);
   int status = LWFB_ST_OK;
-  double tstop = t0;
-  bool at_boundary = true;
   int rec = 1;
 
-  if (d.rec) write_record(d.rec);     // record 0 = raw u0
+  if (d.rec && live) for (int j = i; j < L; j += N) d.rec[(int64_t)j * M + m] = U0(j);     // record 0 = raw u0
+  __syncwarp(LFULL);
 
   for (;;) {
     const bool active = (status == LWFB_ST_OK) && (t < tend);
     if (!__any_sync(LFULL, active && live)) break;
     const bool can_step = active && !at_boundary;
-    const bool warp_steps = __any_sync(LFULL, can_step && live);
 
-    if (!warp_steps) {
+    if (!__any_sync(LFULL, can_step && live)) {
       // ============================== warp-synchronous daily callback at t = tstop
       // soil state of the own layer (SWCHEK clamps the state itself), then all layers gathered
-      double sw = y[0];
+      const double SWATMAX = LC(KC_SWATMAX), E2 = LC(KC_E2);
+      double sw = y;
       if (sw <= 0.0) sw = 0.0; else if (sw > SWATMAX) sw = SWATMAX;
-      const double w = jmin(1.0, (THSAT * sw / SWATMAX - THR) / (THSAT - THR));
+      const double w = jmin(1.0, (LC(KC_THSAT) * sw / SWATMAX - LC(KC_THR)) / LC(KC_DTH));
       const double a = jmax(w, 1.e-6);
       const double la = lwfb_log(a);
-      const double p1 = lwfb_pow_from_log(a, la, E1);
-      const double psim = CPSI * lwfb_pow(p1 - 1.0, E2);
-      const double p3 = lwfb_pow_from_log(a, la, E3);
+      const double p1 = lwfb_pow_from_log(a, la, LC(KC_E1));
+      const double psim = LC(KC_CPSI) * lwfb_pow(p1 - 1.0, E2);
+      const double p3 = lwfb_pow_from_log(a, la, LC(KC_E3));
       const double inner = 1.0 - lwfb_pow(1.0 - p3, 1.0 - E2);
-      const double kkv = KSAT * lwfb_pow_from_log(a, la, TORT) * (inner * inner);
-      const double psit = psim + PSIG;
+      const double kkv = LC(KC_KSAT) * lwfb_pow_from_log(a, la, LC(KC_TORT)) * (inner * inner);
+      const double psit = psim + LC(KC_PSIG);
       double psiti_a[NMAX], kk_a[NMAX], TRANI_a[NMAX], TRANIst_a[NMAX];
       for (int j = 0; j < N; j++) { psiti_a[j] = bcast(psit, j); kk_a[j] = bcast(kkv, j); }
       const double psim0 = bcast(psim, 0);
       const int day = (int)floor(t + 0.5);
       double nRNET, nSMLT, nSLVP, nTA, nRWU;
       int cbst = LWFB_ST_OK;
-      DayState nds = ds;
+      DayState nds;
+      nds.INTS = FIN(ix.INTS); nds.INTR = FIN(ix.INTR); nds.SNOW = FIN(ix.SNOW); nds.CC = FIN(ix.CC); nds.SNOWLQ = FIN(ix.SNOWLQ);
       cb_core<NMAX>(pv, forc + (int64_t)day * LWFB_F, t, psim0, psiti_a, kk_a, nds, TRANI_a, nRNET, nSMLT, nSLVP, nTA,
                     TRANIst_a, nRWU, cbst);
+      __syncwarp(LFULL);                            // every lane has read the day-constant states before lane 0 overwrites them
       if (active) {
-        y[0] = sw;
-        ds = nds;
-        TRANI = TRANI_a[i]; TRANIst = TRANIst_a[i]; RWUst = nRWU;
+        y = sw;
+        TRANI = TRANI_a[i];
         RNET = nRNET; SMLT = nSMLT; SLVP = nSLVP; TA = nTA;
         if (cbst != LWFB_ST_OK) status = cbst;
 #pragma unroll
-        for (int c = 1; c < NC; c++) if (cvalid[c] && cext[c] >= 1) y[c] = 0.0;
-        if (iso) {
-          double dp[2];
-          prec_delta(t, dp);
+        for (int j = 0; j < EQ; j++) Q[j] = 0.0;
+        if (live) {
+          FIN(ix.TRANI + i) = TRANIst_a[i];
+          if (top) {
+            FIN(ix.INTS) = nds.INTS; FIN(ix.INTR) = nds.INTR; FIN(ix.SNOW) = nds.SNOW; FIN(ix.CC) = nds.CC;
+            FIN(ix.SNOWLQ) = nds.SNOWLQ; FIN(ix.RWU) = nRWU;
+            for (int a2 = 0; a2 < LWFB_A_STORAGESWAT; a2++) FIN(ix.ACC + a2) = nds.acc[a2];
+            if (iso) {
+              double dp[2];
+              prec_delta(t, dp);
 #pragma unroll
-          for (int c = 0; c < 3; c++) { dISN[c][0] = dp[0]; dISN[c][1] = dp[1]; }
+              for (int s = 0; s < 2; s++) { FIN(ix.INTS + 1 + s) = dp[s]; FIN(ix.INTR + 1 + s) = dp[s]; FIN(ix.SNOW + 1 + s) = dp[s]; }
+            }
+          }
         }
         reeval = true;
         at_boundary = false;
         tstop = fmin(tstop + 1.0, tend);
       }
+      __syncwarp(LFULL);
       continue;
     }
 
-    // ============================== one attempted step (all lanes execute, only `can_step` lanes commit)
-    // loopheader!
+    // ============================== one attempted step (all lanes execute, only `do_step` lanes commit)
+    // loopheader! (dt already holds the controller's proposal / the shrunk step after a rejection)
     double dt_s = dt;
-    bool first_or_accept = (iter == 0) || accept;
-    if (iter > 0 && !accept) dt_s = dt / jmin(1 / qmin, q11 / gamma);
-    if (iter > 0 && accept) dt_s = dtpropose;
-    double yp[NC], kfirst[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      yp[c] = first_or_accept ? y[c] : yprev[c];
-      kfirst[c] = (iter > 0 && accept && !reeval) ? kk_[c] : k1[c];
-    }
-    const long long iter_s = iter + 1;
     int st_s = LWFB_ST_OK;
-    if (iter_s > d.maxiters) st_s = LWFB_ST_MAXITERS;
+    if (iter + 1u > maxiters) st_s = LWFB_ST_MAXITERS;
     {
-      // unstable_check: NaN in any SWATI of the member
-      const unsigned nanmask = __ballot_sync(LFULL, y[0] != y[0]);
-      const unsigned grp = (N == 32) ? LFULL : (((1u << N) - 1u) << base);
-      if (st_s == LWFB_ST_OK && (nanmask & grp)) st_s = LWFB_ST_UNSTABLE;
+      // unstable_check: NaN in any SWATI of the member (the state last written by the solver)
+      const unsigned nanmask = __ballot_sync(LFULL, cand_nan);
+      if (st_s == LWFB_ST_OK && (nanmask & grpmask)) st_s = LWFB_ST_UNSTABLE;
     }
     dt_s = dt_s < d.dtmax ? dt_s : d.dtmax;
-    { double dtmin_t = fmax(eps_of(t), dtmin_opt); if (dt_s < dtmin_t) dt_s = dtmin_t; }
+    { const double dtmin_t = fmax(eps_of(t), dtmin_opt); if (dt_s < dtmin_t) dt_s = dtmin_t; }
     if (dt_s > tstop - t) dt_s = tstop - t;
     if (st_s == LWFB_ST_OK && !(fabs(dt_s) > dtmin_opt)) st_s = LWFB_ST_DTMIN;
     const bool do_step = can_step && (st_s == LWFB_ST_OK);   // member-level: identical in all lanes of the group
 
     // perform_step!: rolled stage loop (s = 0 is the FSAL re-evaluation after a callback)
-    double xin[NC], kcur[NC], q_[NC][5], aE[NC];
-    double VV = 0, INFLI = 0, DSFLI = 0, nt = ntfli;
-    long long nf_s = nf;
+    double xy = y, xG = G;                           // stage inputs
+    double qy[5] = {0, 0, 0, 0, 0}, qG[5] = {0, 0, 0, 0, 0};
+    double aEy = 0, aEG = 0, kcy = kFy, kcG = kFG;
+    double kfy = kFy, kfG = kFG;                     // k1 of this attempt
+    double Sb[EQ], Sbt[EQ], kfQ[EQ], kcQ[EQ];
 #pragma unroll
-    for (int c = 0; c < NC; c++) { kcur[c] = kfirst[c]; aE[c] = 0; xin[c] = yp[c];
-#pragma unroll
-      for (int p = 0; p < 5; p++) q_[c][p] = 0; }
+    for (int j = 0; j < EQ; j++) { Sb[j] = 0; Sbt[j] = 0; kfQ[j] = kFQ[j]; kcQ[j] = kFQ[j]; }
+    double nt = ntfli;
+    unsigned nf_s = nf;
     const int s_first = __any_sync(LFULL, reeval && can_step) ? 0 : 1;
 #pragma unroll 1
     for (int s = s_first; s <= 6; s++) {
       // ---- stage input
       if (s == 1) {
         const double a = dt_s * 0.161;
+        xy = y + a * kfy; xG = G + a * kfG;
+        aEy = lBT[1] * kfy; aEG = lBT[1] * kfG;
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-          xin[c] = yp[c] + a * kfirst[c];
-          aE[c] = lBT[1] * kfirst[c];
+        for (int p = 0; p < 5; p++) { qy[p] = lCQ[1][p] * kfy; qG[p] = lCQ[1][p] * kfG; }
 #pragma unroll
-          for (int p = 0; p < 5; p++) q_[c][p] = lCQ[1][p] * kfirst[c];
-        }
+        for (int j = 0; j < EQ; j++) { Sb[j] = lB7[1] * kfQ[j]; Sbt[j] = lBT[1] * kfQ[j]; }
       } else if (s >= 2) {
+        xy = y + dt_s * qy[0]; xG = G + dt_s * qG[0];
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-          xin[c] = yp[c] + dt_s * q_[c][0];
-#pragma unroll
-          for (int p = 0; p < 4; p++) q_[c][p] = q_[c][p + 1];
-          q_[c][4] = 0;
-        }
+        for (int p = 0; p < 4; p++) { qy[p] = qy[p + 1]; qG[p] = qG[p + 1]; }
+        qy[4] = 0; qG[4] = 0;
       } else {
-#pragma unroll
-        for (int c = 0; c < NC; c++) xin[c] = yp[c];
+        xy = y; xG = G;
       }
       const double ts = (s == 0) ? t : ((s < 5) ? t + lC[s] * dt_s : t + dt_s);
       const bool skip0 = (s == 0) && !reeval;     // groups that do not need the re-evaluation keep their k1
 
       // ---- RHS f(x, ts)
-      nf_s += skip0 ? 0 : 1;
-      double sw = xin[0];
+      nf_s += skip0 ? 0u : 1u;
+      const double SWATMAX = LC(KC_SWATMAX), THR = LC(KC_THR), DTH = LC(KC_DTH), E2 = LC(KC_E2);
+      double sw = xy;
       if (sw <= 0.0) sw = 0.0; else if (sw > SWATMAX) sw = SWATMAX;
-      const double gw = ext_bcast(xin, 0);
-      const double w = jmin(1.0, (THSAT * sw / SWATMAX - THR) / (THSAT - THR));
+      const double w = jmin(1.0, (LC(KC_THSAT) * sw / SWATMAX - THR) / DTH);
       const double a = jmax(w, 1.e-6);
       const double la = lwfb_log(a);
-      const double p1 = lwfb_pow_from_log(a, la, E1);
-      const double psim = CPSI * lwfb_pow(p1 - 1.0, E2);
-      const double theta = w * (THSAT - THR) + THR;
-      const double p3 = lwfb_pow_from_log(a, la, E3);
-      const double inner = 1.0 - lwfb_pow(1.0 - p3, 1.0 - E2);
-      const double kkv = KSAT * lwfb_pow_from_log(a, la, TORT) * (inner * inner);
+      const double p1 = lwfb_pow_from_log(a, la, LC(KC_E1));
+      const double p3 = lwfb_pow_from_log(a, la, LC(KC_E3));
+      const double pT = lwfb_pow_from_log(a, la, LC(KC_TORT));
+      const double psim = LC(KC_CPSI) * lwfb_pow(p1 - 1.0, E2);
+      const double theta = w * DTH + THR;
+      const double inner = 1.0 - lwfb_pow(1.0 - p3, LC(KC_E4));
+      const double KSAT = LC(KC_KSAT);
+      const double kkv = KSAT * pT * (inner * inner);
       const double lk = lwfb_log(kkv);
-      const double psit = psim + PSIG;
+      const double psit = psim + LC(KC_PSIG);
       double BYFRAC = 0;
-      if (BYPAR) {
-        const double QFFC = pv.S(LWFB_S_QFFC), QFPAR = pv.S(LWFB_S_QFPAR);
-        BYFRAC = jmin(1.0, lwfb_pow(QFFC, 1 - (1 / QFPAR) * (w - WETF) / (1 - WETF)));
-        if (w > 0.99) BYFRAC = 1;
+      if (__any_sync(LFULL, BYPAR)) {
+        const double WETF = LC(KC_WETF);
+        double bf = jmin(1.0, lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (w - WETF) / (1 - WETF)));
+        if (w > 0.99) bf = 1;
+        BYFRAC = BYPAR ? bf : 0.0;
       }
       double SAFRAC = 0.;
       if (__any_sync(LFULL, QLAYER > 0)) {
         double sq = 0;
         for (int j = 0; j < N; j++) { const double v = bcast(sw, j); if (j < QLAYER) sq += v; }
         if (QLAYER > 0) {
-          const double QFFC = pv.S(LWFB_S_QFFC), QFPAR = pv.S(LWFB_S_QFPAR);
-          SAFRAC = jmin(1.0, lwfb_pow(QFFC, 1 - (1 / QFPAR) * (sq - pv.S(LWFB_S_SWATQF)) / (pv.S(LWFB_S_SWATQX) - pv.S(LWFB_S_SWATQF))));
+          const double SWATQF = LC(KC_SWATQF);
+          SAFRAC = jmin(1.0, lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (sq - SWATQF) / (LC(KC_SWATQX) - SWATQF)));
         }
       }
-      const double SRFL = jmin(1., (IMPERV + SAFRAC)) * (RNET + SMLT);
+      const double SRFL = jmin(1., (LC(KC_IMPERV) + SAFRAC)) * (RNET + SMLT);
       const double SLFL = RNET + SMLT - SRFL;
       DSFLI = 0;
-      if (SLOPE) {
-        const double DSLOPE = pv.S(LWFB_S_DSLOPE), LEN = pv.S(LWFB_S_LENGTH_SLOPE);
-        const double cs = lwfb_cos(DSLOPE), sn = lwfb_sin(DSLOPE);
-        const double GRAD = cs * (psim * 2 / (1000 * LEN)) + sn * p_RHOWG;
-        const double ARATIO = THICK * (1 - STONEF) * cs / (1000 * LEN);
-        const double dd = kkv * ARATIO * GRAD / p_RHOWG;
-        DSFLI = dd < 0 ? 0 : dd;
+      const bool any_slope = __any_sync(LFULL, SLOPE);
+      if (any_slope) {
+        const double GRAD = LC(KC_CS) * (psim * 2 / LC(KC_LEN1000)) + LC(KC_SNRHO);
+        const double dd = kkv * LC(KC_ARATIO) * GRAD / p_RHOWG;
+        DSFLI = (SLOPE && !(dd < 0)) ? dd : 0.0;
       }
       // first approximation of the flux to the layer below (bottom layer: drainage)
       const double psit_dn = __shfl_down_sync(LFULL, psit, 1), lk_dn = __shfl_down_sync(LFULL, lk, 1);
       double V0;
-      if (bot) V0 = (DRAIN > 0.00001) ? DRAIN * kkv * (1 - STONEF) : 0.0;
-      else if (fabs(psit - psit_dn) < DPSIMAX) V0 = 0;
-      else {
-        double kkmean = lwfb_exp((THICK_dn * lk + THICK * lk_dn) / (THICK + THICK_dn));
-        kkmean = jmin(jmin(kkmean, KSAT), KSAT_dn);
-        const double grad = (psit - psit_dn) / ((THICK + THICK_dn) / 2.0);
-        V0 = (grad * kkmean / p_RHOWG) * (1.0 - (STONEF + STONEF_dn) / 2.0);
+      {
+        const double THICK = LC(KC_THICK), DRAIN = LC(KC_DRAIN);
+        double kkmean = lwfb_exp((LC(KC_THICK_DN) * lk + THICK * lk_dn) / LC(KC_TSUM));
+        kkmean = jmin(jmin(kkmean, KSAT), LC(KC_KSAT_DN));
+        const double grad = (psit - psit_dn) / LC(KC_THALF);
+        const double vd = (grad * kkmean / p_RHOWG) * LC(KC_STFAC);
+        const double vb = (DRAIN > 0.00001) ? DRAIN * kkv * LC(KC_OMS) : 0.0;
+        V0 = bot ? vb : ((fabs(psit - psit_dn) < LC(KC_DPSIMAX)) ? 0.0 : vd);
       }
       const double V0_up = __shfl_up_sync(LFULL, V0, 1);        // prior flux from the layer above (unused at the top)
       // ITER: min-chain over the layers in index order (the clamp to DTIMIN makes the order matter)
-      const double DTRI = 1.0 - fmod(ts, 1.0);
-      double DTI = jmin(DTRI, DTIMAX);
+      const double DTRI = 1.0 - (ts - floor(ts));                // = 1 - fmod(ts, 1) for ts >= 0
+      double DTI = jmin(DTRI, LC(KC_DTIMAX));
       {
-        const double c1 = CITER / jmax(0.000001, fabs(nt));
-        const double c2 = ((THR - theta) * THICK) / nt / 1.30;
-        const unsigned negm = __ballot_sync(LFULL, nt < 0);
-        double DTINEW = DTI;
-        for (int j = 0; j < N; j++) {
-          DTINEW = jmin(DTINEW, bcast(c1, j));
-          const double c2j = bcast(c2, j);
-          if ((negm >> (base + j)) & 1u) {
-            DTINEW = jmin(DTINEW, c2j);
-            if (DTINEW < p_DTIMIN) DTINEW = p_DTIMIN;
+        const double c1 = LC(KC_CITER) / jmax(0.000001, fabs(nt));
+        const double c2 = ((THR - theta) * LC(KC_THICK)) / nt / 1.30;
+        const bool neg = nt < 0;
+        const double v = neg ? (c2 < c1 ? c2 : c1) : c1;
+        // fast path: no NaN and nothing below DTIMIN anywhere => the chain is a plain minimum
+        const bool slow = (c1 != c1) || (neg && (c2 != c2)) || !(v >= p_DTIMIN) || !(DTI >= p_DTIMIN);
+        if (__any_sync(LFULL, slow)) {
+          const unsigned negm = __ballot_sync(LFULL, neg);
+          double DTINEW = DTI;
+          for (int j = 0; j < N; j++) {
+            DTINEW = jmin(DTINEW, bcast(c1, j));
+            const double c2j = bcast(c2, j);
+            if ((negm >> (base + j)) & 1u) {
+              DTINEW = jmin(DTINEW, c2j);
+              if (DTINEW < p_DTIMIN) DTINEW = p_DTIMIN;
+            }
           }
+          if (DTINEW < DTI) DTI = DTINEW;
+        } else {
+          double gm = v;
+          for (int j = 0; j < N; j++) { const double vj = bcast(v, j); gm = vj < gm ? vj : gm; }
+          if (gm < DTI) DTI = gm;
         }
-        if (DTINEW < DTI) DTI = DTINEW;
       }
       // INFLOW
+      const double INFRAC = LC(KC_INFRAC);
       double BYFLI = SLFL * INFRAC * BYFRAC;
       INFLI = SLFL * INFRAC * (1.0 - BYFRAC);
       VV = V0;
@@ -419,143 +433,176 @@ __device__ void lanes_body(const DevData& d, const int lane, const int64_t warp_
       else du0 = VV_up + INFLI - VV - DSFLI - TRANI;
       const double VN = bcast(VV, N - 1);
       double GWFL, SEEP;
-      if (GSC < 1.0e-8) { SEEP = GSP * VN; GWFL = VN - SEEP; }
-      else {
-        SEEP = gw * GSC * GSP;
-        GWFL = gw * GSC * (1. - GSP);
-        if (gw - (GWFL + SEEP) * 1 < 0) { SEEP = gw / 1 * GSP; GWFL = gw / 1 * (1. - GSP); }
+      {
+        const double GSC = LC(KC_GSC), GSP = LC(KC_GSP);
+        if (GSC < 1.0e-8) { SEEP = GSP * VN; GWFL = VN - SEEP; }
+        else {
+          SEEP = xG * GSC * GSP;
+          GWFL = xG * GSC * (1. - GSP);
+          if (xG - (GWFL + SEEP) * 1 < 0) { SEEP = xG / 1 * GSP; GWFL = xG / 1 * (1. - GSP); }
+        }
       }
       double sby = 0, sds = 0;
-      for (int j = 0; j < N; j++) sby += bcast(BYFLI, j);
-      if (__any_sync(LFULL, SLOPE)) for (int j = 0; j < N; j++) sds += bcast(DSFLI, j);
-      double kn[NC];
-      kn[0] = du0;
+      if (__any_sync(LFULL, BYFLI != 0.0)) for (int j = 0; j < N; j++) sby += bcast(BYFLI, j);
+      if (any_slope) for (int j = 0; j < N; j++) sds += bcast(DSFLI, j);
+      const double kny = du0, knG = VN - GWFL - SEEP;
+      double knQ[EQ];
 #pragma unroll
-      for (int c = 1; c < NC; c++) {
-        const int e = cext[c];
-        double v = VN - GWFL - SEEP;                       // e == 0: GWAT
-        v = (e == 1) ? SRFL + sby + sds + GWFL : v;
-        v = (e == 2) ? SEEP : v;
-        v = (e == 3) ? SRFL : v;
-        v = (e == 4) ? SLFL : v;
-        v = (e == 5) ? sby : v;
-        v = (e == 6) ? sds : v;
-        v = (e == 7) ? GWFL : v;
-        v = (e == 8) ? VN : v;
-        kn[c] = cvalid[c] ? v : 0.0;
+      for (int j = 0; j < EQ; j++) {
+        const int e = qe[j];
+        double v = SRFL + sby + sds + GWFL;                // e == 0: flow
+        v = (e == 1) ? SEEP : v;
+        v = (e == 2) ? SRFL : v;
+        v = (e == 3) ? SLFL : v;
+        v = (e == 4) ? sby : v;
+        v = (e == 5) ? sds : v;
+        v = (e == 6) ? GWFL : v;
+        v = (e == 7) ? VN : v;
+        knQ[j] = (e < 8) ? v : 0.0;
       }
       if (!skip0) nt = du0;
       // ---- end of RHS
 
       if (s == 0) {
+        if (!skip0) {
+          kfy = kny; kfG = knG;
 #pragma unroll
-        for (int c = 0; c < NC; c++) { kfirst[c] = skip0 ? kfirst[c] : kn[c]; }
+          for (int j = 0; j < EQ; j++) kfQ[j] = knQ[j];
+        }
       } else {
         const int ks = s + 1;
+        aEy = aEy + lBT[ks] * kny; aEG = aEG + lBT[ks] * knG;
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-          aE[c] = aE[c] + lBT[ks] * kn[c];
+        for (int p = 0; p < 5; p++)
+          if (ks + 1 + p <= 7) { qy[p] = qy[p] + lCQ[ks][p] * kny; qG[p] = qG[p] + lCQ[ks][p] * knG; }
 #pragma unroll
-          for (int p = 0; p < 5; p++) if (ks + 1 + p <= 7) q_[c][p] = q_[c][p] + lCQ[ks][p] * kn[c];
-          kcur[c] = kn[c];
+        for (int j = 0; j < EQ; j++) {
+          if (ks <= 6) Sb[j] = Sb[j] + lB7[ks] * knQ[j];
+          Sbt[j] = Sbt[j] + lBT[ks] * knQ[j];
+          kcQ[j] = knQ[j];
         }
-        if (s == 6) xin[0] = sw;      // the new state u: SWCHEK clamped it in place
+        kcy = kny; kcG = knG;
+        if (s == 6) xy = sw;          // the new state u: SWCHEK clamped it in place
       }
     }
     // residuals + norm_to_use: sequential chain SWATI[0..N-1], GWAT, 8 accumulators (oracle order)
-    double r2[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const double ut = dt_s * aE[c];
-      const double r = ut / (d.abstol + jmax(fabs(yp[c]), fabs(xin[c])) * d.reltol);
-      r2[c] = r * r;
-    }
+    double Qn[EQ], r2Q[EQ];
     double ss = 0;
-    for (int j = 0; j < N; j++) ss += bcast(r2[0], j);
+    {
+      const double abstol = d.abstol, reltol = d.reltol;
+      double r = (dt_s * aEy) / (abstol + jmax(fabs(y), fabs(xy)) * reltol);
+      const double r2y = r * r;
+      r = (dt_s * aEG) / (abstol + jmax(fabs(G), fabs(xG)) * reltol);
+      const double r2G = r * r;
+#pragma unroll
+      for (int j = 0; j < EQ; j++) {
+        Qn[j] = Q[j] + dt_s * Sb[j];
+        r = (dt_s * Sbt[j]) / (abstol + jmax(fabs(Q[j]), fabs(Qn[j])) * reltol);
+        r2Q[j] = r * r;
+      }
+      for (int j = 0; j < N; j++) ss += bcast(r2y, j);
+      ss += r2G;
 #pragma unroll 1
-    for (int e = 0; e < 9; e++) ss += ext_bcast(r2, e);
+      for (int e = 0; e < 8; e++) ss += q_bcast(r2Q, e);
+    }
     const double EEst = sqrt(ss / (double)(3 * N + 39));
     // loopfooter!: PI controller
-    const double ttmp = t + dt_s;
-    double q, q11n = q11;
+    double q, q11 = 1.0;
     if (EEst == 0.0) q = 1 / qmax;
     else {
-      q11n = fastpow(EEst, beta1);
-      q = q11n / fastpow(qold, beta2);
+      q11 = fastpow(EEst, beta1);
+      q = q11 / fastpow(qold, beta2);
       q = jmax(1 / qmax, jmin(1 / qmin, q / gamma));
     }
     const bool acc_s = (EEst <= 1.0);
 
     // ---- commit
     if (can_step) {
-      // what loopheader / the checks did
-      iter = iter_s;
+      iter = iter + 1u;
       if (st_s != LWFB_ST_OK) status = st_s;
     }
+    const bool accepted = do_step && acc_s;
+    double dtt = 0;
     if (do_step) {
+      nf = nf_s; ntfli = nt;
+      kFy = kfy; kFG = kfG;
 #pragma unroll
-      for (int c = 0; c < NC; c++) { yprev[c] = yp[c]; k1[c] = kfirst[c]; kk_[c] = kcur[c]; y[c] = xin[c]; }
-      dt = dt_s; nf = nf_s; ntfli = nt; q11 = q11n;
+      for (int j = 0; j < EQ; j++) kFQ[j] = kfQ[j];
       reeval = false;
-      accept = acc_s;
+      cand_nan = (xy != xy);
       if (acc_s) {
         naccept++;
+        y = xy; G = xG;
+        kFy = kcy; kFG = kcG;                       // FSAL
+#pragma unroll
+        for (int j = 0; j < EQ; j++) { Q[j] = Qn[j]; kFQ[j] = kcQ[j]; }
         qold = jmax(EEst, qoldinit);
         const double dtnew = dt_s / q;
-        tprev = t;
-        t = (fabs(ttmp - tstop) < 100 * eps_of(fmax(t, tstop))) ? tstop : ttmp;
-        dtpropose = d.dtmax < dtnew ? d.dtmax : dtnew;
-        { double dtmin_t = fmax(eps_of(t), dtmin_opt); if (dtpropose < dtmin_t) dtpropose = dtmin_t; }
+        const double ttmp = t + dt_s;
+        const double tn = (fabs(ttmp - tstop) < 100 * eps_of(fmax(t, tstop))) ? tstop : ttmp;
+        dtt = tn - t;
+        t = tn;
+        dt = d.dtmax < dtnew ? d.dtmax : dtnew;
+        { const double dtmin_t = fmax(eps_of(t), dtmin_opt); if (dt < dtmin_t) dt = dtmin_t; }
       } else {
         nreject++;
+        dt = dt_s / jmin(1 / qmin, q11 / gamma);
       }
     }
-    const bool accepted = do_step && acc_s;
     const bool at_stop = accepted && (t == tstop);
     // ---- record + balance at the day boundary (saved before the callbacks and before this step's isotope update)
     if (__any_sync(LFULL, at_stop)) {
       double Ssum = 0;
-      for (int j = 0; j < N; j++) Ssum += bcast(y[0], j);
-      double ev[9];
+      for (int j = 0; j < N; j++) Ssum += bcast(y, j);
+      double ev[8];
 #pragma unroll 1
-      for (int e = 0; e < 9; e++) ev[e] = ext_bcast(y, e);
+      for (int e = 0; e < 8; e++) ev[e] = q_bcast(Q, e);
+      if (at_stop) flush_state();
+      __syncwarp(LFULL);
+      double bs = 0, bt = 0, Wt = 0;
       if (at_stop) {
-        if (d.rec) write_record(d.rec + (int64_t)rec * L * M);
+        if (d.rec && live) {
+          double* __restrict__ dst = d.rec + (int64_t)rec * L * M;
+          for (int j = i; j < L; j += N) dst[(int64_t)j * M + m] = FIN(j);
+        }
         rec++;
         if (t < tend) {
-          double* a = ds.acc;   // LWFBrook90R_check_balance_errors!
-          const double Wt = ds.INTR + ds.INTS + ds.SNOW + Ssum + ev[0];
-          const double qin = 0 + (ev[4] - ev[5]);
-          const double qout = ev[8] + ev[6] + a[LWFB_A_CUM_D_TRAN] + a[LWFB_A_CUM_D_SLVP];
-          const double qin_t = a[LWFB_A_CUM_D_PREC];
-          const double qout_t = a[LWFB_A_CUM_D_EVAP] + ev[1] + ev[2];
-          a[LWFB_A_BALERD_SWAT] = (qin - qout) - (Ssum - a[LWFB_A_STORAGESWAT]);
-          a[LWFB_A_BALERD_TOTAL] = (qin_t - qout_t) - (Wt - a[LWFB_A_STORAGEWATER]);
-          a[LWFB_A_STORAGESWAT] = Ssum;
-          a[LWFB_A_STORAGEWATER] = Wt;
+          // LWFBrook90R_check_balance_errors!
+          Wt = FIN(ix.INTR) + FIN(ix.INTS) + FIN(ix.SNOW) + Ssum + G;
+          const double qin = 0 + (ev[3] - ev[4]);
+          const double qout = ev[7] + ev[5] + FIN(ix.ACC + LWFB_A_CUM_D_TRAN) + FIN(ix.ACC + LWFB_A_CUM_D_SLVP);
+          const double qin_t = FIN(ix.ACC + LWFB_A_CUM_D_PREC);
+          const double qout_t = FIN(ix.ACC + LWFB_A_CUM_D_EVAP) + ev[0] + ev[1];
+          bs = (qin - qout) - (Ssum - FIN(ix.ACC + LWFB_A_STORAGESWAT));
+          bt = (qin_t - qout_t) - (Wt - FIN(ix.ACC + LWFB_A_STORAGEWATER));
           at_boundary = true;
         }
       }
+      __syncwarp(LFULL);                            // all reads of the old balance entries done
+      if (at_stop && t < tend && top && live) {
+        FIN(ix.ACC + LWFB_A_BALERD_SWAT) = bs; FIN(ix.ACC + LWFB_A_BALERD_TOTAL) = bt;
+        FIN(ix.ACC + LWFB_A_STORAGESWAT) = Ssum; FIN(ix.ACC + LWFB_A_STORAGEWATER) = Wt;
+      }
+      __syncwarp(LFULL);
     }
     // ---- isotope advection-dispersion step with the flux caches of stage 7
     const bool do_ade = accepted && iso && (t != tstop || t < tend);
     if (__any_sync(LFULL, do_ade)) {
       double dp[2];
       prec_delta(t, dp);
-      const double dtt = t - tprev;
-      const double S1 = y[0];
-      const double w1 = jmin(1.0, (THSAT * S1 / SWATMAX - THR) / (THSAT - THR));
-      const double th1 = w1 * (THSAT - THR) + THR;
+      const double THR = LC(KC_THR), DTH = LC(KC_DTH);
+      const double S1 = y;
+      const double w1 = jmin(1.0, (LC(KC_THSAT) * S1 / LC(KC_SWATMAX) - THR) / DTH);
+      const double th1 = w1 * DTH + THR;
       const double Tk = TA + 273.15;
-      const double Lam = pv.S(LWFB_S_DISPERSIVITY), VXYLEM = pv.S(LWFB_S_VXYLEM);
       const double ee = lwfb_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
       double sumT = 0;
       for (int j = 0; j < N; j++) sumT += bcast(TRANI, j);
-      const double tauth = lwfb_pow(th1, 7.0 / 3) / (THSAT * THSAT);
-      const double aq = Lam * fabs(VV / 1000);
-      const double G1 = ext_bcast(y, 0);
+      const double tauth = lwfb_pow(th1, 7.0 / 3) / LC(KC_THS2);
+      const double aq = LC(KC_LAM) * fabs(VV / 1000);
       const double VN = bcast(VV, N - 1);
       const double VV_up = __shfl_up_sync(LFULL, VV, 1);
+      const double DZ_up = LC(KC_DZ_UP), DZ_dn = LC(KC_DZ_DN), VXYLEM = LC(KC_VXYLEM);
 #pragma unroll
       for (int s = 0; s < 2; s++) {
         const double R = s == 0 ? R18 : R2H;
@@ -581,11 +628,11 @@ __device__ void lanes_body(const DevData& d, const int lane, const int64_t warp_
         const double dd = dxdt_to_dddt(dC, C, R);
         const double CN = bcast(C, N - 1);
         double ddG;
-        if ((G1 == 0) && (VN == 0)) ddG = NAN;
-        else if ((G1 == 0) && (VN > 0)) ddG = 0;
+        if ((G == 0) && (VN == 0)) ddG = NAN;
+        else if ((G == 0) && (VN > 0)) ddG = 0;
         else {
           const double CG = d_to_x(dG[s], R);
-          const double dCG = VN / G1 * (CN - CG);
+          const double dCG = VN / G * (CN - CG);
           ddG = dxdt_to_dddt(dCG, CG, R);
         }
         double swt = 0;
@@ -596,8 +643,8 @@ __device__ void lanes_body(const DevData& d, const int lane, const int64_t warp_
         if (do_ade) {
           dG[s] += dtt * ddG;
           dS[s] += dtt * dd;
-          dRWU[s] = dRW;
           dXY[s] += dtt * ddxy;
+          if (top && live) FIN(ix.RWU + 1 + s) = dRW;
         }
       }
     }
@@ -609,7 +656,7 @@ __device__ void lanes_body(const DevData& d, const int lane, const int64_t warp_
         for (int j = i; j < L; j += N) dst[(int64_t)j * M + m] = NAN;
       }
     }
-    write_record(d.fin);
+    flush_state();
     if (top) {
       d.status[m] = status;
       d.counters[(int64_t)LWFB_C_NACCEPT * M + m] = naccept;
@@ -620,9 +667,10 @@ __device__ void lanes_body(const DevData& d, const int lane, const int64_t warp_
 }
 
 #ifdef __CUDACC__
-template <int NMAX, int EMAX>
-__global__ void __launch_bounds__(128) integrate_lanes(DevData d) {
-  lanes_body<NMAX, EMAX>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+template <int NMAX, int EQ>
+__global__ void __launch_bounds__(LWFB_LANES_BLOCK, LWFB_LANES_MINBLOCKS) integrate_lanes(DevData d) {
+  extern __shared__ double lanes_smem[];
+  lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + threadIdx.x);
 }
 #endif
 

@@ -50,6 +50,7 @@ template <typename T> static inline T simt_shfl(T v, int src, int op) { return s
 #define __ballot_sync(mask, p) simt::vote((p), LWFB_OP_ID)
 #define __any_sync(mask, p) (simt::vote((p), LWFB_OP_ID) != 0u)
 #define __all_sync(mask, p) (simt::vote((p), LWFB_OP_ID) == 0xffffffffu)
+#define __syncwarp(mask) ((void)simt::vote(true, LWFB_OP_ID))
 #else
 #include <cuda_runtime.h>
 #endif

@@ -130,14 +130,16 @@ struct Job {
   std::atomic<long> ops{0};
 };
 
-struct WarpArg { const lwfb::DevData* d; int64_t warp_g; };
+struct WarpArg { const lwfb::DevData* d; int64_t warp_g; double* cst; };
 
 void lanes_entry(void* a, int lane) {
   const WarpArg* wa = (const WarpArg*)a;
   const lwfb::DevData& d = *wa->d;
-  if (d.N <= 4) lwfb::lanes_body<8, 3>(d, lane, wa->warp_g);
-  else if (d.N <= 8) lwfb::lanes_body<8, 2>(d, lane, wa->warp_g);
-  else lwfb::lanes_body<32, 1>(d, lane, wa->warp_g);
+  double* cst = wa->cst + lane;                  // this lane's column of the "shared memory" constant block
+  if (d.N == 3) lwfb::lanes_body<8, 3>(d, lane, wa->warp_g, cst);
+  else if (d.N < 8) lwfb::lanes_body<8, 2>(d, lane, wa->warp_g, cst);
+  else if (d.N == 8) lwfb::lanes_body<8, 1>(d, lane, wa->warp_g, cst);
+  else lwfb::lanes_body<32, 1>(d, lane, wa->warp_g, cst);
 }
 
 void* worker(void* p) {
@@ -146,7 +148,8 @@ void* worker(void* p) {
     int64_t u = j->next.fetch_add(1);
     if (u >= j->n_units) break;
     if (j->kernel == 0) {
-      WarpArg wa{&j->d, u};
+      std::vector<double> cst((size_t)lwfb::KC_COUNT * LWFB_LANES_BLOCK);
+      WarpArg wa{&j->d, u, cst.data()};
       run_warp(lanes_entry, &wa);
     } else {
       lwfb::integrate_member<0>(j->d, u);
