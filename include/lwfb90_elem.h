@@ -58,28 +58,51 @@ LWFB_ELEM double lwfb_i2d(int64_t i) {
 #define LWFB_PIO2_LO2 -0x1.f1976b7ed8fbcp-110
 #define LWFB_2OPI 0x1.45f306dc9c883p-1
 
+/* Polynomial coefficients.  On the device they live in constant memory so that they are read as
+ * constant-bank operands of the DFMA instructions (a literal would cost two UMOV instructions each);
+ * on the host they are ordinary static tables.  Same values, same order of operations. */
+#define LWFB_EXP_COEF  { 1.0 / 87178291200.0, 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, \
+                         1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, \
+                         1.0 / 24.0, 1.0 / 6.0, 0.5, LWFB_INVLN2, LWFB_LN2_HI, LWFB_LN2_LO, \
+                         709.782712893384, -745.1332191019412 }
+#define LWFB_LOG_COEF  { 2.0 / 25.0, 2.0 / 23.0, 2.0 / 21.0, 2.0 / 19.0, 2.0 / 17.0, 2.0 / 15.0, 2.0 / 13.0, 2.0 / 11.0, \
+                         2.0 / 9.0, 2.0 / 7.0, 2.0 / 5.0, 2.0 / 3.0, LWFB_LN2_HI, LWFB_LN2_LO, 0x1.6a09e667f3bcdp+0 }
+#if defined(__CUDACC__)
+static __constant__ double lwfb_exp_coef_d[18] = LWFB_EXP_COEF;
+static __constant__ double lwfb_log_coef_d[15] = LWFB_LOG_COEF;
+#endif
+static const double lwfb_exp_coef_h[18] = LWFB_EXP_COEF;
+static const double lwfb_log_coef_h[15] = LWFB_LOG_COEF;
+#if defined(__CUDA_ARCH__)
+#define LWFB_EC(i) lwfb_exp_coef_d[i]
+#define LWFB_LGC(i) lwfb_log_coef_d[i]
+#else
+#define LWFB_EC(i) lwfb_exp_coef_h[i]
+#define LWFB_LGC(i) lwfb_log_coef_h[i]
+#endif
+
 /* e^x: k = rint(x/ln2), Cody-Waite reduction with fma, degree-14 Taylor polynomial on |r| <= ln2/2.
  * Written without branches (selects only) so that several independent calls can be interleaved by the
  * instruction scheduler: the polynomial runs on the argument clamped to [-746, 710] and the special
  * results (NaN, overflow, underflow) are selected at the end. */
 LWFB_ELEM double lwfb_exp(double x) {
   double xs = fmin(fmax(x, -746.0), 710.0);   /* fmin/fmax drop a NaN argument: xs is always finite */
-  double kf = rint(xs * LWFB_INVLN2);
-  double r = fma(-kf, LWFB_LN2_HI, xs);
-  r = fma(-kf, LWFB_LN2_LO, r);
-  double q = 1.0 / 87178291200.0;           /* 1/14! */
-  q = fma(q, r, 1.0 / 6227020800.0);        /* 1/13! */
-  q = fma(q, r, 1.0 / 479001600.0);
-  q = fma(q, r, 1.0 / 39916800.0);
-  q = fma(q, r, 1.0 / 3628800.0);
-  q = fma(q, r, 1.0 / 362880.0);
-  q = fma(q, r, 1.0 / 40320.0);
-  q = fma(q, r, 1.0 / 5040.0);
-  q = fma(q, r, 1.0 / 720.0);
-  q = fma(q, r, 1.0 / 120.0);
-  q = fma(q, r, 1.0 / 24.0);
-  q = fma(q, r, 1.0 / 6.0);
-  q = fma(q, r, 0.5);
+  double kf = rint(xs * LWFB_EC(13));
+  double r = fma(-kf, LWFB_EC(14), xs);
+  r = fma(-kf, LWFB_EC(15), r);
+  double q = LWFB_EC(0);                    /* 1/14! */
+  q = fma(q, r, LWFB_EC(1));                /* 1/13! */
+  q = fma(q, r, LWFB_EC(2));
+  q = fma(q, r, LWFB_EC(3));
+  q = fma(q, r, LWFB_EC(4));
+  q = fma(q, r, LWFB_EC(5));
+  q = fma(q, r, LWFB_EC(6));
+  q = fma(q, r, LWFB_EC(7));
+  q = fma(q, r, LWFB_EC(8));
+  q = fma(q, r, LWFB_EC(9));
+  q = fma(q, r, LWFB_EC(10));
+  q = fma(q, r, LWFB_EC(11));
+  q = fma(q, r, LWFB_EC(12));
   double res = 1.0 + fma(r * r, q, r);
   int k = (int)kf;
   /* two-step scaling outside the normal exponent range; adj = 0 multiplies by 1.0 (exact) */
@@ -87,8 +110,8 @@ LWFB_ELEM double lwfb_exp(double x) {
   res = res * lwfb_i2d((int64_t)(adj + 1023) << 52);
   k -= adj;
   res = res * lwfb_i2d((int64_t)(k + 1023) << 52);
-  res = x > 709.782712893384 ? INFINITY : res;
-  res = x < -745.1332191019412 ? 0.0 : res;
+  res = x > LWFB_EC(16) ? INFINITY : res;
+  res = x < LWFB_EC(17) ? 0.0 : res;
   return x != x ? x : res;
 }
 
@@ -103,28 +126,28 @@ LWFB_ELEM double lwfb_log(double x) {
   e += (int)((ix >> 52) & 0x7ff) - 1023;
   ix = (ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
   double m = lwfb_i2d(ix);
-  int big = m > 0x1.6a09e667f3bcdp+0;
+  int big = m > LWFB_LGC(14);
   m = big ? m * 0.5 : m;
   e += big;
   double f = m - 1.0;
   double s = f / (2.0 + f);
   double z = s * s;
-  double R = 2.0 / 25.0;
-  R = fma(R, z, 2.0 / 23.0);
-  R = fma(R, z, 2.0 / 21.0);
-  R = fma(R, z, 2.0 / 19.0);
-  R = fma(R, z, 2.0 / 17.0);
-  R = fma(R, z, 2.0 / 15.0);
-  R = fma(R, z, 2.0 / 13.0);
-  R = fma(R, z, 2.0 / 11.0);
-  R = fma(R, z, 2.0 / 9.0);
-  R = fma(R, z, 2.0 / 7.0);
-  R = fma(R, z, 2.0 / 5.0);
-  R = fma(R, z, 2.0 / 3.0);
+  double R = LWFB_LGC(0);
+  R = fma(R, z, LWFB_LGC(1));
+  R = fma(R, z, LWFB_LGC(2));
+  R = fma(R, z, LWFB_LGC(3));
+  R = fma(R, z, LWFB_LGC(4));
+  R = fma(R, z, LWFB_LGC(5));
+  R = fma(R, z, LWFB_LGC(6));
+  R = fma(R, z, LWFB_LGC(7));
+  R = fma(R, z, LWFB_LGC(8));
+  R = fma(R, z, LWFB_LGC(9));
+  R = fma(R, z, LWFB_LGC(10));
+  R = fma(R, z, LWFB_LGC(11));
   R = R * z;
   double hfsq = 0.5 * f * f;
   double dk = (double)e;
-  double res = dk * LWFB_LN2_HI - ((hfsq - (s * (hfsq + R) + dk * LWFB_LN2_LO)) - f);
+  double res = dk * LWFB_LGC(12) - ((hfsq - (s * (hfsq + R) + dk * LWFB_LGC(13))) - f);
   res = x == INFINITY ? x : res;
   res = x == 0.0 ? -INFINITY : res;
   res = x < 0.0 ? NAN : res;

@@ -312,7 +312,14 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
     const int64_t warps = (d.M + mpw - 1) / mpw;
     const int wpb = LWFB_LANES_BLOCK / 32;
     const unsigned lgrid = (unsigned)((warps + wpb - 1) / wpb);
-    const size_t smem = (size_t)KC_COUNT * LWFB_LANES_BLOCK * sizeof(double);
+    size_t smem = (size_t)KC_COUNT * LWFB_LANES_BLOCK * sizeof(double);
+    if (const char* pad = getenv("LWFB_LANES_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // profiling knob: fewer resident blocks
+    if (smem > 48 * 1024) {
+      cudaFuncSetAttribute(integrate_lanes<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(integrate_lanes<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(integrate_lanes<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(integrate_lanes<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     if (d.N == 3) integrate_lanes<8, 3><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
     else if (d.N < 8) integrate_lanes<8, 2><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
     else if (d.N == 8) integrate_lanes<8, 1><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);

@@ -28,6 +28,23 @@ __device__ constexpr double p_WTOMJ = 0.0864, p_ETOM = 0.4085, p_CPRHO = 1240., 
 // Julia min/max propagate NaN (fmin/fmax do not)
 __device__ __forceinline__ double jmin(double a, double b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
 __device__ __forceinline__ double jmax(double a, double b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
+// the same against a bound c that is known not to be NaN: one compare (NaN in x fails it and is passed on)
+__device__ __forceinline__ double jminc(double x, double c) { return !(x >= c) ? x : c; }
+__device__ __forceinline__ double jmaxc(double x, double c) { return !(x <= c) ? x : c; }
+// jmax(|a|, |b|): for sign-cleared doubles the integer order of the bit patterns is the numeric order with
+// every NaN above +inf, so an integer max propagates NaN and stays off the FP64 pipe
+__device__ __forceinline__ double jmax_abs(double a, double b) {
+  const long long ia = __double_as_longlong(fabs(a)), ib = __double_as_longlong(fabs(b));
+  return __longlong_as_double(ia > ib ? ia : ib);
+}
+// a / b where the dividend is often exactly zero and b is normally positive and finite.  The hardware division
+// sequence leaves its fast path for a zero dividend (a ~60-instruction subroutine); 0 / b = a (sign kept) for
+// positive finite b, so that case is answered without dividing.  Bit-identical to a / b for all arguments.
+__device__ __forceinline__ double div_z(double a, double b) {
+  const bool z = (a == 0.0) && (b > 0.0) && (b < INFINITY);
+  const double q = (z ? 1.0 : a) / b;
+  return z ? a : q;
+}
 
 struct DevData {
   int64_t M;        // members
@@ -864,7 +881,7 @@ __device__ constexpr double R18 = 2005.2e-6, R2H = 155.76e-6;
 __device__ __forceinline__ double d_to_x(double d, double R) { return 1 / (1 + 1 / (R * (d / 1000 + 1))); }
 __device__ __forceinline__ double x_to_d(double x, double R) { return (1 / (R * (1 / x - 1)) - 1) * 1000; }
 __device__ __forceinline__ double dxdt_to_dddt(double dxdt, double x, double R) {
-  return dxdt * 1 / R * 1 / ((x - 1) * (x - 1)) * 1000;
+  return div_z(div_z(dxdt * 1, R) * 1, ((x - 1) * (x - 1))) * 1000;    // dxdt * 1 / R * 1 / (x-1)^2 * 1000
 }
 
 // isotope state carried between steps: delta of SWATI[N], GWAT, RWU, XYLEM for 18O and 2H

@@ -49,9 +49,26 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
                                        LWFB_A_BYFL, LWFB_A_DSFL, LWFB_A_GWFL, LWFB_A_VRFLN};
 
 #define LFULL 0xffffffffu
-#define LWFB_LANES_BLOCK 128        // threads per block = stride of the shared-memory constant columns
+#ifndef LWFB_LANES_BLOCK
+#define LWFB_LANES_BLOCK 256        // threads per block = stride of the shared-memory constant columns
+#endif
 #ifndef LWFB_LANES_MINBLOCKS
-#define LWFB_LANES_MINBLOCKS 4      // resident blocks per SM the register allocation is sized for
+#define LWFB_LANES_MINBLOCKS (512 / LWFB_LANES_BLOCK)   // resident blocks per SM the register allocation is sized for
+#endif
+// Block-level control votes: the warps of a block advance in LOCK STEP.  "Does anybody step / need the callback /
+// need the FSAL re-evaluation" are block-uniform decisions taken with __syncthreads_or, and every Runge-Kutta stage
+// starts with a barrier.  Reason (profiles/r01_*): the stepping loop is ~40 KB of straight-line code; free-running
+// warps each stream it through the instruction caches on their own and spent 7.8 cycles per issued instruction
+// waiting for instruction fetch (IPC 1.0 per SM).  In lock step the warps that share a scheduler fetch the same
+// lines at the same time: fetch stalls drop to 0.2-0.6 cycles per instruction and IPC doubles.  The price is that a
+// block waits for its slowest member at every step (a few % more executed instructions).  Results do not depend on
+// the grouping: a member that waits does not change state.  -DLWFB_LANES_FREE_RUNNING restores warp-level votes.
+#if !defined(LWFB_LANES_FREE_RUNNING) && defined(__CUDACC__)
+#define LWFB_VOTE_ANY(p) (__syncthreads_or((p) ? 1 : 0) != 0)
+#define LWFB_STAGE_SYNC() __syncthreads()
+#else
+#define LWFB_VOTE_ANY(p) __any_sync(LFULL, (p))
+#define LWFB_STAGE_SYNC() ((void)0)
 #endif
 
 // per-thread constant column (shared memory): element k of this thread is cst[k * LWFB_LANES_BLOCK]
@@ -80,6 +97,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   const bool live = lane_valid && m_raw < M;
   const int64_t m = (m_raw < M) ? m_raw : M - 1;
   const bool top = (i == 0), bot = (i == N - 1);
+  const bool nodn = bot || !lane_valid, noup = top || !lane_valid;   // lanes without a real neighbour below / above
   const int L = d.L;
   const bool iso = d.iso != 0;
   const SIdx ix(N, d.iso);
@@ -191,17 +209,17 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 
   for (;;) {
     const bool active = (status == LWFB_ST_OK) && (t < tend);
-    if (!__any_sync(LFULL, active && live)) break;
+    if (!LWFB_VOTE_ANY(active && live)) break;
     const bool can_step = active && !at_boundary;
 
-    if (!__any_sync(LFULL, can_step && live)) {
+    if (!LWFB_VOTE_ANY(can_step && live)) {
       // ============================== warp-synchronous daily callback at t = tstop
       // soil state of the own layer (SWCHEK clamps the state itself), then all layers gathered
       const double SWATMAX = LC(KC_SWATMAX), E2 = LC(KC_E2);
       double sw = y;
       if (sw <= 0.0) sw = 0.0; else if (sw > SWATMAX) sw = SWATMAX;
-      const double w = jmin(1.0, (LC(KC_THSAT) * sw / SWATMAX - LC(KC_THR)) / LC(KC_DTH));
-      const double a = jmax(w, 1.e-6);
+      const double w = jminc((LC(KC_THSAT) * sw / SWATMAX - LC(KC_THR)) / LC(KC_DTH), 1.0);
+      const double a = jmaxc(w, 1.e-6);
       const double la = lwfb_log(a);
       const double p1 = lwfb_pow_from_log(a, la, LC(KC_E1));
       const double psim = LC(KC_CPSI) * lwfb_pow(p1 - 1.0, E2);
@@ -267,31 +285,44 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 
     // perform_step!: rolled stage loop (s = 0 is the FSAL re-evaluation after a callback)
     double xy = y, xG = G;                           // stage inputs
-    double qy[5] = {0, 0, 0, 0, 0}, qG[5] = {0, 0, 0, 0, 0};
-    double aEy = 0, aEG = 0, kcy = kFy, kcG = kFG;
+    double qy[5] = {0, 0, 0, 0, 0}, qG[4] = {0, 0, 0, 0};    // qG: inputs of stages 3..6 (only if GWAT feeds back)
+    double aEy = 0, aEG = 0, kcy = kFy, kcG = kFG, SbG = 0;
     double kfy = kFy, kfG = kFG;                     // k1 of this attempt
     double Sb[EQ], Sbt[EQ], kfQ[EQ], kcQ[EQ];
 #pragma unroll
     for (int j = 0; j < EQ; j++) { Sb[j] = 0; Sbt[j] = 0; kfQ[j] = kFQ[j]; kcQ[j] = kFQ[j]; }
     double nt = ntfli;
     unsigned nf_s = nf;
-    const int s_first = __any_sync(LFULL, reeval && can_step) ? 0 : 1;
+    const int s_first = LWFB_VOTE_ANY(reeval && can_step) ? 0 : 1;
+    const bool gw_feedback = __any_sync(LFULL, !(LC(KC_GSC) < 1.0e-8));   // GWAT enters the RHS only through GSC >= 1e-8
 #pragma unroll 1
     for (int s = s_first; s <= 6; s++) {
+      LWFB_STAGE_SYNC();
       // ---- stage input
       if (s == 1) {
         const double a = dt_s * 0.161;
         xy = y + a * kfy; xG = G + a * kfG;
-        aEy = lBT[1] * kfy; aEG = lBT[1] * kfG;
+        aEy = lBT[1] * kfy; aEG = lBT[1] * kfG; SbG = lB7[1] * kfG;
 #pragma unroll
-        for (int p = 0; p < 5; p++) { qy[p] = lCQ[1][p] * kfy; qG[p] = lCQ[1][p] * kfG; }
+        for (int p = 0; p < 5; p++) qy[p] = lCQ[1][p] * kfy;
+        if (gw_feedback) {
+#pragma unroll
+          for (int p = 0; p < 4; p++) qG[p] = lCQ[1][p] * kfG;
+        }
 #pragma unroll
         for (int j = 0; j < EQ; j++) { Sb[j] = lB7[1] * kfQ[j]; Sbt[j] = lBT[1] * kfQ[j]; }
       } else if (s >= 2) {
-        xy = y + dt_s * qy[0]; xG = G + dt_s * qG[0];
+        xy = y + dt_s * qy[0];
 #pragma unroll
-        for (int p = 0; p < 4; p++) { qy[p] = qy[p + 1]; qG[p] = qG[p + 1]; }
-        qy[4] = 0; qG[4] = 0;
+        for (int p = 0; p < 4; p++) qy[p] = qy[p + 1];
+        qy[4] = 0;
+        if (s == 6) xG = G + dt_s * SbG;             // the new GWAT: uprev + dt * sum a7j kj (same summation order)
+        else if (gw_feedback) {
+          xG = G + dt_s * qG[0];
+#pragma unroll
+          for (int p = 0; p < 3; p++) qG[p] = qG[p + 1];
+          qG[3] = 0;
+        }
       } else {
         xy = y; xG = G;
       }
@@ -303,8 +334,8 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       const double SWATMAX = LC(KC_SWATMAX), THR = LC(KC_THR), DTH = LC(KC_DTH), E2 = LC(KC_E2);
       double sw = xy;
       if (sw <= 0.0) sw = 0.0; else if (sw > SWATMAX) sw = SWATMAX;
-      const double w = jmin(1.0, (LC(KC_THSAT) * sw / SWATMAX - THR) / DTH);
-      const double a = jmax(w, 1.e-6);
+      const double w = jminc((LC(KC_THSAT) * sw / SWATMAX - THR) / DTH, 1.0);
+      const double a = jmaxc(w, 1.e-6);
       const double la = lwfb_log(a);
       const double p1 = lwfb_pow_from_log(a, la, LC(KC_E1));
       const double p3 = lwfb_pow_from_log(a, la, LC(KC_E3));
@@ -319,7 +350,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       double BYFRAC = 0;
       if (__any_sync(LFULL, BYPAR)) {
         const double WETF = LC(KC_WETF);
-        double bf = jmin(1.0, lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (w - WETF) / (1 - WETF)));
+        double bf = jminc(lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (w - WETF) / (1 - WETF)), 1.0);
         if (w > 0.99) bf = 1;
         BYFRAC = BYPAR ? bf : 0.0;
       }
@@ -329,10 +360,10 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
         for (int j = 0; j < N; j++) { const double v = bcast(sw, j); if (j < QLAYER) sq += v; }
         if (QLAYER > 0) {
           const double SWATQF = LC(KC_SWATQF);
-          SAFRAC = jmin(1.0, lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (sq - SWATQF) / (LC(KC_SWATQX) - SWATQF)));
+          SAFRAC = jminc(lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (sq - SWATQF) / (LC(KC_SWATQX) - SWATQF)), 1.0);
         }
       }
-      const double SRFL = jmin(1., (LC(KC_IMPERV) + SAFRAC)) * (RNET + SMLT);
+      const double SRFL = jminc(LC(KC_IMPERV) + SAFRAC, 1.) * (RNET + SMLT);
       const double SLFL = RNET + SMLT - SRFL;
       DSFLI = 0;
       const bool any_slope = __any_sync(LFULL, SLOPE);
@@ -348,7 +379,8 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
         const double THICK = LC(KC_THICK), DRAIN = LC(KC_DRAIN);
         double kkmean = lwfb_exp((LC(KC_THICK_DN) * lk + THICK * lk_dn) / LC(KC_TSUM));
         kkmean = jmin(jmin(kkmean, KSAT), LC(KC_KSAT_DN));
-        const double grad = (psit - psit_dn) / LC(KC_THALF);
+        const double dpsi = nodn ? 1.0 : (psit - psit_dn);     // no layer below: value unused, keep the divisions on their fast path
+        const double grad = dpsi / LC(KC_THALF);
         const double vd = (grad * kkmean / p_RHOWG) * LC(KC_STFAC);
         const double vb = (DRAIN > 0.00001) ? DRAIN * kkv * LC(KC_OMS) : 0.0;
         V0 = bot ? vb : ((fabs(psit - psit_dn) < LC(KC_DPSIMAX)) ? 0.0 : vd);
@@ -358,7 +390,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       const double DTRI = 1.0 - (ts - floor(ts));                // = 1 - fmod(ts, 1) for ts >= 0
       double DTI = jmin(DTRI, LC(KC_DTIMAX));
       {
-        const double c1 = LC(KC_CITER) / jmax(0.000001, fabs(nt));
+        const double c1 = LC(KC_CITER) / jmaxc(fabs(nt), 0.000001);
         const double c2 = ((THR - theta) * LC(KC_THICK)) / nt / 1.30;
         const bool neg = nt < 0;
         const double v = neg ? (c2 < c1 ? c2 : c1) : c1;
@@ -472,9 +504,15 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       } else {
         const int ks = s + 1;
         aEy = aEy + lBT[ks] * kny; aEG = aEG + lBT[ks] * knG;
+        if (ks <= 6) SbG = SbG + lB7[ks] * knG;
 #pragma unroll
         for (int p = 0; p < 5; p++)
-          if (ks + 1 + p <= 7) { qy[p] = qy[p] + lCQ[ks][p] * kny; qG[p] = qG[p] + lCQ[ks][p] * knG; }
+          if (ks + 1 + p <= 7) qy[p] = qy[p] + lCQ[ks][p] * kny;
+        if (gw_feedback) {
+#pragma unroll
+          for (int p = 0; p < 4; p++)
+            if (ks + 1 + p <= 6) qG[p] = qG[p] + lCQ[ks][p] * knG;
+        }
 #pragma unroll
         for (int j = 0; j < EQ; j++) {
           if (ks <= 6) Sb[j] = Sb[j] + lB7[ks] * knQ[j];
@@ -490,14 +528,14 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     double ss = 0;
     {
       const double abstol = d.abstol, reltol = d.reltol;
-      double r = (dt_s * aEy) / (abstol + jmax(fabs(y), fabs(xy)) * reltol);
+      double r = div_z(dt_s * aEy, abstol + jmax_abs(y, xy) * reltol);
       const double r2y = r * r;
-      r = (dt_s * aEG) / (abstol + jmax(fabs(G), fabs(xG)) * reltol);
+      r = div_z(dt_s * aEG, abstol + jmax_abs(G, xG) * reltol);
       const double r2G = r * r;
 #pragma unroll
       for (int j = 0; j < EQ; j++) {
         Qn[j] = Q[j] + dt_s * Sb[j];
-        r = (dt_s * Sbt[j]) / (abstol + jmax(fabs(Q[j]), fabs(Qn[j])) * reltol);
+        r = div_z(dt_s * Sbt[j], abstol + jmax_abs(Q[j], Qn[j]) * reltol);
         r2Q[j] = r * r;
       }
       for (int j = 0; j < N; j++) ss += bcast(r2y, j);
@@ -592,29 +630,33 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       prec_delta(t, dp);
       const double THR = LC(KC_THR), DTH = LC(KC_DTH);
       const double S1 = y;
-      const double w1 = jmin(1.0, (LC(KC_THSAT) * S1 / LC(KC_SWATMAX) - THR) / DTH);
+      const double w1 = jminc((LC(KC_THSAT) * S1 / LC(KC_SWATMAX) - THR) / DTH, 1.0);
       const double th1 = w1 * DTH + THR;
       const double Tk = TA + 273.15;
       const double ee = lwfb_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
       double sumT = 0;
       for (int j = 0; j < N; j++) sumT += bcast(TRANI, j);
       const double tauth = lwfb_pow(th1, 7.0 / 3) / LC(KC_THS2);
-      const double aq = LC(KC_LAM) * fabs(VV / 1000);
+      const double aq = LC(KC_LAM) * fabs(div_z(VV, 1000.0));
       const double VN = bcast(VV, N - 1);
       const double VV_up = __shfl_up_sync(LFULL, VV, 1);
       const double DZ_up = LC(KC_DZ_UP), DZ_dn = LC(KC_DZ_DN), VXYLEM = LC(KC_VXYLEM);
-#pragma unroll
+      // the two species share one copy of the code (rolled loop, state picked by select)
+#pragma unroll 1
       for (int s = 0; s < 2; s++) {
         const double R = s == 0 ? R18 : R2H;
         const double D0 = (s == 0 ? 0.96691 : 0.98331) * 1e-9 * ee * 3600 * 24;
-        const double Cxy = d_to_x(dXY[s], R), Cinf = d_to_x(dp[s], R);
+        const double dSs = s == 0 ? dS[0] : dS[1], dGs = s == 0 ? dG[0] : dG[1], dXYs = s == 0 ? dXY[0] : dXY[1];
+        const double dps = s == 0 ? dp[0] : dp[1];
+        const double Cxy = d_to_x(dXYs, R), Cinf = d_to_x(dps, R);
         const double Dd = D0 * tauth * th1 + aq;
-        const double C = d_to_x(dS[s], R);
+        const double C = d_to_x(dSs, R);
         const double Ctr = (TRANI < 0) ? Cxy : C;
         const double C_up = __shfl_up_sync(LFULL, C, 1), C_dn = __shfl_down_sync(LFULL, C, 1);
         const double Dd_up = __shfl_up_sync(LFULL, Dd, 1), Dd_dn = __shfl_down_sync(LFULL, Dd, 1);
-        const double diff_upp = top ? 0.0 : ((Dd_up + Dd) / 2) * ((C - C_up) / DZ_up);
-        const double diff_low = bot ? 0.0 : ((Dd + Dd_dn) / 2) * ((C_dn - C) / DZ_dn);
+        // lanes without a neighbour get a non-zero dummy dividend (result unused; keeps the division on its fast path)
+        const double diff_upp = top ? 0.0 : ((Dd_up + Dd) / 2) * ((noup ? 1.0 : (C - C_up)) / DZ_up);
+        const double diff_low = bot ? 0.0 : ((Dd + Dd_dn) / 2) * ((nodn ? 1.0 : (C_dn - C)) / DZ_dn);
         const double qC_upp = top ? 0.0 : VV_up * C_up;
         const double qC_low = VV * C;
         const double slv = top ? C : 0.0;
@@ -631,19 +673,22 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
         if ((G == 0) && (VN == 0)) ddG = NAN;
         else if ((G == 0) && (VN > 0)) ddG = 0;
         else {
-          const double CG = d_to_x(dG[s], R);
-          const double dCG = VN / G * (CN - CG);
+          const double CG = d_to_x(dGs, R);
+          const double dCG = div_z(VN, G) * (CN - CG);
           ddG = dxdt_to_dddt(dCG, CG, R);
         }
         double swt = 0;
         const double ctt = Ctr * TRANI;
         for (int j = 0; j < N; j++) swt += bcast(ctt, j);
-        const double dRW = x_to_d(swt / sumT, R);
-        const double ddxy = (dRW != dRW) ? 0.0 : sumT / VXYLEM * (dRW - dXY[s]);
+        // 0/0 (no uptake at all) is NaN by definition; answered without sending the divisions down their slow path
+        const bool nouptake = (swt == 0.0) && (sumT == 0.0);
+        const double dRWc = x_to_d((nouptake ? 1.0 : swt) / (nouptake ? 2.0 : sumT), R);
+        const double dRW = nouptake ? NAN : dRWc;
+        const double ddxy = (dRW != dRW) ? 0.0 : sumT / VXYLEM * (dRW - dXYs);
         if (do_ade) {
-          dG[s] += dtt * ddG;
-          dS[s] += dtt * dd;
-          dXY[s] += dtt * ddxy;
+          const double nG = dGs + dtt * ddG, nS = dSs + dtt * dd, nXY = dXYs + dtt * ddxy;
+          if (s == 0) { dG[0] = nG; dS[0] = nS; dXY[0] = nXY; }
+          else { dG[1] = nG; dS[1] = nS; dXY[1] = nXY; }
           if (top && live) FIN(ix.RWU + 1 + s) = dRW;
         }
       }
