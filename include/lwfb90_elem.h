@@ -27,8 +27,10 @@
 
 #if defined(__CUDACC__)
 #define LWFB_ELEM __host__ __device__ __forceinline__
+#define LWFB_ELEM_COLD static __host__ __device__ __noinline__
 #else
 #define LWFB_ELEM static inline
+#define LWFB_ELEM_COLD static __attribute__((noinline, unused))
 #endif
 
 LWFB_ELEM int64_t lwfb_d2i(double x) {
@@ -81,14 +83,14 @@ static const double lwfb_log_coef_h[15] = LWFB_LOG_COEF;
 #define LWFB_LGC(i) lwfb_log_coef_h[i]
 #endif
 
-/* e^x: k = rint(x/ln2), Cody-Waite reduction with fma, degree-14 Taylor polynomial on |r| <= ln2/2.
- * Written without branches (selects only) so that several independent calls can be interleaved by the
- * instruction scheduler: the polynomial runs on the argument clamped to [-746, 710] and the special
- * results (NaN, overflow, underflow) are selected at the end. */
+/* e^x: k = rint(x/ln2), Cody-Waite reduction with fma, degree-14 Taylor polynomial on |r| <= ln2/2, result scaled by
+ * 2^k in two exact steps (so that overflow to inf and gradual underflow to 0 come out of the multiplications).
+ * Straight-line code (no branches): independent calls interleave in the FP64 pipe.  |x| >= 747 (incl. inf, NaN) is
+ * decided on the high word with integer instructions and answered by a select: NaN -> NaN, +big -> inf, -big -> 0. */
 LWFB_ELEM double lwfb_exp(double x) {
-  double xs = fmin(fmax(x, -746.0), 710.0);   /* fmin/fmax drop a NaN argument: xs is always finite */
-  double kf = rint(xs * LWFB_EC(13));
-  double r = fma(-kf, LWFB_EC(14), xs);
+  const int big = (int)((uint64_t)lwfb_d2i(x) >> 32 & 0x7fffffffu) >= 0x40875800;   /* |x| >= 747 or inf / NaN */
+  double kf = rint(x * LWFB_EC(13));
+  double r = fma(-kf, LWFB_EC(14), x);
   r = fma(-kf, LWFB_EC(15), r);
   double q = LWFB_EC(0);                    /* 1/14! */
   q = fma(q, r, LWFB_EC(1));                /* 1/13! */
@@ -104,26 +106,21 @@ LWFB_ELEM double lwfb_exp(double x) {
   q = fma(q, r, LWFB_EC(11));
   q = fma(q, r, LWFB_EC(12));
   double res = 1.0 + fma(r * r, q, r);
-  int k = (int)kf;
-  /* two-step scaling outside the normal exponent range; adj = 0 multiplies by 1.0 (exact) */
-  int adj = k > 1023 ? 1023 : (k < -1021 ? -1000 : 0);
+  int k = big ? 0 : (int)kf;                /* |k| <= 1078 */
+  int adj = k > 1023 ? 1023 : (k < -1021 ? -1000 : 0);   /* adj = 0 multiplies by 1.0 (exact) */
   res = res * lwfb_i2d((int64_t)(adj + 1023) << 52);
   k -= adj;
   res = res * lwfb_i2d((int64_t)(k + 1023) << 52);
-  res = x > LWFB_EC(16) ? INFINITY : res;
-  res = x < LWFB_EC(17) ? 0.0 : res;
-  return x != x ? x : res;
+  const double special = !(x <= 0.0) ? x * INFINITY : 0.0;   /* NaN -> NaN, x > 0 -> inf, else 0 */
+  return big ? special : res;
 }
 
-/* log(x): x = 2^e * m, m in (sqrt(1/2), sqrt(2)]; log(m) = 2 atanh(s), s = (m-1)/(m+1), evaluated as
- * f - (f^2/2 - s*(f^2/2 + R(s^2))) to avoid the rounding error of the division near m = 1.
- * Branch-free like lwfb_exp: special arguments (NaN, negative, 0, inf) are selected at the end. */
-LWFB_ELEM double lwfb_log(double x) {
-  int sub = x < 0x1p-1022;
-  double xs = sub ? x * 0x1p54 : x;
-  int e = sub ? -54 : 0;
-  int64_t ix = lwfb_d2i(xs);
-  e += (int)((ix >> 52) & 0x7ff) - 1023;
+/* log(x) for positive, normal, finite x: x = 2^e * m, m in (sqrt(1/2), sqrt(2)]; log(m) = 2 atanh(s),
+ * s = (m-1)/(m+1), evaluated as f - (f^2/2 - s*(f^2/2 + R(s^2))) to avoid the rounding error of the division near
+ * m = 1.  Straight-line code. */
+LWFB_ELEM double lwfb_log_core(double x, int e0) {
+  int64_t ix = lwfb_d2i(x);
+  int e = e0 + (int)((ix >> 52) & 0x7ff) - 1023;
   ix = (ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL;
   double m = lwfb_i2d(ix);
   int big = m > LWFB_LGC(14);
@@ -147,11 +144,24 @@ LWFB_ELEM double lwfb_log(double x) {
   R = R * z;
   double hfsq = 0.5 * f * f;
   double dk = (double)e;
-  double res = dk * LWFB_LGC(12) - ((hfsq - (s * (hfsq + R) + dk * LWFB_LGC(13))) - f);
-  res = x == INFINITY ? x : res;
-  res = x == 0.0 ? -INFINITY : res;
-  res = x < 0.0 ? NAN : res;
-  return x != x ? x : res;
+  return dk * LWFB_LGC(12) - ((hfsq - (s * (hfsq + R) + dk * LWFB_LGC(13))) - f);
+}
+LWFB_ELEM double lwfb_log_main(double x) { return lwfb_log_core(x, 0); }
+/* everything lwfb_log_main does not cover: 0, subnormal, negative, inf, NaN (rare; kept out of line on the device) */
+LWFB_ELEM int lwfb_log_isspecial(double x) {
+  return ((uint32_t)((uint64_t)lwfb_d2i(x) >> 32) - 0x00100000u) >= 0x7fe00000u;   /* not in [2^-1022, inf) */
+}
+LWFB_ELEM_COLD double lwfb_log_cold(double x) {
+  if (x != x) return x;
+  if (x < 0.0) return NAN;
+  if (x == 0.0) return -INFINITY;
+  if (x == INFINITY) return x;
+  return lwfb_log_core(x * 0x1p54, -54);    /* subnormal */
+}
+LWFB_ELEM double lwfb_log(double x) {
+  double r = lwfb_log_main(x);
+  if (lwfb_log_isspecial(x)) r = lwfb_log_cold(x);
+  return r;
 }
 
 /* x^y for x >= 0 (x < 0 gives NaN; the reference would throw a DomainError there).
@@ -166,6 +176,8 @@ LWFB_ELEM double lwfb_pow_from_log(double x, double lx, double y) {
   double r = lwfb_exp(y * lx);
   return y == 0.0 ? 1.0 : r;
 }
+/* the same for exponents known to be non-zero (saves the select) */
+LWFB_ELEM double lwfb_pow_from_log_nz(double lx, double y) { return lwfb_exp(y * lx); }
 
 /* sin and cos kernels on |r| <= pi/4 (Taylor, exact coefficients 1/n!) */
 LWFB_ELEM double lwfb_ksin(double r) {

@@ -42,7 +42,9 @@ __device__ __forceinline__ double jmax_abs(double a, double b) {
 // positive finite b, so that case is answered without dividing.  Bit-identical to a / b for all arguments.
 __device__ __forceinline__ double div_z(double a, double b) {
   const bool z = (a == 0.0) && (b > 0.0) && (b < INFINITY);
-  const double q = (z ? 1.0 : a) / b;
+  double aa = z ? 1.0 : a;
+  LWFB_OPAQUE(aa);                // otherwise the compiler sees that the quotient of the z case is unused and divides a itself
+  const double q = aa / b;
   return z ? a : q;
 }
 

@@ -79,6 +79,8 @@ enum {
   // member-level
   KC_DPSIMAX, KC_DTIMAX, KC_DRAIN, KC_GSC, KC_GSP, KC_IMPERV, KC_QFFC, KC_QFPAR, KC_SWATQF, KC_SWATQX,
   KC_CS, KC_SNRHO, KC_LEN1000, KC_LAM, KC_VXYLEM,
+  // day constants written by the daily callback
+  KC_SUMT, KC_SUMT_V,
   KC_COUNT
 };
 #define LC(k) (*(const volatile double*)(cst + (k) * LWFB_LANES_BLOCK))
@@ -169,11 +171,11 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 
   // value of accumulator e (held by lane e % N in slot e / N), broadcast to the group
   auto q_bcast = [&](const double* v, int e) {
-    const int slot = e / N;
+    const int slot = (e >= N) + (e >= 2 * N);          // e / N for e < 8, N >= 3
     double mine = v[0];
 #pragma unroll
     for (int j = 1; j < EQ; j++) mine = (slot == j) ? v[j] : mine;
-    return bcast(mine, e % N);
+    return bcast(mine, e - slot * N);
   };
   // registers -> fin for everything that evolves per step
   auto flush_state = [&]() {
@@ -241,6 +243,12 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       if (active) {
         y = sw;
         TRANI = TRANI_a[i];
+        {
+          double sT = 0;                         // sum of the layer uptakes and its ratio to the xylem volume (isotope step)
+          for (int j = 0; j < N; j++) sT += TRANI_a[j];
+          cst[KC_SUMT * LWFB_LANES_BLOCK] = sT;
+          cst[KC_SUMT_V * LWFB_LANES_BLOCK] = sT / LC(KC_VXYLEM);
+        }
         RNET = nRNET; SMLT = nSMLT; SLVP = nSLVP; TA = nTA;
         if (cbst != LWFB_ST_OK) status = cbst;
 #pragma unroll
@@ -336,13 +344,19 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       if (sw <= 0.0) sw = 0.0; else if (sw > SWATMAX) sw = SWATMAX;
       const double w = jminc((LC(KC_THSAT) * sw / SWATMAX - THR) / DTH, 1.0);
       const double a = jmaxc(w, 1.e-6);
-      const double la = lwfb_log(a);
-      const double p1 = lwfb_pow_from_log(a, la, LC(KC_E1));
-      const double p3 = lwfb_pow_from_log(a, la, LC(KC_E3));
+      // a in [1e-6, 1]: log on its main path.  The exponents -1/m, n/(n-1), 1/n, 1-1/n are non-zero for every valid
+      // van Genuchten n (finite, > 1), so x^y = exp(y log x) needs no y == 0 case; only the tortuosity l may be 0.
+      const double la = lwfb_log_main(a);
+      const double p1 = lwfb_pow_from_log_nz(la, LC(KC_E1));
+      const double p3 = lwfb_pow_from_log_nz(la, LC(KC_E3));
       const double pT = lwfb_pow_from_log(a, la, LC(KC_TORT));
-      const double psim = LC(KC_CPSI) * lwfb_pow(p1 - 1.0, E2);
+      const double x1 = p1 - 1.0, x3 = 1.0 - p3;             // both are 0 at saturation (log -> -inf, power -> 0)
+      double l1 = lwfb_log_main(x1), l3 = lwfb_log_main(x3);  // two independent chains, then the rare fix-ups
+      if (lwfb_log_isspecial(x1)) l1 = lwfb_log_cold(x1);
+      if (lwfb_log_isspecial(x3)) l3 = lwfb_log_cold(x3);
+      const double psim = LC(KC_CPSI) * lwfb_exp(E2 * l1);
       const double theta = w * DTH + THR;
-      const double inner = 1.0 - lwfb_pow(1.0 - p3, LC(KC_E4));
+      const double inner = 1.0 - lwfb_exp(LC(KC_E4) * l3);
       const double KSAT = LC(KC_KSAT);
       const double kkv = KSAT * pT * (inner * inner);
       const double lk = lwfb_log(kkv);
@@ -634,13 +648,13 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       const double th1 = w1 * DTH + THR;
       const double Tk = TA + 273.15;
       const double ee = lwfb_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
-      double sumT = 0;
-      for (int j = 0; j < N; j++) sumT += bcast(TRANI, j);
+      const double sumT = LC(KC_SUMT), sumT_V = LC(KC_SUMT_V);
       const double tauth = lwfb_pow(th1, 7.0 / 3) / LC(KC_THS2);
       const double aq = LC(KC_LAM) * fabs(div_z(VV, 1000.0));
       const double VN = bcast(VV, N - 1);
       const double VV_up = __shfl_up_sync(LFULL, VV, 1);
-      const double DZ_up = LC(KC_DZ_UP), DZ_dn = LC(KC_DZ_DN), VXYLEM = LC(KC_VXYLEM);
+      const double DZ_up = LC(KC_DZ_UP), DZ_dn = LC(KC_DZ_DN);
+      const double rS1 = 1 / S1, VN_G = div_z(VN, G);
       // the two species share one copy of the code (rolled loop, state picked by select)
 #pragma unroll 1
       for (int s = 0; s < 2; s++) {
@@ -648,15 +662,18 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
         const double D0 = (s == 0 ? 0.96691 : 0.98331) * 1e-9 * ee * 3600 * 24;
         const double dSs = s == 0 ? dS[0] : dS[1], dGs = s == 0 ? dG[0] : dG[1], dXYs = s == 0 ? dXY[0] : dXY[1];
         const double dps = s == 0 ? dp[0] : dp[1];
-        const double Cxy = d_to_x(dXYs, R), Cinf = d_to_x(dps, R);
+        // the three member-level mixing ratios (xylem, precipitation, groundwater) are converted by lanes 0, 1, 2 of the
+        // group in ONE evaluation of d_to_x and broadcast
+        const double X = d_to_x(i == 1 ? dps : (i == 2 ? dGs : dXYs), R);
+        const double Cxy = bcast(X, 0), Cinf = bcast(X, 1), CG = bcast(X, 2);
         const double Dd = D0 * tauth * th1 + aq;
         const double C = d_to_x(dSs, R);
         const double Ctr = (TRANI < 0) ? Cxy : C;
         const double C_up = __shfl_up_sync(LFULL, C, 1), C_dn = __shfl_down_sync(LFULL, C, 1);
         const double Dd_up = __shfl_up_sync(LFULL, Dd, 1), Dd_dn = __shfl_down_sync(LFULL, Dd, 1);
         // lanes without a neighbour get a non-zero dummy dividend (result unused; keeps the division on its fast path)
-        const double diff_upp = top ? 0.0 : ((Dd_up + Dd) / 2) * ((noup ? 1.0 : (C - C_up)) / DZ_up);
-        const double diff_low = bot ? 0.0 : ((Dd + Dd_dn) / 2) * ((nodn ? 1.0 : (C_dn - C)) / DZ_dn);
+        const double diff_upp = top ? 0.0 : ((Dd_up + Dd) / 2) * div_z(noup ? 1.0 : (C - C_up), DZ_up);
+        const double diff_low = bot ? 0.0 : ((Dd + Dd_dn) / 2) * div_z(nodn ? 1.0 : (C_dn - C), DZ_dn);
         const double qC_upp = top ? 0.0 : VV_up * C_up;
         const double qC_low = VV * C;
         const double slv = top ? C : 0.0;
@@ -666,17 +683,11 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
         innr = innr - DSFLI * C;
         innr = innr - SLVP * slv;
         innr = innr - TRANI * Ctr;
-        const double dC = -C / S1 * ntfli + 1 / S1 * innr;
+        const double dC = -C / S1 * ntfli + rS1 * innr;
         const double dd = dxdt_to_dddt(dC, C, R);
         const double CN = bcast(C, N - 1);
-        double ddG;
-        if ((G == 0) && (VN == 0)) ddG = NAN;
-        else if ((G == 0) && (VN > 0)) ddG = 0;
-        else {
-          const double CG = d_to_x(dGs, R);
-          const double dCG = div_z(VN, G) * (CN - CG);
-          ddG = dxdt_to_dddt(dCG, CG, R);
-        }
+        double ddG = dxdt_to_dddt(VN_G * (CN - CG), CG, R);
+        if (G == 0) ddG = (VN == 0) ? NAN : ((VN > 0) ? 0.0 : ddG);
         double swt = 0;
         const double ctt = Ctr * TRANI;
         for (int j = 0; j < N; j++) swt += bcast(ctt, j);
@@ -684,7 +695,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
         const bool nouptake = (swt == 0.0) && (sumT == 0.0);
         const double dRWc = x_to_d((nouptake ? 1.0 : swt) / (nouptake ? 2.0 : sumT), R);
         const double dRW = nouptake ? NAN : dRWc;
-        const double ddxy = (dRW != dRW) ? 0.0 : sumT / VXYLEM * (dRW - dXYs);
+        const double ddxy = (dRW != dRW) ? 0.0 : sumT_V * (dRW - dXYs);
         if (do_ade) {
           const double nG = dGs + dtt * ddG, nS = dSs + dtt * dd, nXY = dXYs + dtt * ddxy;
           if (s == 0) { dG[0] = nG; dS[0] = nS; dXY[0] = nXY; }
@@ -715,7 +726,9 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 template <int NMAX, int EQ>
 __global__ void __launch_bounds__(LWFB_LANES_BLOCK, LWFB_LANES_MINBLOCKS) integrate_lanes(DevData d) {
   extern __shared__ double lanes_smem[];
-  lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + threadIdx.x);
+  double* cst = lanes_smem + threadIdx.x;
+  asm volatile("" : "+l"(cst));     // keep the column address in a register (otherwise it is re-derived from %tid at every use)
+  lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, cst);
 }
 #endif
 

@@ -51,6 +51,22 @@ template <typename T> static inline T simt_shfl(T v, int src, int op) { return s
 #define __any_sync(mask, p) (simt::vote((p), LWFB_OP_ID) != 0u)
 #define __all_sync(mask, p) (simt::vote((p), LWFB_OP_ID) == 0xffffffffu)
 #define __syncwarp(mask) ((void)simt::vote(true, LWFB_OP_ID))
+// redux.sync min over the lanes named in `mask` (every lane passes the mask of its own group)
+static inline unsigned simt_reduce_min(unsigned mask, unsigned v, int op) {
+  unsigned r = 0xffffffffu;
+  for (int l = 0; l < 32; l++) {
+    const unsigned vl = (unsigned)simt::exchange(v, l, op * 64 + l);
+    if ((mask >> l) & 1u) r = vl < r ? vl : r;
+  }
+  return r;
+}
+#define __reduce_min_sync(mask, v) simt_reduce_min((mask), (v), LWFB_OP_ID)
+static inline int __double2hiint(double x) { long long i; memcpy(&i, &x, 8); return (int)(i >> 32); }
+static inline int __double2loint(double x) { long long i; memcpy(&i, &x, 8); return (int)(i & 0xffffffffLL); }
+static inline double __hiloint2double(int hi, int lo) { long long i = ((long long)hi << 32) | (unsigned)lo; double x; memcpy(&x, &i, 8); return x; }
+// value barrier: the optimiser must treat x as unknown from here on
+#define LWFB_OPAQUE(x) asm volatile("" : "+x"(x))
 #else
 #include <cuda_runtime.h>
+#define LWFB_OPAQUE(x) asm volatile("" : "+d"(x))
 #endif
