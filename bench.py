@@ -33,7 +33,9 @@ warnings.simplefilter("ignore")
 import numpy as np  # noqa: E402
 
 METRIC = "site-days/sec, 1M-member DAV2020-full iso ensemble at 1/2/4/8 B200 vs CPU"
-MEMBERS_PER_GPU = 131072          # 8 x 131072 = 1,048,576 members at N = 8 (weak scaling)
+# 9 full waves of the lane kernel on one B200: 148 SMs x 2 blocks x 8 warps x 6 members = 14208 members per wave.
+# 8 x 127872 = 1,022,976 members at N = 8 (weak scaling).
+MEMBERS_PER_GPU = 127872
 
 # FLOP-equivalents per site-day (SURVEY 8d convention: add/mul/div/min/max = 1, FMA = 2, sqrt = 4,
 # exp/log/trig = 20, pow = 45; only live arithmetic counts)
@@ -285,8 +287,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"DAV2020-full isotope ensemble: {M} members per GPU x {world} GPU(s) "
-                                   f"(= 1,048,576 at 8 GPUs), N=5 layers, {nd} days, state length {L}, Philox seed 1234; "
-                                   "per step: integrate + score kernel + score all-gather",
+                                   f"(= {8 * M:,} at 8 GPUs), N=5 layers, {nd} days, state length {L}, Philox seed 1234; "
+                                   "per step: integrate + score kernel + score all-gather; adaptive placement "
+                                   "(members cost-sorted from the previous run of the handle, lwfb_set_placement)",
                        "members_per_gpu": M, "n_days": nd, "n_layers": N,
                        "l2": "member blocks (%.0f MB) and daily record (%.1f GB) per launch exceed the 126 MB L2"
                              % (h2d / 1e6, M * (nd + 1) * L * 8 / 1e9),

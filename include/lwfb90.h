@@ -247,6 +247,13 @@ int lwfb_debug_get_block(lwfb_handle* h, int32_t which, double* out);
  * is otherwise used only for N < 3 or N > 32 layers) instead of the lane-per-layer production kernel */
 int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on);
 
+/* Placement of the members in the kernel's execution slots (no reference analogue; results do not depend on it).
+ * The members that share a thread block advance in lock step and wait for each other at every step, so a block
+ * is as slow as its member with the most steps.  mode 1 (default, "adaptive"): every lwfb_run sorts the members by the
+ * number of RHS evaluations they needed in the PREVIOUS run of this handle (same member count), most expensive first;
+ * the first run uses the given order.  Meant for calibration loops that re-run similar ensembles.  mode 0: as given. */
+int lwfb_set_placement(lwfb_handle* h, int32_t mode);
+
 /* kernel launch statistics of the last lwfb_run: number of kernel launches, device ms */
 int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* device_ms);
 

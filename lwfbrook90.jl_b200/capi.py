@@ -37,7 +37,7 @@ _lib = None
 SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error", "lwfb_set_sites",
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
            "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
-           "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy"]
+           "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy", "lwfb_set_placement"]
 
 
 def lib():
@@ -214,6 +214,11 @@ class Handle:
         """Testing aid: use the thread-per-member kernel instead of the lane-per-layer kernel."""
         self._L.lwfb_debug_force_legacy.argtypes = [C.c_void_p, C.c_int32]
         self._ck(self._L.lwfb_debug_force_legacy(self._h, int(on)))
+
+    def set_placement(self, mode: int):
+        """0: members run in the given order; 1 (default): cost-sorted from the previous run of this handle."""
+        self._L.lwfb_set_placement.argtypes = [C.c_void_p, C.c_int32]
+        self._ck(self._L.lwfb_set_placement(self._h, int(mode)))
 
     def last_run_stats(self):
         n = C.c_int32()

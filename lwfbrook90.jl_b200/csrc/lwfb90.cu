@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -144,6 +145,11 @@ struct lwfb_handle {
   float last_ms = 0.f;
   bool ran = false;
   bool force_legacy = false;   // testing: run the thread-per-member kernel also for 3 <= N <= 32
+  // placement of members in the lane kernel's slots (lwfb_set_placement)
+  int placement = 1;           // 0 identity, 1 adaptive (cost-sorted from the previous run)
+  int32_t* d_perm = nullptr;
+  bool perm_valid = false;     // d_perm holds a permutation for the current member count
+  bool cost_valid = false;     // d_counters holds the RHS-evaluation counts of a completed lane-kernel run
   std::string err;
 };
 
@@ -190,7 +196,8 @@ extern "C" int lwfb_create(lwfb_handle** out, const lwfb_opts* opts) {
 
 static void free_members(lwfb_handle* h) {
   cudaFree(h->d_scal); cudaFree(h->d_lay); cudaFree(h->d_u0); cudaFree(h->d_rec); cudaFree(h->d_fin);
-  cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores);
+  cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm);
+  h->d_perm = nullptr; h->perm_valid = false; h->cost_valid = false;
   h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
   h->d_site = h->d_status = nullptr; h->d_counters = nullptr;
   h->M = 0; h->ran = false;
@@ -273,6 +280,7 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
     CK(cudaMalloc(&h->d_status, (size_t)M * sizeof(int32_t)));
     CK(cudaMalloc(&h->d_counters, (size_t)M * LWFB_NCOUNTERS * sizeof(long long)));
     CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
+    CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
     if (h->o.record_daily) {
       size_t bytes = (size_t)M * (h->o.n_days + 1) * L * sizeof(double);
       cudaError_t e = cudaMalloc(&h->d_rec, bytes);
@@ -294,6 +302,7 @@ static DevData make_dev(lwfb_handle* h) {
   d.M = h->M; d.N = h->o.n_layers; d.iso = h->o.simulate_isotopes; d.t0_day = h->o.t0_day; d.n_days = h->o.n_days;
   d.n_rows = h->n_rows; d.L = h->L;
   d.scal = h->d_scal; d.lay = h->d_lay; d.forc = h->d_forc; d.site = h->d_site; d.u0 = h->d_u0;
+  d.perm = (h->placement == 1 && h->perm_valid) ? h->d_perm : nullptr;
   d.rec = h->d_rec; d.fin = h->d_fin; d.status = h->d_status; d.counters = h->d_counters;
   d.reltol = h->o.reltol; d.abstol = h->o.abstol; d.dt_init = h->o.dt_init; d.dtmax = h->o.dtmax;
   d.maxiters = h->o.maxiters;
@@ -304,9 +313,22 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
   if (!h || h->M < 1) return LWFB_ERR_ARG;
   CK(cudaSetDevice(h->o.device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
+  const bool lanes = h->o.n_layers >= 3 && h->o.n_layers <= 32 && !h->force_legacy;
+  if (lanes && h->placement == 1 && h->cost_valid) {
+    // adaptive placement: members sorted by the number of RHS evaluations of the previous run (most expensive first),
+    // so that the members that share a block (and wait for each other at every step) have similar step counts
+    std::vector<long long> nf((size_t)h->M);
+    CK(cudaMemcpy(nf.data(), h->d_counters + (size_t)LWFB_C_NF * h->M, nf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> perm((size_t)h->M);
+    for (int64_t i = 0; i < h->M; i++) perm[(size_t)i] = (int32_t)i;
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return nf[(size_t)a] > nf[(size_t)b]; });
+    CK(cudaMemcpy(h->d_perm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->perm_valid = true;
+    h->cost_valid = false;
+  }
   DevData d = make_dev(h);
   CK(cudaEventRecord(h->ev0, st));
-  if (d.N >= 3 && d.N <= 32 && !h->force_legacy) {
+  if (lanes) {
     // production path: one lane per soil layer, 32/N members per warp; per-thread constants in shared memory
     const int mpw = 32 / d.N;
     const int64_t warps = (d.M + mpw - 1) / mpw;
@@ -331,6 +353,7 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
   CK(cudaEventRecord(h->ev1, st));
   h->n_launches = 1;
   h->ran = true;
+  h->cost_valid = lanes;
   return LWFB_OK;
 }
 
@@ -531,5 +554,13 @@ extern "C" int lwfb_fp64_peak(int32_t device, int32_t reps, double* tflops) {
 extern "C" int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on) {
   if (!h) return LWFB_ERR_ARG;
   h->force_legacy = on != 0;
+  return LWFB_OK;
+}
+
+// placement of the members in the lane kernel's slots: 0 = as given, 1 = adaptive (default)
+extern "C" int lwfb_set_placement(lwfb_handle* h, int32_t mode) {
+  if (!h || mode < 0 || mode > 1) return LWFB_ERR_ARG;
+  h->placement = mode;
+  if (mode == 0) h->perm_valid = false;
   return LWFB_OK;
 }

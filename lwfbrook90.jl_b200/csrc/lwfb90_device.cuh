@@ -55,6 +55,7 @@ struct DevData {
   const double* __restrict__ lay;    // [LWFB_PL][N][M]
   const double* __restrict__ forc;   // [n_sites][n_rows][LWFB_F]
   const int32_t* __restrict__ site;  // [M]
+  const int32_t* __restrict__ perm;  // [M] placement: slot -> member (null: identity); see lwfb_set_placement
   const double* __restrict__ u0;     // [L][M]
   double* __restrict__ rec;          // [n_days+1][L][M]  (may be null: no daily record)
   double* __restrict__ fin;          // [L][M] final state (always written)

@@ -95,9 +95,10 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   const bool lane_valid = g < mpw;
   if (!lane_valid) { g = 0; i = 0; }                 // surplus lanes shadow lane 0 and never commit
   const int base = g * N;
-  const int64_t m_raw = warp_g * mpw + g;
+  const int64_t m_raw = warp_g * mpw + g;            // slot of the group
   const bool live = lane_valid && m_raw < M;
-  const int64_t m = (m_raw < M) ? m_raw : M - 1;
+  const int64_t slot = (m_raw < M) ? m_raw : M - 1;
+  const int64_t m = d.perm ? (int64_t)__ldg(d.perm + slot) : slot;   // member placed in this slot
   const bool top = (i == 0), bot = (i == N - 1);
   const bool nodn = bot || !lane_valid, noup = top || !lane_valid;   // lanes without a real neighbour below / above
   const int L = d.L;
@@ -205,6 +206,10 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   bool reeval = false, at_boundary = true, cand_nan = (y != y);
   int status = LWFB_ST_OK;
   int rec = 1;
+#ifdef LWFB_DEBUG_ITERS
+  unsigned dbg_iters = 0;          // step-phase iterations of the block (profiling: lock-step waiting overhead)
+  unsigned dbg_day_iter0 = 0;
+#endif
 
   if (d.rec && live) for (int j = i; j < L; j += N) d.rec[(int64_t)j * M + m] = U0(j);     // record 0 = raw u0
   __syncwarp(LFULL);
@@ -275,6 +280,9 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       continue;
     }
 
+#ifdef LWFB_DEBUG_ITERS
+    dbg_iters++;
+#endif
     // ============================== one attempted step (all lanes execute, only `do_step` lanes commit)
     // loopheader! (dt already holds the controller's proposal / the shrunk step after a rejection)
     double dt_s = dt;
@@ -302,6 +310,12 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     double nt = ntfli;
     unsigned nf_s = nf;
     const int s_first = LWFB_VOTE_ANY(reeval && can_step) ? 0 : 1;
+    if (!__any_sync(LFULL, can_step && live)) {
+      // no member of THIS warp steps (all wait at the day boundary for slower members of the block, or are done):
+      // keep the block's barrier choreography and issue nothing else
+      for (int s = s_first; s <= 6; s++) LWFB_STAGE_SYNC();
+      continue;
+    }
     const bool gw_feedback = __any_sync(LFULL, !(LC(KC_GSC) < 1.0e-8));   // GWAT enters the RHS only through GSC >= 1e-8
 #pragma unroll 1
     for (int s = s_first; s <= 6; s++) {
@@ -610,6 +624,9 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 #pragma unroll 1
       for (int e = 0; e < 8; e++) ev[e] = q_bcast(Q, e);
       if (at_stop) flush_state();
+#ifdef LWFB_DEBUG_ITERS
+      if (at_stop && live && top) { FIN(ix.AUX) = (double)(iter - dbg_day_iter0); dbg_day_iter0 = iter; }   // attempted steps of this day
+#endif
       __syncwarp(LFULL);
       double bs = 0, bt = 0, Wt = 0;
       if (at_stop) {
@@ -716,7 +733,11 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     if (top) {
       d.status[m] = status;
       d.counters[(int64_t)LWFB_C_NACCEPT * M + m] = naccept;
+#ifdef LWFB_DEBUG_ITERS
+      d.counters[(int64_t)LWFB_C_NREJECT * M + m] = dbg_iters;
+#else
       d.counters[(int64_t)LWFB_C_NREJECT * M + m] = nreject;
+#endif
       d.counters[(int64_t)LWFB_C_NF * M + m] = nf;
     }
   }

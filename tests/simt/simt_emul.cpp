@@ -169,7 +169,7 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
                              const double* forcing, int64_t M, const int32_t* site_of_member, const double* scal,
                              const double* lay, const double* u0, double reltol, double abstol, double dt_init,
                              double dtmax, int64_t maxiters, int n_threads, double* out_daily, int32_t* status,
-                             int64_t* counters) {
+                             int64_t* counters, const int32_t* perm) {
   (void)n_sites;
   const int L = LWFB_STATE_LEN(N, iso);
   if (kernel == 0 && (N < 3 || N > 32)) return -1;
@@ -182,7 +182,7 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   Job job;
   lwfb::DevData& d = job.d;
   d.M = M; d.N = N; d.iso = iso; d.t0_day = t0_day; d.n_days = n_days; d.n_rows = n_rows; d.L = L;
-  d.scal = s_scal.data(); d.lay = s_lay.data(); d.forc = forcing; d.site = site_of_member; d.u0 = s_u0.data();
+  d.scal = s_scal.data(); d.lay = s_lay.data(); d.forc = forcing; d.site = site_of_member; d.perm = perm; d.u0 = s_u0.data();
   d.rec = rec.data(); d.fin = fin.data(); d.status = status; d.counters = cnt.data();
   d.reltol = reltol; d.abstol = abstol; d.dt_init = dt_init; d.dtmax = dtmax; d.maxiters = maxiters;
   job.kernel = kernel;

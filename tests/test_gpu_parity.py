@@ -189,6 +189,22 @@ def test_lane_kernel_all_group_sizes(lw, N):
     h.close()
 
 
+def test_adaptive_placement_is_result_neutral(dav_full):
+    """Second and later runs of a handle place the members cost-sorted (lwfb_set_placement mode 1); records, status
+    and counters must not change, with identity placement (mode 0) as the cross-check."""
+    ens = en.make_ensemble(dav_full, 300)
+    h, sub, nd = gpu_run(ens, 150)
+    first = h.get_daily(); st1, cnt1 = h.get_status()
+    h.run()                                   # placement now sorted by the first run's RHS counts
+    second = h.get_daily(); st2, cnt2 = h.get_status()
+    assert np.array_equal(first, second, equal_nan=True) and np.array_equal(st1, st2) and np.array_equal(cnt1, cnt2)
+    h.set_placement(0); h.run()
+    assert np.array_equal(first, h.get_daily(), equal_nan=True)
+    ref, st_o, cnt_o = oracle_run(sub, nd, "elem")
+    assert np.array_equal(second, ref, equal_nan=True) and np.array_equal(cnt2, cnt_o)
+    h.close()
+
+
 def test_nonzero_start_day_and_short_span(dav_full):
     """tspan not starting at 0 (initial conditions applied at t0, forcing taken from the right rows)."""
     e = en.make_ensemble(dav_full, 16)

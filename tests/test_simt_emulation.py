@@ -92,6 +92,17 @@ def test_member_kernel_generic_layer_count(lw, dav_full):
     check(en.make_ensemble(dav_full, 6), 10, emul.MEMBER)
 
 
+def test_lane_kernel_placement_does_not_change_results(dav_full):
+    """Members may be placed in any slot (lwfb_set_placement): a random permutation gives the same records."""
+    e = en.make_ensemble(dav_full, 15)
+    orc.use("elem")
+    ref, st_o, cnt_o = orc.run(e.N, e.iso, e.t0_day, 6, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, n_threads=8)
+    perm = np.random.default_rng(3).permutation(e.M).astype(np.int32)
+    got, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, 6, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, perm=perm)
+    assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
+    assert np.array_equal(got, ref, equal_nan=True)
+
+
 def test_emulator_rejects_divergent_warp_primitives():
     """The emulator aborts when lanes meet at different warp primitives; a well-formed run reports none.  (The
     abort path itself is exercised by the build of every kernel change: a divergent shuffle never gets here.)"""
