@@ -251,7 +251,9 @@ int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on);
  * The members that share a thread block advance in lock step and wait for each other at every step, so a block
  * is as slow as its member with the most steps.  mode 1 (default, "adaptive"): every lwfb_run sorts the members by the
  * number of RHS evaluations they needed in the PREVIOUS run of this handle (same member count), most expensive first;
- * the first run uses the given order.  Meant for calibration loops that re-run similar ensembles.  mode 0: as given. */
+ * the first run uses the given order, and so do launches of fewer than three waves of blocks (sorting would only
+ * concentrate the expensive members in the slowest block).  Meant for calibration loops that re-run similar
+ * ensembles.  mode 0: as given.  mode 2: like 1 but also for small launches (testing). */
 int lwfb_set_placement(lwfb_handle* h, int32_t mode);
 
 /* kernel launch statistics of the last lwfb_run: number of kernel launches, device ms */

@@ -146,7 +146,7 @@ struct lwfb_handle {
   bool ran = false;
   bool force_legacy = false;   // testing: run the thread-per-member kernel also for 3 <= N <= 32
   // placement of members in the lane kernel's slots (lwfb_set_placement)
-  int placement = 1;           // 0 identity, 1 adaptive (cost-sorted from the previous run)
+  int placement = 1;           // 0 identity, 1 adaptive (cost-sorted from the previous run), 2 the same for any launch size
   int32_t* d_perm = nullptr;
   bool perm_valid = false;     // d_perm holds a permutation for the current member count
   bool cost_valid = false;     // d_counters holds the RHS-evaluation counts of a completed lane-kernel run
@@ -302,7 +302,7 @@ static DevData make_dev(lwfb_handle* h) {
   d.M = h->M; d.N = h->o.n_layers; d.iso = h->o.simulate_isotopes; d.t0_day = h->o.t0_day; d.n_days = h->o.n_days;
   d.n_rows = h->n_rows; d.L = h->L;
   d.scal = h->d_scal; d.lay = h->d_lay; d.forc = h->d_forc; d.site = h->d_site; d.u0 = h->d_u0;
-  d.perm = (h->placement == 1 && h->perm_valid) ? h->d_perm : nullptr;
+  d.perm = (h->placement >= 1 && h->perm_valid) ? h->d_perm : nullptr;
   d.rec = h->d_rec; d.fin = h->d_fin; d.status = h->d_status; d.counters = h->d_counters;
   d.reltol = h->o.reltol; d.abstol = h->o.abstol; d.dt_init = h->o.dt_init; d.dtmax = h->o.dtmax;
   d.maxiters = h->o.maxiters;
@@ -314,7 +314,15 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
   CK(cudaSetDevice(h->o.device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const bool lanes = h->o.n_layers >= 3 && h->o.n_layers <= 32 && !h->force_legacy;
-  if (lanes && h->placement == 1 && h->cost_valid) {
+  // Sorting concentrates the expensive members in few blocks: good when the blocks outnumber the resident slots several
+  // times (the block scheduler balances), bad for a launch of one or two waves (it only makes the slowest block slower).
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->o.device);
+  const int64_t members_per_block = (int64_t)(LWFB_LANES_BLOCK / 32) * (32 / (lanes ? h->o.n_layers : 32));
+  const int64_t n_blocks = lanes ? (h->M + members_per_block - 1) / members_per_block : 0;
+  const bool many_waves = h->placement == 2 || n_blocks >= 3 * (int64_t)n_sm * LWFB_LANES_MINBLOCKS;
+  if (lanes && h->placement >= 1 && !many_waves) h->perm_valid = false;
+  if (lanes && h->placement >= 1 && h->cost_valid && many_waves) {
     // adaptive placement: members sorted by the number of RHS evaluations of the previous run (most expensive first),
     // so that the members that share a block (and wait for each other at every step) have similar step counts
     std::vector<long long> nf((size_t)h->M);
@@ -559,7 +567,7 @@ extern "C" int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on) {
 
 // placement of the members in the lane kernel's slots: 0 = as given, 1 = adaptive (default)
 extern "C" int lwfb_set_placement(lwfb_handle* h, int32_t mode) {
-  if (!h || mode < 0 || mode > 1) return LWFB_ERR_ARG;
+  if (!h || mode < 0 || mode > 2) return LWFB_ERR_ARG;
   h->placement = mode;
   if (mode == 0) h->perm_valid = false;
   return LWFB_OK;

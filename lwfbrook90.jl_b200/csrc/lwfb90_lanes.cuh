@@ -80,7 +80,9 @@ enum {
   KC_DPSIMAX, KC_DTIMAX, KC_DRAIN, KC_GSC, KC_GSP, KC_IMPERV, KC_QFFC, KC_QFPAR, KC_SWATQF, KC_SWATQX,
   KC_CS, KC_SNRHO, KC_LEN1000, KC_LAM, KC_VXYLEM,
   // day constants written by the daily callback
-  KC_SUMT, KC_SUMT_V,
+  KC_SUMT, KC_SUMT_V, KC_D0_18O, KC_D0_2H,
+  // isotope state of the lane (touched once per accepted step): delta18O / delta2H of SWATI[i], GWAT, XYLEM
+  KC_DS_18O, KC_DS_2H, KC_DG_18O, KC_DG_2H, KC_DXY_18O, KC_DXY_2H,
   KC_COUNT
 };
 #define LC(k) (*(const volatile double*)(cst + (k) * LWFB_LANES_BLOCK))
@@ -161,13 +163,14 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     kFQ[j] = 0;
   }
   double kFy = 0, kFG = 0;                           // FSAL derivative of SWATI / GWAT
-  double dS[2] = {0, 0}, dG[2] = {0, 0}, dXY[2] = {0, 0};
-  if (iso) {
-#pragma unroll
-    for (int s = 0; s < 2; s++) { dS[s] = U0(ix.SWATI + (s + 1) * N + i); dG[s] = U0(ix.GWAT + 1 + s); dXY[s] = U0(ix.XYLEM + 1 + s); }
+  auto SETK = [&](int k, double v) { cst[k * LWFB_LANES_BLOCK] = v; };
+  for (int s = 0; s < 2; s++) {
+    SETK(KC_DS_18O + s, iso ? U0(ix.SWATI + (s + 1) * N + i) : 0.0);
+    SETK(KC_DG_18O + s, iso ? U0(ix.GWAT + 1 + s) : 0.0);
+    SETK(KC_DXY_18O + s, iso ? U0(ix.XYLEM + 1 + s) : 0.0);
   }
   double TRANI = NAN, ntfli = NAN;                   // frozen uptake of the layer; du_NTFLI of the previous RHS call
-  double RNET = NAN, SMLT = NAN, SLVP = NAN, TA = NAN;
+  double RS = NAN, SLVP = NAN;                        // RNET + SMLT and SLVP of the day
   double VV = 0, INFLI = 0, DSFLI = 0;               // flux caches of the last RHS (isotope step)
 
   // value of accumulator e (held by lane e % N in slot e / N), broadcast to the group
@@ -182,12 +185,12 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   auto flush_state = [&]() {
     if (!live) return;
     FIN(ix.SWATI + i) = y;
-    if (iso) { FIN(ix.SWATI + N + i) = dS[0]; FIN(ix.SWATI + 2 * N + i) = dS[1]; }
+    if (iso) { FIN(ix.SWATI + N + i) = LC(KC_DS_18O); FIN(ix.SWATI + 2 * N + i) = LC(KC_DS_2H); }
 #pragma unroll
     for (int j = 0; j < EQ; j++) if (qe[j] < 8) FIN(ix.ACC + lAccPos[qe[j] & 7]) = Q[j];
     if (top) {
       FIN(ix.GWAT) = G;
-      if (iso) { FIN(ix.GWAT + 1) = dG[0]; FIN(ix.GWAT + 2) = dG[1]; FIN(ix.XYLEM + 1) = dXY[0]; FIN(ix.XYLEM + 2) = dXY[1]; }
+      if (iso) { FIN(ix.GWAT + 1) = LC(KC_DG_18O); FIN(ix.GWAT + 2) = LC(KC_DG_2H); FIN(ix.XYLEM + 1) = LC(KC_DXY_18O); FIN(ix.XYLEM + 2) = LC(KC_DXY_2H); }
     }
   };
   auto prec_delta = [&](double t, double* dp) {
@@ -254,7 +257,14 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
           cst[KC_SUMT * LWFB_LANES_BLOCK] = sT;
           cst[KC_SUMT_V * LWFB_LANES_BLOCK] = sT / LC(KC_VXYLEM);
         }
-        RNET = nRNET; SMLT = nSMLT; SLVP = nSLVP; TA = nTA;
+        RS = nRNET + nSMLT; SLVP = nSLVP;
+        {
+          // molecular diffusivities of the day (soil temperature = daily mean air temperature)
+          const double Tk = nTA + 273.15;
+          const double ee = lwfb_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
+          SETK(KC_D0_18O, 0.96691 * 1e-9 * ee * 3600 * 24);
+          SETK(KC_D0_2H, 0.98331 * 1e-9 * ee * 3600 * 24);
+        }
         if (cbst != LWFB_ST_OK) status = cbst;
 #pragma unroll
         for (int j = 0; j < EQ; j++) Q[j] = 0.0;
@@ -303,36 +313,43 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     double xy = y, xG = G;                           // stage inputs
     double qy[5] = {0, 0, 0, 0, 0}, qG[4] = {0, 0, 0, 0};    // qG: inputs of stages 3..6 (only if GWAT feeds back)
     double aEy = 0, aEG = 0, kcy = kFy, kcG = kFG, SbG = 0;
-    double kfy = kFy, kfG = kFG;                     // k1 of this attempt
-    double Sb[EQ], Sbt[EQ], kfQ[EQ], kcQ[EQ];
+    double Sb[EQ], Sbt[EQ], kcQ[EQ];
 #pragma unroll
-    for (int j = 0; j < EQ; j++) { Sb[j] = 0; Sbt[j] = 0; kfQ[j] = kFQ[j]; kcQ[j] = kFQ[j]; }
+    for (int j = 0; j < EQ; j++) { Sb[j] = 0; Sbt[j] = 0; kcQ[j] = kFQ[j]; }
     double nt = ntfli;
     unsigned nf_s = nf;
     const int s_first = LWFB_VOTE_ANY(reeval && can_step) ? 0 : 1;
     if (!__any_sync(LFULL, can_step && live)) {
       // no member of THIS warp steps (all wait at the day boundary for slower members of the block, or are done):
       // keep the block's barrier choreography and issue nothing else
+#ifdef LWFB_STAGE_SYNC_MASK
+      for (int s = s_first; s <= 6; s++) if ((LWFB_STAGE_SYNC_MASK >> s) & 1) LWFB_STAGE_SYNC();
+#else
       for (int s = s_first; s <= 6; s++) LWFB_STAGE_SYNC();
+#endif
       continue;
     }
     const bool gw_feedback = __any_sync(LFULL, !(LC(KC_GSC) < 1.0e-8));   // GWAT enters the RHS only through GSC >= 1e-8
 #pragma unroll 1
     for (int s = s_first; s <= 6; s++) {
+#ifdef LWFB_STAGE_SYNC_MASK
+      if ((LWFB_STAGE_SYNC_MASK >> s) & 1) LWFB_STAGE_SYNC();
+#else
       LWFB_STAGE_SYNC();
+#endif
       // ---- stage input
       if (s == 1) {
         const double a = dt_s * 0.161;
-        xy = y + a * kfy; xG = G + a * kfG;
-        aEy = lBT[1] * kfy; aEG = lBT[1] * kfG; SbG = lB7[1] * kfG;
+        xy = y + a * kFy; xG = G + a * kFG;
+        aEy = lBT[1] * kFy; aEG = lBT[1] * kFG; SbG = lB7[1] * kFG;
 #pragma unroll
-        for (int p = 0; p < 5; p++) qy[p] = lCQ[1][p] * kfy;
+        for (int p = 0; p < 5; p++) qy[p] = lCQ[1][p] * kFy;
         if (gw_feedback) {
 #pragma unroll
-          for (int p = 0; p < 4; p++) qG[p] = lCQ[1][p] * kfG;
+          for (int p = 0; p < 4; p++) qG[p] = lCQ[1][p] * kFG;
         }
 #pragma unroll
-        for (int j = 0; j < EQ; j++) { Sb[j] = lB7[1] * kfQ[j]; Sbt[j] = lBT[1] * kfQ[j]; }
+        for (int j = 0; j < EQ; j++) { Sb[j] = lB7[1] * kFQ[j]; Sbt[j] = lBT[1] * kFQ[j]; }
       } else if (s >= 2) {
         xy = y + dt_s * qy[0];
 #pragma unroll
@@ -391,8 +408,8 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
           SAFRAC = jminc(lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (sq - SWATQF) / (LC(KC_SWATQX) - SWATQF)), 1.0);
         }
       }
-      const double SRFL = jminc(LC(KC_IMPERV) + SAFRAC, 1.) * (RNET + SMLT);
-      const double SLFL = RNET + SMLT - SRFL;
+      const double SRFL = jminc(LC(KC_IMPERV) + SAFRAC, 1.) * RS;
+      const double SLFL = RS - SRFL;
       DSFLI = 0;
       const bool any_slope = __any_sync(LFULL, SLOPE);
       if (any_slope) {
@@ -524,10 +541,11 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       // ---- end of RHS
 
       if (s == 0) {
-        if (!skip0) {
-          kfy = kny; kfG = knG;
+        // the re-evaluated k1 is committed at once: a member that needed it either steps now or has ended
+        if (!skip0 && can_step) {
+          kFy = kny; kFG = knG;
 #pragma unroll
-          for (int j = 0; j < EQ; j++) kfQ[j] = knQ[j];
+          for (int j = 0; j < EQ; j++) kFQ[j] = knQ[j];
         }
       } else {
         const int ks = s + 1;
@@ -591,9 +609,6 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     double dtt = 0;
     if (do_step) {
       nf = nf_s; ntfli = nt;
-      kFy = kfy; kFG = kfG;
-#pragma unroll
-      for (int j = 0; j < EQ; j++) kFQ[j] = kfQ[j];
       reeval = false;
       cand_nan = (xy != xy);
       if (acc_s) {
@@ -663,8 +678,6 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       const double S1 = y;
       const double w1 = jminc((LC(KC_THSAT) * S1 / LC(KC_SWATMAX) - THR) / DTH, 1.0);
       const double th1 = w1 * DTH + THR;
-      const double Tk = TA + 273.15;
-      const double ee = lwfb_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
       const double sumT = LC(KC_SUMT), sumT_V = LC(KC_SUMT_V);
       const double tauth = lwfb_pow(th1, 7.0 / 3) / LC(KC_THS2);
       const double aq = LC(KC_LAM) * fabs(div_z(VV, 1000.0));
@@ -676,8 +689,8 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 #pragma unroll 1
       for (int s = 0; s < 2; s++) {
         const double R = s == 0 ? R18 : R2H;
-        const double D0 = (s == 0 ? 0.96691 : 0.98331) * 1e-9 * ee * 3600 * 24;
-        const double dSs = s == 0 ? dS[0] : dS[1], dGs = s == 0 ? dG[0] : dG[1], dXYs = s == 0 ? dXY[0] : dXY[1];
+        const double D0 = LC(KC_D0_18O + s);
+        const double dSs = LC(KC_DS_18O + s), dGs = LC(KC_DG_18O + s), dXYs = LC(KC_DXY_18O + s);
         const double dps = s == 0 ? dp[0] : dp[1];
         // the three member-level mixing ratios (xylem, precipitation, groundwater) are converted by lanes 0, 1, 2 of the
         // group in ONE evaluation of d_to_x and broadcast
@@ -714,9 +727,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
         const double dRW = nouptake ? NAN : dRWc;
         const double ddxy = (dRW != dRW) ? 0.0 : sumT_V * (dRW - dXYs);
         if (do_ade) {
-          const double nG = dGs + dtt * ddG, nS = dSs + dtt * dd, nXY = dXYs + dtt * ddxy;
-          if (s == 0) { dG[0] = nG; dS[0] = nS; dXY[0] = nXY; }
-          else { dG[1] = nG; dS[1] = nS; dXY[1] = nXY; }
+          SETK(KC_DG_18O + s, dGs + dtt * ddG); SETK(KC_DS_18O + s, dSs + dtt * dd); SETK(KC_DXY_18O + s, dXYs + dtt * ddxy);
           if (top && live) FIN(ix.RWU + 1 + s) = dRW;
         }
       }

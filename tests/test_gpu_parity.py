@@ -195,6 +195,7 @@ def test_adaptive_placement_is_result_neutral(dav_full):
     ens = en.make_ensemble(dav_full, 300)
     h, sub, nd = gpu_run(ens, 150)
     first = h.get_daily(); st1, cnt1 = h.get_status()
+    h.set_placement(2)                        # mode 1 sorts only launches of several waves; 2 sorts always
     h.run()                                   # placement now sorted by the first run's RHS counts
     second = h.get_daily(); st2, cnt2 = h.get_status()
     assert np.array_equal(first, second, equal_nan=True) and np.array_equal(st1, st2) and np.array_equal(cnt1, cnt2)
