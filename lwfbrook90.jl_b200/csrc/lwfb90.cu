@@ -148,6 +148,7 @@ struct lwfb_handle {
   // placement of members in the lane kernel's slots (lwfb_set_placement)
   int placement = 1;           // 0 identity, 1 adaptive (cost-sorted from the previous run), 2 the same for any launch size
   int32_t* d_perm = nullptr;
+  double* d_ck = nullptr;      // checkpoint block of the segmented execution [LWFB_CK + N][M]
   bool perm_valid = false;     // d_perm holds a permutation for the current member count
   bool cost_valid = false;     // d_counters holds the RHS-evaluation counts of a completed lane-kernel run
   std::string err;
@@ -196,8 +197,8 @@ extern "C" int lwfb_create(lwfb_handle** out, const lwfb_opts* opts) {
 
 static void free_members(lwfb_handle* h) {
   cudaFree(h->d_scal); cudaFree(h->d_lay); cudaFree(h->d_u0); cudaFree(h->d_rec); cudaFree(h->d_fin);
-  cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm);
-  h->d_perm = nullptr; h->perm_valid = false; h->cost_valid = false;
+  cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm); cudaFree(h->d_ck);
+  h->d_perm = nullptr; h->d_ck = nullptr; h->perm_valid = false; h->cost_valid = false;
   h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
   h->d_site = h->d_status = nullptr; h->d_counters = nullptr;
   h->M = 0; h->ran = false;
@@ -281,6 +282,7 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
     CK(cudaMalloc(&h->d_counters, (size_t)M * LWFB_NCOUNTERS * sizeof(long long)));
     CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
     CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
+    CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + N) * sizeof(double)));
     if (h->o.record_daily) {
       size_t bytes = (size_t)M * (h->o.n_days + 1) * L * sizeof(double);
       cudaError_t e = cudaMalloc(&h->d_rec, bytes);
@@ -306,37 +308,39 @@ static DevData make_dev(lwfb_handle* h) {
   d.rec = h->d_rec; d.fin = h->d_fin; d.status = h->d_status; d.counters = h->d_counters;
   d.reltol = h->o.reltol; d.abstol = h->o.abstol; d.dt_init = h->o.dt_init; d.dtmax = h->o.dtmax;
   d.maxiters = h->o.maxiters;
+  d.seg_day0 = h->o.t0_day; d.seg_day1 = h->o.t0_day + h->o.n_days; d.resume = 0; d.ck = h->d_ck;
   return d;
 }
 
-extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
-  if (!h || h->M < 1) return LWFB_ERR_ARG;
-  CK(cudaSetDevice(h->o.device));
-  cudaStream_t st = (cudaStream_t)cuda_stream;
-  const bool lanes = h->o.n_layers >= 3 && h->o.n_layers <= 32 && !h->force_legacy;
-  // Sorting concentrates the expensive members in few blocks: good when the blocks outnumber the resident slots several
-  // times (the block scheduler balances), bad for a launch of one or two waves (it only makes the slowest block slower).
+static bool use_lanes(const lwfb_handle* h) { return h->o.n_layers >= 3 && h->o.n_layers <= 32 && !h->force_legacy; }
+
+// Sorting concentrates the expensive members in few blocks: good when the blocks outnumber the resident slots several
+// times (the block scheduler balances), bad for a launch of one or two waves (it only makes the slowest block slower).
+static bool many_waves(const lwfb_handle* h) {
+  if (h->placement == 2) return true;
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->o.device);
-  const int64_t members_per_block = (int64_t)(LWFB_LANES_BLOCK / 32) * (32 / (lanes ? h->o.n_layers : 32));
-  const int64_t n_blocks = lanes ? (h->M + members_per_block - 1) / members_per_block : 0;
-  const bool many_waves = h->placement == 2 || n_blocks >= 3 * (int64_t)n_sm * LWFB_LANES_MINBLOCKS;
-  if (lanes && h->placement >= 1 && !many_waves) h->perm_valid = false;
-  if (lanes && h->placement >= 1 && h->cost_valid && many_waves) {
-    // adaptive placement: members sorted by the number of RHS evaluations of the previous run (most expensive first),
-    // so that the members that share a block (and wait for each other at every step) have similar step counts
-    std::vector<long long> nf((size_t)h->M);
-    CK(cudaMemcpy(nf.data(), h->d_counters + (size_t)LWFB_C_NF * h->M, nf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    std::vector<int32_t> perm((size_t)h->M);
-    for (int64_t i = 0; i < h->M; i++) perm[(size_t)i] = (int32_t)i;
-    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return nf[(size_t)a] > nf[(size_t)b]; });
-    CK(cudaMemcpy(h->d_perm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    h->perm_valid = true;
-    h->cost_valid = false;
-  }
-  DevData d = make_dev(h);
-  CK(cudaEventRecord(h->ev0, st));
-  if (lanes) {
+  const int64_t members_per_block = (int64_t)(LWFB_LANES_BLOCK / 32) * (32 / h->o.n_layers);
+  const int64_t n_blocks = (h->M + members_per_block - 1) / members_per_block;
+  return n_blocks >= 3 * (int64_t)n_sm * LWFB_LANES_MINBLOCKS;
+}
+
+// placement := members sorted by the number of RHS evaluations counted so far (most expensive first), so that the
+// members that share a block (and wait for each other at every step) have similar step counts
+static int sort_members_by_cost(lwfb_handle* h) {
+  std::vector<long long> nf((size_t)h->M);
+  CK(cudaMemcpy(nf.data(), h->d_counters + (size_t)LWFB_C_NF * h->M, nf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  std::vector<int32_t> perm((size_t)h->M);
+  for (int64_t i = 0; i < h->M; i++) perm[(size_t)i] = (int32_t)i;
+  std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return nf[(size_t)a] > nf[(size_t)b]; });
+  CK(cudaMemcpy(h->d_perm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  h->perm_valid = true;
+  return LWFB_OK;
+}
+
+// one launch of the integrator over the days (d.seg_day0, d.seg_day1]
+static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) {
+  if (use_lanes(h)) {
     // production path: one lane per soil layer, 32/N members per warp; per-thread constants in shared memory
     const int mpw = 32 / d.N;
     const int64_t warps = (d.M + mpw - 1) / mpw;
@@ -358,8 +362,29 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
     launch_member_integrate(d, st);   // thread-per-member, runtime layer count (N < 3 or N > 32)
   }
   CK(cudaGetLastError());
+  h->n_launches++;
+  return LWFB_OK;
+}
+
+// single launch over the whole record; with adaptive placement the members are sorted by the cost of the previous run
+extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
+  if (!h || h->M < 1) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const bool lanes = use_lanes(h);
+  const bool sortable = lanes && h->placement >= 1 && many_waves(h);
+  if (lanes && !sortable) h->perm_valid = false;
+  if (sortable && h->cost_valid) {
+    int rc = sort_members_by_cost(h);
+    if (rc) return rc;
+    h->cost_valid = false;
+  }
+  DevData d = make_dev(h);
+  h->n_launches = 0;
+  CK(cudaEventRecord(h->ev0, st));
+  int rc = launch_integrator(h, d, st);
+  if (rc) return rc;
   CK(cudaEventRecord(h->ev1, st));
-  h->n_launches = 1;
   h->ran = true;
   h->cost_valid = lanes;
   return LWFB_OK;
@@ -373,9 +398,41 @@ extern "C" int lwfb_sync(lwfb_handle* h) {
   return LWFB_OK;
 }
 
+// Synchronous run.  A handle that has no cost information yet (first run, new member count) and enough members for
+// sorting to pay integrates the record in SEGMENTS of LWFB_SEG_DAYS days (default 30): after each segment the members
+// are re-sorted by the RHS evaluations they needed so far, and the next launch resumes every member at the day boundary
+// from its state vector in HBM plus a small checkpoint (controller state, counters, du_NTFLI).  Results are identical
+// to a single launch.
 extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
-  int rc = lwfb_run_async(h, cuda_stream);
-  if (rc) return rc;
+  if (!h || h->M < 1) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  int seg = 30;
+  if (const char* e = getenv("LWFB_SEG_DAYS")) seg = atoi(e);
+  const bool segmented = use_lanes(h) && h->placement >= 1 && !h->cost_valid && seg > 0 && h->o.n_days > seg && many_waves(h);
+  if (!segmented) {
+    int rc = lwfb_run_async(h, cuda_stream);
+    if (rc) return rc;
+    return lwfb_sync(h);
+  }
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  h->perm_valid = false;
+  h->n_launches = 0;
+  CK(cudaEventRecord(h->ev0, st));
+  for (int d0 = 0; d0 < h->o.n_days; d0 += seg) {
+    DevData d = make_dev(h);
+    d.seg_day0 = h->o.t0_day + d0;
+    d.seg_day1 = h->o.t0_day + (d0 + seg < h->o.n_days ? d0 + seg : h->o.n_days);
+    d.resume = d0 > 0;
+    int rc = launch_integrator(h, d, st);
+    if (rc) return rc;
+    if (d0 + seg < h->o.n_days) {
+      CK(cudaStreamSynchronize(st));
+      if ((rc = sort_members_by_cost(h))) return rc;
+    }
+  }
+  CK(cudaEventRecord(h->ev1, st));
+  h->ran = true;
+  h->cost_valid = true;
   return lwfb_sync(h);
 }
 

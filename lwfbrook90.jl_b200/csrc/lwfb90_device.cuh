@@ -63,7 +63,13 @@ struct DevData {
   long long* __restrict__ counters;  // [LWFB_NCOUNTERS][M]
   double reltol, abstol, dt_init, dtmax;
   long long maxiters;
+  // segmented execution of the lane kernel (one launch per segment of days, state carried in fin + ck):
+  int seg_day0, seg_day1;            // this launch integrates (seg_day0, seg_day1]; seg_day0 == t0_day && !resume: fresh start
+  int resume;                        // 1: continue at the day boundary seg_day0 from fin / ck
+  double* __restrict__ ck;           // [LWFB_CK + N][M] member-level controller state + per-layer du_NTFLI (null: single launch)
 };
+// rows of the checkpoint block
+enum { LWFB_CK_DT = 0, LWFB_CK_QOLD, LWFB_CK_ITER, LWFB_CK_NACCEPT, LWFB_CK_NREJECT, LWFB_CK_NF, LWFB_CK_REC, LWFB_CK_PAD, LWFB_CK };
 
 // state-vector offsets, src/func_DiffEq_definition_u0.jl:42-73
 struct SIdx {

@@ -152,24 +152,28 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   const unsigned grpmask = (N == 32) ? LFULL : (((1u << N) - 1u) << base);
 
   // ---- live state: fin := u0 (then kept current at day boundaries); registers for what evolves per step
-  if (live) for (int j = i; j < L; j += N) FIN(j) = U0(j);
-  double y = U0(ix.SWATI + i), G = U0(ix.GWAT);
+  const bool resume = d.resume != 0;                 // continue at the day boundary d.seg_day0 (segmented execution)
+  auto CKP = [&](int r) -> double& { return d.ck[(int64_t)r * M + m]; };
+  if (live && !resume) for (int j = i; j < L; j += N) FIN(j) = U0(j);
+  __syncwarp(LFULL);
+  double y = FIN(ix.SWATI + i), G = FIN(ix.GWAT);
   double Q[EQ], kFQ[EQ];
   int qe[EQ];                                        // accumulator held in slot j (>= 8: none)
 #pragma unroll
   for (int j = 0; j < EQ; j++) {
     qe[j] = i + j * N;
-    Q[j] = qe[j] < 8 ? U0(ix.ACC + lAccPos[qe[j] & 7]) : 0.0;
+    Q[j] = qe[j] < 8 ? FIN(ix.ACC + lAccPos[qe[j] & 7]) : 0.0;
     kFQ[j] = 0;
   }
   double kFy = 0, kFG = 0;                           // FSAL derivative of SWATI / GWAT
   auto SETK = [&](int k, double v) { cst[k * LWFB_LANES_BLOCK] = v; };
   for (int s = 0; s < 2; s++) {
-    SETK(KC_DS_18O + s, iso ? U0(ix.SWATI + (s + 1) * N + i) : 0.0);
-    SETK(KC_DG_18O + s, iso ? U0(ix.GWAT + 1 + s) : 0.0);
-    SETK(KC_DXY_18O + s, iso ? U0(ix.XYLEM + 1 + s) : 0.0);
+    SETK(KC_DS_18O + s, iso ? FIN(ix.SWATI + (s + 1) * N + i) : 0.0);
+    SETK(KC_DG_18O + s, iso ? FIN(ix.GWAT + 1 + s) : 0.0);
+    SETK(KC_DXY_18O + s, iso ? FIN(ix.XYLEM + 1 + s) : 0.0);
   }
-  double TRANI = NAN, ntfli = NAN;                   // frozen uptake of the layer; du_NTFLI of the previous RHS call
+  double TRANI = NAN;                                // frozen uptake of the layer
+  double ntfli = resume ? CKP(LWFB_CK + i) : NAN;    // du_NTFLI of the previous RHS call (NaN on a fresh problem)
   double RS = NAN, SLVP = NAN;                        // RNET + SMLT and SLVP of the day
   double VV = 0, INFLI = 0, DSFLI = 0;               // flux caches of the last RHS (isotope step)
 
@@ -202,23 +206,30 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 
   const double qmin = 0.2, qmax = 10.0, gamma = 0.9, beta1 = 0.14, beta2 = 0.08, qoldinit = 1e-4;
   const double t0 = (double)d.t0_day, tend = (double)(d.t0_day + d.n_days);
-  double t = t0, dt = d.dt_init, qold = qoldinit, tstop = t0;
+  const double tend_seg = (double)d.seg_day1;        // this launch stops at this day boundary (== tend without segments)
+  double t = resume ? (double)d.seg_day0 : t0, tstop = t;
+  double dt = resume ? CKP(LWFB_CK_DT) : d.dt_init, qold = resume ? CKP(LWFB_CK_QOLD) : qoldinit;
   const double dtmin_opt = fmax(eps_of(tend), eps_of(t0));
   const unsigned maxiters = d.maxiters > 0x7fffffffLL ? 0x7fffffffu : (unsigned)d.maxiters;
   unsigned naccept = 0, nreject = 0, iter = 0, nf = 0;
   bool reeval = false, at_boundary = true, cand_nan = (y != y);
   int status = LWFB_ST_OK;
   int rec = 1;
+  if (resume) {
+    iter = (unsigned)CKP(LWFB_CK_ITER); naccept = (unsigned)CKP(LWFB_CK_NACCEPT); nreject = (unsigned)CKP(LWFB_CK_NREJECT);
+    nf = (unsigned)CKP(LWFB_CK_NF); rec = (int)CKP(LWFB_CK_REC); status = d.status[m];
+  }
+  const int status_in = status;
 #ifdef LWFB_DEBUG_ITERS
   unsigned dbg_iters = 0;          // step-phase iterations of the block (profiling: lock-step waiting overhead)
   unsigned dbg_day_iter0 = 0;
 #endif
 
-  if (d.rec && live) for (int j = i; j < L; j += N) d.rec[(int64_t)j * M + m] = U0(j);     // record 0 = raw u0
+  if (d.rec && live && !resume) for (int j = i; j < L; j += N) d.rec[(int64_t)j * M + m] = U0(j);     // record 0 = raw u0
   __syncwarp(LFULL);
 
   for (;;) {
-    const bool active = (status == LWFB_ST_OK) && (t < tend);
+    const bool active = (status == LWFB_ST_OK) && (t < tend_seg);
     if (!LWFB_VOTE_ANY(active && live)) break;
     const bool can_step = active && !at_boundary;
 
@@ -734,7 +745,17 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     }
   }
   if (live) {
-    if (d.rec) {
+    if (d.ck) {
+      // checkpoint for the next segment: controller state and counters of the member, du_NTFLI of the layer
+      CKP(LWFB_CK + i) = ntfli;
+      if (top) {
+        CKP(LWFB_CK_DT) = dt; CKP(LWFB_CK_QOLD) = qold; CKP(LWFB_CK_ITER) = (double)iter;
+        CKP(LWFB_CK_NACCEPT) = (double)naccept; CKP(LWFB_CK_NREJECT) = (double)nreject; CKP(LWFB_CK_NF) = (double)nf;
+        CKP(LWFB_CK_REC) = (double)rec;
+      }
+    }
+    if (d.rec && status != LWFB_ST_OK && status_in == LWFB_ST_OK) {
+      // the member ended in this launch before the end of the record: the records it did not reach are NaN
       for (; rec <= d.n_days; rec++) {
         double* dst = d.rec + (int64_t)rec * L * M;
         for (int j = i; j < L; j += N) dst[(int64_t)j * M + m] = NAN;

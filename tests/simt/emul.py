@@ -43,7 +43,7 @@ def lib():
         _lib.lwfb_emul_run.restype = C.c_int
         _lib.lwfb_emul_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int64, _ip,
                                        _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int,
-                                       _dp, _ip, _lp, _ip]
+                                       _dp, _ip, _lp, _ip, C.c_int, C.c_int]
     return _lib
 
 
@@ -52,8 +52,9 @@ def _p(a, t=_dp):
 
 
 def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, *, reltol=1e-5, abstol=1e-6,
-        dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000, n_threads=8, perm=None):
-    """Same shapes and return values as oracle.run.  perm: optional placement (slot -> member) of the lane kernel."""
+        dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000, n_threads=8, perm=None, seg_len=0, resort=False):
+    """Same shapes and return values as oracle.run.  perm: optional placement (slot -> member) of the lane kernel;
+    seg_len > 0: segmented execution (one launch per seg_len days), resort: re-sort the members between segments."""
     forcing = np.ascontiguousarray(forcing, dtype=np.float64)
     if forcing.ndim == 2:
         forcing = forcing[None]
@@ -71,7 +72,8 @@ def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, 
     rc = lib().lwfb_emul_run(int(kernel), N, int(iso), int(t0_day), int(n_days), n_sites, n_rows, _p(forcing), M, _p(som, _ip),
                              _p(scal), _p(lay), _p(u0), reltol, abstol, dt_init, dtmax, maxiters, int(n_threads), _p(out),
                              _p(status, _ip), _p(counters, _lp),
-                             None if perm is None else _p(np.ascontiguousarray(perm, dtype=np.int32), _ip))
+                             None if perm is None else _p(np.ascontiguousarray(perm, dtype=np.int32), _ip),
+                             int(seg_len), int(bool(resort)))
     if rc != 0:
         raise RuntimeError(f"lwfb_emul_run failed ({rc})")
     return out, status, counters

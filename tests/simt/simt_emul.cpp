@@ -16,6 +16,7 @@
 #include <stdlib.h>
 #include <ucontext.h>
 
+#include <algorithm>
 #include <atomic>
 #include <vector>
 
@@ -169,7 +170,7 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
                              const double* forcing, int64_t M, const int32_t* site_of_member, const double* scal,
                              const double* lay, const double* u0, double reltol, double abstol, double dt_init,
                              double dtmax, int64_t maxiters, int n_threads, double* out_daily, int32_t* status,
-                             int64_t* counters, const int32_t* perm) {
+                             int64_t* counters, const int32_t* perm, int seg_len, int resort) {
   (void)n_sites;
   const int L = LWFB_STATE_LEN(N, iso);
   if (kernel == 0 && (N < 3 || N > 32)) return -1;
@@ -189,9 +190,26 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   if (kernel == 0) { const int mpw = 32 / N; job.n_units = (M + mpw - 1) / mpw; }
   else job.n_units = M;
   if (n_threads < 1) n_threads = 1;
-  std::vector<pthread_t> th(n_threads);
-  for (int i = 0; i < n_threads; i++) pthread_create(&th[i], nullptr, worker, &job);
-  for (int i = 0; i < n_threads; i++) pthread_join(th[i], nullptr);
+  // segmented execution as in lwfb_run: one "launch" per segment, members re-sorted by their RHS count so far
+  std::vector<double> ck((size_t)(lwfb::LWFB_CK + N) * M);
+  std::vector<int32_t> perm2((size_t)M);
+  if (kernel != 0 || seg_len <= 0 || seg_len >= n_days) seg_len = n_days;
+  d.ck = ck.data();
+  for (int d0 = 0; d0 < n_days; d0 += seg_len) {
+    d.seg_day0 = t0_day + d0;
+    d.seg_day1 = t0_day + (d0 + seg_len < n_days ? d0 + seg_len : n_days);
+    d.resume = d0 > 0;
+    if (d0 > 0 && resort) {
+      for (int64_t i = 0; i < M; i++) perm2[(size_t)i] = (int32_t)i;
+      std::stable_sort(perm2.begin(), perm2.end(), [&](int32_t a, int32_t b) {
+        return cnt[(size_t)LWFB_C_NF * M + a] > cnt[(size_t)LWFB_C_NF * M + b]; });
+      d.perm = perm2.data();
+    }
+    job.next = 0;
+    std::vector<pthread_t> th(n_threads);
+    for (int i = 0; i < n_threads; i++) pthread_create(&th[i], nullptr, worker, &job);
+    for (int i = 0; i < n_threads; i++) pthread_join(th[i], nullptr);
+  }
   // [day][L][M] -> [M][day][L]
   const int64_t K = (int64_t)(n_days + 1) * L;
   for (int64_t m = 0; m < M; m++)

@@ -103,6 +103,20 @@ def test_lane_kernel_placement_does_not_change_results(dav_full):
     assert np.array_equal(got, ref, equal_nan=True)
 
 
+def test_lane_kernel_segmented_execution_with_resorting(dav_full, isobea):
+    """One launch per segment of days, members re-sorted by their RHS count between the launches (what lwfb_run does
+    for a handle without cost information): every member resumes at the day boundary from its state vector plus the
+    checkpoint block.  Must equal the oracle's single pass, also with one-day segments."""
+    for sim, M, nd, seg in ((dav_full, 14, 11, 3), (dav_full, 7, 5, 1), (isobea, 5, 7, 2)):
+        e = en.make_ensemble(sim, M)
+        orc.use("elem")
+        ref, st_o, cnt_o = orc.run(e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, n_threads=8)
+        got, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
+                                seg_len=seg, resort=True)
+        assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
+        assert np.array_equal(got, ref, equal_nan=True)
+
+
 def test_emulator_rejects_divergent_warp_primitives():
     """The emulator aborts when lanes meet at different warp primitives; a well-formed run reports none.  (The
     abort path itself is exercised by the build of every kernel change: a divergent shuffle never gets here.)"""
