@@ -179,6 +179,77 @@ LWFB_ELEM double lwfb_pow_from_log(double x, double lx, double y) {
 /* the same for exponents known to be non-zero (saves the select) */
 LWFB_ELEM double lwfb_pow_from_log_nz(double lx, double y) { return lwfb_exp(y * lx); }
 
+
+/* ---- interleaved evaluations -------------------------------------------------------------------------------------
+ * lwfb_exp2 / lwfb_exp3 / lwfb_log_main2 evaluate two or three INDEPENDENT arguments with the operations of the
+ * chains written alternately, so that the dependent FMA chains of the polynomials overlap in the FP64 pipe (the
+ * compiler keeps each inlined call as one serial chain otherwise).  Every chain performs exactly the operations of
+ * the scalar function: the results are bit-identical to lwfb_exp / lwfb_log_main. */
+#if defined(__CUDACC__)
+#define LWFB_UNROLL _Pragma("unroll")
+#else
+#define LWFB_UNROLL
+#endif
+#define LWFB_EXP_HEAD(x, big, kf, r, q) \
+  const int big = (int)((uint64_t)lwfb_d2i(x) >> 32 & 0x7fffffffu) >= 0x40875800; \
+  double kf = rint(x * LWFB_EC(13)); \
+  double r = fma(-kf, LWFB_EC(14), x); \
+  r = fma(-kf, LWFB_EC(15), r); \
+  double q = LWFB_EC(0);
+#define LWFB_EXP_TAIL(x, big, kf, r, q, out) { \
+  double res = 1.0 + fma(r * r, q, r); \
+  int k = big ? 0 : (int)kf; \
+  int adj = k > 1023 ? 1023 : (k < -1021 ? -1000 : 0); \
+  res = res * lwfb_i2d((int64_t)(adj + 1023) << 52); \
+  k -= adj; \
+  res = res * lwfb_i2d((int64_t)(k + 1023) << 52); \
+  const double special = !(x <= 0.0) ? x * INFINITY : 0.0; \
+  out = big ? special : res; }
+LWFB_ELEM void lwfb_exp2(double x1, double x2, double* o1, double* o2) {
+  LWFB_EXP_HEAD(x1, b1, k1, r1, q1)
+  LWFB_EXP_HEAD(x2, b2, k2, r2, q2)
+  LWFB_UNROLL
+  for (int j = 1; j <= 12; j++) { q1 = fma(q1, r1, LWFB_EC(j)); q2 = fma(q2, r2, LWFB_EC(j)); }
+  LWFB_EXP_TAIL(x1, b1, k1, r1, q1, *o1)
+  LWFB_EXP_TAIL(x2, b2, k2, r2, q2, *o2)
+}
+LWFB_ELEM void lwfb_exp3(double x1, double x2, double x3, double* o1, double* o2, double* o3) {
+  LWFB_EXP_HEAD(x1, b1, k1, r1, q1)
+  LWFB_EXP_HEAD(x2, b2, k2, r2, q2)
+  LWFB_EXP_HEAD(x3, b3, k3, r3, q3)
+  LWFB_UNROLL
+  for (int j = 1; j <= 12; j++) { q1 = fma(q1, r1, LWFB_EC(j)); q2 = fma(q2, r2, LWFB_EC(j)); q3 = fma(q3, r3, LWFB_EC(j)); }
+  LWFB_EXP_TAIL(x1, b1, k1, r1, q1, *o1)
+  LWFB_EXP_TAIL(x2, b2, k2, r2, q2, *o2)
+  LWFB_EXP_TAIL(x3, b3, k3, r3, q3, *o3)
+}
+#define LWFB_LOG_HEAD(x, e, f, s, z, R) \
+  int e; double f, s, z, R; { \
+  int64_t ix = lwfb_d2i(x); \
+  e = (int)((ix >> 52) & 0x7ff) - 1023; \
+  ix = (ix & 0x000fffffffffffffLL) | 0x3ff0000000000000LL; \
+  double m = lwfb_i2d(ix); \
+  int big = m > LWFB_LGC(14); \
+  m = big ? m * 0.5 : m; \
+  e += big; \
+  f = m - 1.0; \
+  s = f / (2.0 + f); \
+  z = s * s; \
+  R = LWFB_LGC(0); }
+#define LWFB_LOG_TAIL(e, f, s, z, R, out) { \
+  double Rz = R * z; \
+  double hfsq = 0.5 * f * f; \
+  double dk = (double)e; \
+  out = dk * LWFB_LGC(12) - ((hfsq - (s * (hfsq + Rz) + dk * LWFB_LGC(13))) - f); }
+LWFB_ELEM void lwfb_log_main2(double x1, double x2, double* o1, double* o2) {
+  LWFB_LOG_HEAD(x1, e1, f1, s1, z1, R1)
+  LWFB_LOG_HEAD(x2, e2, f2, s2, z2, R2)
+  LWFB_UNROLL
+  for (int j = 1; j <= 11; j++) { R1 = fma(R1, z1, LWFB_LGC(j)); R2 = fma(R2, z2, LWFB_LGC(j)); }
+  LWFB_LOG_TAIL(e1, f1, s1, z1, R1, *o1)
+  LWFB_LOG_TAIL(e2, f2, s2, z2, R2, *o2)
+}
+
 /* sin and cos kernels on |r| <= pi/4 (Taylor, exact coefficients 1/n!) */
 LWFB_ELEM double lwfb_ksin(double r) {
   double z = r * r;

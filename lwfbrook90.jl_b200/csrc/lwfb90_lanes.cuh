@@ -150,6 +150,10 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     SETC(KC_LAM, pv.S(LWFB_S_DISPERSIVITY)); SETC(KC_VXYLEM, pv.S(LWFB_S_VXYLEM));
   }
   const unsigned grpmask = (N == 32) ? LFULL : (((1u << N) - 1u) << base);
+  // warp-uniform switches, voted once (inside the loops they would be re-derived from global memory at every use)
+  const bool any_bypar = __any_sync(LFULL, BYPAR), any_qlayer = __any_sync(LFULL, QLAYER > 0);
+  const bool any_slope = __any_sync(LFULL, SLOPE);
+  const bool gw_feedback = __any_sync(LFULL, !(pv.S(LWFB_S_GSC) < 1.0e-8));   // GWAT enters the RHS only through GSC >= 1e-8
 
   // ---- live state: fin := u0 (then kept current at day boundaries); registers for what evolves per step
   const bool resume = d.resume != 0;                 // continue at the day boundary d.seg_day0 (segmented execution)
@@ -340,7 +344,6 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 #endif
       continue;
     }
-    const bool gw_feedback = __any_sync(LFULL, !(LC(KC_GSC) < 1.0e-8));   // GWAT enters the RHS only through GSC >= 1e-8
 #pragma unroll 1
     for (int s = s_first; s <= 6; s++) {
 #ifdef LWFB_STAGE_SYNC_MASK
@@ -389,29 +392,33 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       // a in [1e-6, 1]: log on its main path.  The exponents -1/m, n/(n-1), 1/n, 1-1/n are non-zero for every valid
       // van Genuchten n (finite, > 1), so x^y = exp(y log x) needs no y == 0 case; only the tortuosity l may be 0.
       const double la = lwfb_log_main(a);
-      const double p1 = lwfb_pow_from_log_nz(la, LC(KC_E1));
-      const double p3 = lwfb_pow_from_log_nz(la, LC(KC_E3));
-      const double pT = lwfb_pow_from_log(a, la, LC(KC_TORT));
+      const double TORT = LC(KC_TORT);
+      double p1, p3, pT;                                      // a^(-1/m), a^(n/(n-1)), a^l: three chains interleaved
+      lwfb_exp3(LC(KC_E1) * la, LC(KC_E3) * la, TORT * la, &p1, &p3, &pT);
+      pT = (TORT == 0.0) ? 1.0 : pT;                          // x^0 = 1 also where exp(0 * log x) would not say so
       const double x1 = p1 - 1.0, x3 = 1.0 - p3;             // both are 0 at saturation (log -> -inf, power -> 0)
-      double l1 = lwfb_log_main(x1), l3 = lwfb_log_main(x3);  // two independent chains, then the rare fix-ups
+      double l1, l3;
+      lwfb_log_main2(x1, x3, &l1, &l3);                       // two interleaved chains, then the rare fix-ups
       if (lwfb_log_isspecial(x1)) l1 = lwfb_log_cold(x1);
       if (lwfb_log_isspecial(x3)) l3 = lwfb_log_cold(x3);
-      const double psim = LC(KC_CPSI) * lwfb_exp(E2 * l1);
+      double e1, e3;
+      lwfb_exp2(E2 * l1, LC(KC_E4) * l3, &e1, &e3);
+      const double psim = LC(KC_CPSI) * e1;
       const double theta = w * DTH + THR;
-      const double inner = 1.0 - lwfb_exp(LC(KC_E4) * l3);
+      const double inner = 1.0 - e3;
       const double KSAT = LC(KC_KSAT);
       const double kkv = KSAT * pT * (inner * inner);
       const double lk = lwfb_log(kkv);
       const double psit = psim + LC(KC_PSIG);
       double BYFRAC = 0;
-      if (__any_sync(LFULL, BYPAR)) {
+      if (any_bypar) {
         const double WETF = LC(KC_WETF);
         double bf = jminc(lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (w - WETF) / (1 - WETF)), 1.0);
         if (w > 0.99) bf = 1;
         BYFRAC = BYPAR ? bf : 0.0;
       }
       double SAFRAC = 0.;
-      if (__any_sync(LFULL, QLAYER > 0)) {
+      if (any_qlayer) {
         double sq = 0;
         for (int j = 0; j < N; j++) { const double v = bcast(sw, j); if (j < QLAYER) sq += v; }
         if (QLAYER > 0) {
@@ -422,7 +429,6 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       const double SRFL = jminc(LC(KC_IMPERV) + SAFRAC, 1.) * RS;
       const double SLFL = RS - SRFL;
       DSFLI = 0;
-      const bool any_slope = __any_sync(LFULL, SLOPE);
       if (any_slope) {
         const double GRAD = LC(KC_CS) * (psim * 2 / LC(KC_LEN1000)) + LC(KC_SNRHO);
         const double dd = kkv * LC(KC_ARATIO) * GRAD / p_RHOWG;
