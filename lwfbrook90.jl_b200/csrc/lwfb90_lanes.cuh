@@ -472,7 +472,15 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
           if (DTINEW < DTI) DTI = DTINEW;
         } else {
           double gm = v;
-          for (int j = 0; j < N; j++) { const double vj = bcast(v, j); gm = vj < gm ? vj : gm; }
+          if (NMAX <= 8) {
+            double vj[NMAX];
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) vj[j] = bcast(v, j < N ? j : 0);     // independent shuffles, issued back to back
+#pragma unroll
+            for (int j = 0; j < NMAX; j++) gm = vj[j] < gm ? vj[j] : gm;
+          } else {
+            for (int j = 0; j < N; j++) { const double vj = bcast(v, j); gm = vj < gm ? vj : gm; }
+          }
           if (gm < DTI) DTI = gm;
         }
       }
@@ -601,7 +609,15 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
         r = div_z(dt_s * Sbt[j], abstol + jmax_abs(Q[j], Qn[j]) * reltol);
         r2Q[j] = r * r;
       }
-      for (int j = 0; j < N; j++) ss += bcast(r2y, j);
+      if (NMAX <= 8) {
+        double rj[NMAX];
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) rj[j] = bcast(r2y, j < N ? j : 0);
+#pragma unroll
+        for (int j = 0; j < NMAX; j++) if (j < N) ss += rj[j];
+      } else {
+        for (int j = 0; j < N; j++) ss += bcast(r2y, j);
+      }
       ss += r2G;
 #pragma unroll 1
       for (int e = 0; e < 8; e++) ss += q_bcast(r2Q, e);
@@ -785,9 +801,10 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 template <int NMAX, int EQ>
 __global__ void __launch_bounds__(LWFB_LANES_BLOCK, LWFB_LANES_MINBLOCKS) integrate_lanes(DevData d) {
   extern __shared__ double lanes_smem[];
-  double* cst = lanes_smem + threadIdx.x;
-  asm volatile("" : "+l"(cst));     // keep the column address in a register (otherwise it is re-derived from %tid at every use)
-  lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, cst);
+  unsigned tid = threadIdx.x;
+  asm volatile("" : "+r"(tid));     // opaque copy of %tid: the column address stays in a register (it would be re-derived
+                                    // from %tid at every use otherwise) and is still known to point to shared memory
+  lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + tid);
 }
 #endif
 
