@@ -70,6 +70,12 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
 #define LWFB_VOTE_ANY(p) __any_sync(LFULL, (p))
 #define LWFB_STAGE_SYNC() ((void)0)
 #endif
+// A member that has reached its day boundary waits at most this many step iterations of its block for the others;
+// then the daily callback phase runs for the members that are waiting (the rest of the block idles through it).
+// Bounds the cost of one member's bad day for the members that share its block.  Results do not depend on it.
+#ifndef LWFB_CB_WAIT
+#define LWFB_CB_WAIT 32
+#endif
 
 // per-thread constant column (shared memory): element k of this thread is cst[k * LWFB_LANES_BLOCK]
 enum {
@@ -217,6 +223,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   const unsigned maxiters = d.maxiters > 0x7fffffffLL ? 0x7fffffffu : (unsigned)d.maxiters;
   unsigned naccept = 0, nreject = 0, iter = 0, nf = 0;
   bool reeval = false, at_boundary = true, cand_nan = (y != y);
+  int waited = 0;                                    // step iterations spent waiting at the day boundary
   int status = LWFB_ST_OK;
   int rec = 1;
   if (resume) {
@@ -236,8 +243,13 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     const bool active = (status == LWFB_ST_OK) && (t < tend_seg);
     if (!LWFB_VOTE_ANY(active && live)) break;
     const bool can_step = active && !at_boundary;
+    const bool at_cb = active && at_boundary;        // waits for (or is about to get) its daily callback
+    // (two votes: __syncthreads_or returns a truth value, not the OR of the arguments)
+    const bool any_step = LWFB_VOTE_ANY(can_step && live);
+    const bool any_overdue = LWFB_VOTE_ANY(at_cb && live && waited >= LWFB_CB_WAIT);
 
-    if (!LWFB_VOTE_ANY(can_step && live)) {
+    if (!any_step || any_overdue) {
+      if (!__any_sync(LFULL, at_cb)) continue;       // nothing to do in this warp
       // ============================== warp-synchronous daily callback at t = tstop
       // soil state of the own layer (SWCHEK clamps the state itself), then all layers gathered
       const double SWATMAX = LC(KC_SWATMAX), E2 = LC(KC_E2);
@@ -263,7 +275,8 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       cb_core<NMAX>(pv, forc + (int64_t)day * LWFB_F, t, psim0, psiti_a, kk_a, nds, TRANI_a, nRNET, nSMLT, nSLVP, nTA,
                     TRANIst_a, nRWU, cbst);
       __syncwarp(LFULL);                            // every lane has read the day-constant states before lane 0 overwrites them
-      if (active) {
+      if (at_cb) {
+        waited = 0;
         y = sw;
         TRANI = TRANI_a[i];
         {
@@ -308,6 +321,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 #ifdef LWFB_DEBUG_ITERS
     dbg_iters++;
 #endif
+    if (at_cb) waited++;
     // ============================== one attempted step (all lanes execute, only `do_step` lanes commit)
     // loopheader! (dt already holds the controller's proposal / the shrunk step after a rejection)
     double dt_s = dt;
