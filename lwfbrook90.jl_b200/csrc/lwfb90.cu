@@ -399,14 +399,14 @@ extern "C" int lwfb_sync(lwfb_handle* h) {
 }
 
 // Synchronous run.  A handle that has no cost information yet (first run, new member count) and enough members for
-// sorting to pay integrates the record in SEGMENTS of LWFB_SEG_DAYS days (default 30): after each segment the members
+// sorting to pay integrates the record in SEGMENTS of 4, 8, 16, ... up to LWFB_SEG_DAYS days (default 32): after each segment the members
 // are re-sorted by the RHS evaluations they needed so far, and the next launch resumes every member at the day boundary
 // from its state vector in HBM plus a small checkpoint (controller state, counters, du_NTFLI).  Results are identical
 // to a single launch.
 extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   if (!h || h->M < 1) return LWFB_ERR_ARG;
   CK(cudaSetDevice(h->o.device));
-  int seg = 30;
+  int seg = 32;
   if (const char* e = getenv("LWFB_SEG_DAYS")) seg = atoi(e);
   const bool segmented = use_lanes(h) && h->placement >= 1 && !h->cost_valid && seg > 0 && h->o.n_days > seg && many_waves(h);
   if (!segmented) {
@@ -418,17 +418,22 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   h->perm_valid = false;
   h->n_launches = 0;
   CK(cudaEventRecord(h->ev0, st));
-  for (int d0 = 0; d0 < h->o.n_days; d0 += seg) {
+  // segment lengths grow 4, 8, 16, ... up to `seg` days: the first re-sorts come early, when nothing is known yet
+  int len = seg < 4 ? seg : 4;
+  for (int d0 = 0; d0 < h->o.n_days;) {
+    const int d1 = d0 + len < h->o.n_days ? d0 + len : h->o.n_days;
     DevData d = make_dev(h);
     d.seg_day0 = h->o.t0_day + d0;
-    d.seg_day1 = h->o.t0_day + (d0 + seg < h->o.n_days ? d0 + seg : h->o.n_days);
+    d.seg_day1 = h->o.t0_day + d1;
     d.resume = d0 > 0;
     int rc = launch_integrator(h, d, st);
     if (rc) return rc;
-    if (d0 + seg < h->o.n_days) {
+    if (d1 < h->o.n_days) {
       CK(cudaStreamSynchronize(st));
       if ((rc = sort_members_by_cost(h))) return rc;
     }
+    d0 = d1;
+    len = 2 * len < seg ? 2 * len : seg;
   }
   CK(cudaEventRecord(h->ev1, st));
   h->ran = true;

@@ -217,7 +217,7 @@ def test_segmented_cold_run_is_result_neutral(dav_full, monkeypatch):
     h.set_placement(2)                        # segment + sort regardless of the launch size
     h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
     h.run()
-    assert h.last_run_stats()[0] == 9         # ceil(60 / 7) launches
+    assert h.last_run_stats()[0] == 9         # segments of 4, 7, 7, ... days
     assert_bit_identical(h, ens, nd)
     h.close()
 
