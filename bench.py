@@ -113,6 +113,8 @@ def cpu_oracle_rate(ens, n_threads, target_s=15.0):
     import oracle as orc
     orc.use("libm")
     probe = min(ens.M, 4 * n_threads)
+    orc.run(ens.N, ens.iso, ens.t0_day, 3, ens.forcing, ens.site_of_member[:probe], ens.scal[:probe],
+            ens.lay[:probe], ens.u0[:probe], n_threads=n_threads, record=False)      # warm-up (library load, thread start)
     t = time.perf_counter()
     orc.run(ens.N, ens.iso, ens.t0_day, ens.n_days, ens.forcing, ens.site_of_member[:probe], ens.scal[:probe],
             ens.lay[:probe], ens.u0[:probe], n_threads=n_threads, record=False)
