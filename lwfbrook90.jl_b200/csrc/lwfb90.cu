@@ -346,7 +346,7 @@ static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) 
     const int64_t warps = (d.M + mpw - 1) / mpw;
     const int wpb = LWFB_LANES_BLOCK / 32;
     const unsigned lgrid = (unsigned)((warps + wpb - 1) / wpb);
-    size_t smem = (size_t)KC_COUNT * LWFB_LANES_BLOCK * sizeof(double);
+    size_t smem = ((size_t)KC_COUNT * LWFB_LANES_BLOCK + 3 * LWFB_LOG_TAB_N) * sizeof(double);   // constant columns + log table
     if (const char* pad = getenv("LWFB_LANES_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // profiling knob: fewer resident blocks
     if (smem > 48 * 1024) {
       cudaFuncSetAttribute(integrate_lanes<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

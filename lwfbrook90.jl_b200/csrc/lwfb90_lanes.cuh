@@ -31,20 +31,29 @@
 
 namespace lwfb {
 
+// Tsit5 tableau for the rolled stage loop.  The rows are indexed with the (warp-uniform) stage number at run time:
+// constant memory on the device (a __device__ constexpr array would be read from global memory).
 // CQ[ks][p] = a(ks+1+p, ks): contribution of k_ks to the input of stage ks+1+p (stage 7 = the new state)
-__device__ constexpr double lCQ[7][5] = {
-    {0, 0, 0, 0, 0},
-    {-0.008480655492356989, 2.8971530571054935, 5.325864828439257, 5.86145544294642, 0.09646076681806523},   // k1 -> stages 3..7
-    {0.335480655492357, -6.359448489975075, -11.748883564062828, -12.92096931784711, 0.01},                  // k2 -> stages 3..7
-    {4.3622954328695815, 7.4955393428898365, 8.159367898576159, 0.4798896504144996, 0},                       // k3 -> stages 4..7
-    {-0.09249506636175525, -0.071584973281401, 1.379008574103742, 0, 0},                                      // k4 -> stages 5..7
-    {-0.028269050394068383, -3.290069515436081, 0, 0, 0},                                                     // k5 -> stages 6..7
-    {2.324710524099774, 0, 0, 0, 0}};                                                                         // k6 -> stage 7
-__device__ constexpr double lB7[8] = {0, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742,
-                                      -3.290069515436081, 2.324710524099774, 0};                              // a(7, ks)
-__device__ constexpr double lBT[8] = {0, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
-                                      -0.1447110071732629, 0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
-__device__ constexpr double lC[7] = {0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};   // time of the stage evaluated at s
+#define LWFB_TAB_CQ { {0, 0, 0, 0, 0}, \
+    {-0.008480655492356989, 2.8971530571054935, 5.325864828439257, 5.86145544294642, 0.09646076681806523}, \
+    {0.335480655492357, -6.359448489975075, -11.748883564062828, -12.92096931784711, 0.01}, \
+    {4.3622954328695815, 7.4955393428898365, 8.159367898576159, 0.4798896504144996, 0}, \
+    {-0.09249506636175525, -0.071584973281401, 1.379008574103742, 0, 0}, \
+    {-0.028269050394068383, -3.290069515436081, 0, 0, 0}, \
+    {2.324710524099774, 0, 0, 0, 0} }
+#define LWFB_TAB_B7 {0, 0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774, 0}
+#define LWFB_TAB_BT {0, -0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629, \
+                     0.5823571654525552, -0.45808210592918697, 0.015151515151515152}
+#define LWFB_TAB_C {0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0}
+#ifdef __CUDACC__
+#define LWFB_TABQ static __constant__
+#else
+#define LWFB_TABQ static const
+#endif
+LWFB_TABQ double lCQ[7][5] = LWFB_TAB_CQ;
+LWFB_TABQ double lB7[8] = LWFB_TAB_B7;        // a(7, ks)
+LWFB_TABQ double lBT[8] = LWFB_TAB_BT;
+LWFB_TABQ double lC[7] = LWFB_TAB_C;          // time of the stage evaluated at s
 __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LWFB_A_SLFL,
                                        LWFB_A_BYFL, LWFB_A_DSFL, LWFB_A_GWFL, LWFB_A_VRFLN};
 
@@ -94,7 +103,8 @@ enum {
 #define LC(k) (*(const volatile double*)(cst + (k) * LWFB_LANES_BLOCK))
 
 template <int NMAX, int EQ>
-__device__ __forceinline__ void lanes_body(const DevData& d, const int lane, const int64_t warp_g, double* cst) {
+__device__ __forceinline__ void lanes_body(const DevData& d, const int lane, const int64_t warp_g, double* cst,
+                                           const double* ltab /* log table (shared-memory copy on the device) */) {
   const int N = d.N;
   const int mpw = 32 / N;                            // members per warp
   const int64_t M = d.M;
@@ -405,14 +415,14 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       const double a = jmaxc(w, 1.e-6);
       // a in [1e-6, 1]: log on its main path.  The exponents -1/m, n/(n-1), 1/n, 1-1/n are non-zero for every valid
       // van Genuchten n (finite, > 1), so x^y = exp(y log x) needs no y == 0 case; only the tortuosity l may be 0.
-      const double la = lwfb_log_main(a);
+      const double la = lwfb_log_main_t(a, ltab);
       const double TORT = LC(KC_TORT);
       double p1, p3, pT;                                      // a^(-1/m), a^(n/(n-1)), a^l: three chains interleaved
       lwfb_exp3(LC(KC_E1) * la, LC(KC_E3) * la, TORT * la, &p1, &p3, &pT);
       pT = (TORT == 0.0) ? 1.0 : pT;                          // x^0 = 1 also where exp(0 * log x) would not say so
       const double x1 = p1 - 1.0, x3 = 1.0 - p3;             // both are 0 at saturation (log -> -inf, power -> 0)
       double l1, l3;
-      lwfb_log_main2(x1, x3, &l1, &l3);                       // two interleaved chains, then the rare fix-ups
+      lwfb_log_main2_t(x1, x3, &l1, &l3, ltab);               // two interleaved chains, then the rare fix-ups
       if (lwfb_log_isspecial(x1)) l1 = lwfb_log_cold(x1);
       if (lwfb_log_isspecial(x3)) l3 = lwfb_log_cold(x3);
       double e1, e3;
@@ -422,7 +432,8 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       const double inner = 1.0 - e3;
       const double KSAT = LC(KC_KSAT);
       const double kkv = KSAT * pT * (inner * inner);
-      const double lk = lwfb_log(kkv);
+      double lk = lwfb_log_main_t(kkv, ltab);
+      if (lwfb_log_isspecial(kkv)) lk = lwfb_log_cold(kkv);
       const double psit = psim + LC(KC_PSIG);
       double BYFRAC = 0;
       if (any_bypar) {
@@ -815,10 +826,13 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 template <int NMAX, int EQ>
 __global__ void __launch_bounds__(LWFB_LANES_BLOCK, LWFB_LANES_MINBLOCKS) integrate_lanes(DevData d) {
   extern __shared__ double lanes_smem[];
+  double* ltab = lanes_smem + (size_t)KC_COUNT * LWFB_LANES_BLOCK;     // shared-memory copy of the log table
+  for (int k = threadIdx.x; k < 3 * LWFB_LOG_TAB_N; k += LWFB_LANES_BLOCK) ltab[k] = lwfb_log_tab_d[k];
+  __syncthreads();
   unsigned tid = threadIdx.x;
   asm volatile("" : "+r"(tid));     // opaque copy of %tid: the column address stays in a register (it would be re-derived
                                     // from %tid at every use otherwise) and is still known to point to shared memory
-  lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + tid);
+  lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + tid, ltab);
 }
 #endif
 

@@ -137,10 +137,10 @@ void lanes_entry(void* a, int lane) {
   const WarpArg* wa = (const WarpArg*)a;
   const lwfb::DevData& d = *wa->d;
   double* cst = wa->cst + lane;                  // this lane's column of the "shared memory" constant block
-  if (d.N == 3) lwfb::lanes_body<8, 3>(d, lane, wa->warp_g, cst);
-  else if (d.N < 8) lwfb::lanes_body<8, 2>(d, lane, wa->warp_g, cst);
-  else if (d.N == 8) lwfb::lanes_body<8, 1>(d, lane, wa->warp_g, cst);
-  else lwfb::lanes_body<32, 1>(d, lane, wa->warp_g, cst);
+  if (d.N == 3) lwfb::lanes_body<8, 3>(d, lane, wa->warp_g, cst, lwfb_log_tab_h);
+  else if (d.N < 8) lwfb::lanes_body<8, 2>(d, lane, wa->warp_g, cst, lwfb_log_tab_h);
+  else if (d.N == 8) lwfb::lanes_body<8, 1>(d, lane, wa->warp_g, cst, lwfb_log_tab_h);
+  else lwfb::lanes_body<32, 1>(d, lane, wa->warp_g, cst, lwfb_log_tab_h);
 }
 
 void* worker(void* p) {
