@@ -15,9 +15,8 @@ _OBJ = os.path.join(_HERE, "_obj")
 # host replay (oracle mode B); the elementary functions use explicit fma().
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC"]
-# translation units: (source, extra flags).  lwfb90_member.cu (fallback kernels, not on the measured path) is
-# compiled with NVVM -O1, see the note at the top of that file.
-UNITS = [("lwfb90.cu", []), ("lwfb90_member.cu", ["-Xcicc", "-O1"])]
+# translation units: (source, extra flags); two units so that they compile in parallel
+UNITS = [("lwfb90.cu", []), ("lwfb90_member.cu", [])]
 
 
 def _deps():

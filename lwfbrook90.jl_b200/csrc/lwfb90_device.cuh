@@ -774,7 +774,7 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
   }
   // ---- MSBDAYNIGHT
   double PTR[2], GER[2], PIR[2], GIR[2], PGER[2];
-  double ATRI0[NMAX], ATRI1[NMAX];
+  double ATRI2[2][NMAX];      // day / night uptake by layer
   double C1 = pv.S(LWFB_S_C1), C2 = pv.S(LWFB_S_C2), C3 = pv.S(LWFB_S_C3), CR = pv.S(LWFB_S_CR);
   double GLMIN = pv.S(LWFB_S_GLMIN), PSICR = pv.S(LWFB_S_PSICR);
   bool NOOUTF = pv.S(LWFB_S_NOOUTF) != 0.0;
@@ -796,7 +796,7 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
     swpe(AA, ASUBS, VPD, RAA, RAC, RAS, RSC, RSS, DELTA, PTR[J - 1], GER[J - 1]);
     swpe(AA, ASUBS, VPD, RAA, RAC, RAS, 0, RSS, DELTA, PIR[J - 1], GIR[J - 1]);
     swpe(AA, ASUBS, VPD, RAA, RAC, RAS, RSC, 0, DELTA, dmy, PGER[J - 1]);
-    double* ATRI = (J == 1) ? ATRI0 : ATRI1;
+    double* ATRI = ATRI2[J - 1];
     if (PTR[J - 1] > 0.001) {
       double ATR = tbylayer<NMAX>(N, J, PTR[J - 1], DISPC, ALPHA, kk, RROOTI, RXYLEM, psiti, PSICR, NOOUTF, ATRI);
       if (ATR < PTR[J - 1]) GER[J - 1] = swge(AA, ASUBS, VPD, RAA, RAS, RSS, DELTA, ATR);
@@ -810,7 +810,7 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
   double GEVP = (GER[0] * DAYLEN + GER[1] * (1 - DAYLEN));
   double PINT = (PIR[0] * DAYLEN + PIR[1] * (1 - DAYLEN));
   double GIVP = (GIR[0] * DAYLEN + GIR[1] * (1 - DAYLEN));
-  for (int i = 0; i < N; i++) TRANI[i] = (ATRI0[i] * DAYLEN + ATRI1[i] * (1 - DAYLEN));
+  for (int i = 0; i < N; i++) TRANI[i] = (ATRI2[0][i] * DAYLEN + ATRI2[1][i] * (1 - DAYLEN));
   // ---- MSBPREINT
   const double DTP = 1.0;
   double SFAL = SNOFRC * PREC, RFAL = PREC - SFAL;

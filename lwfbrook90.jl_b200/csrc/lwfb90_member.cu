@@ -1,11 +1,12 @@
 // lwfb90_member.cu — thread-per-member kernels: the fallback integrator for layer counts outside the
 // lane-per-layer kernel's range (N < 3 or N > 32) and the single-RHS kernel of the unit parity tests.
 //
-// Own translation unit because it is compiled with `-Xcicc -O1`: with the default NVVM optimisation level
-// (nvcc 12.9, sm_100a) this code gives results that differ from the CPU oracle in the 4th digit after one
-// day, while -O0, -O1, -G and a host build of the same text (tests/simt) all agree with the oracle bit for
-// bit; the cause inside NVVM's -O2/-O3 pipeline was not isolated (profiles/r01_notes.md).  These kernels
-// are not on the measured path.
+// Own translation unit so that it compiles in parallel with lwfb90.cu.  (History: an earlier version of the daily
+// callback selected between the addresses of two thread-local arrays inside a non-unrolled loop,
+// `double* ATRI = (J == 1) ? ATRI0 : ATRI1;`; with NVVM -O2/-O3 (nvcc 12.9, sm_100a) this kernel then produced results
+// that differed from the CPU oracle in the 4th digit, while -O0, -O1, -G and a host build of the same text agreed
+// with it bit for bit.  One two-dimensional array instead of the pointer select removed the problem,
+// profiles/r01_notes.md.)  These kernels are not on the measured path.
 #include "lwfb90_launch.h"
 #include "lwfb90_member.cuh"
 
