@@ -214,11 +214,15 @@ def main():
         t = torch.as_tensor(DeviceArray(ptr, (M, lo.NSCORES)), device=f"cuda:{local_rank}")
         return allgather_scores(t, M * world, rank, world)
 
+    launches = []                                             # kernels launched per step (integrator launches + score)
+
     def step_resident():
         h.run()
         ptr = h.scores_device(obs_day, obs_layer, obs_th, obs_d18)
         gather(ptr)
-        return h.last_run_stats()[1]
+        n, ms = h.last_run_stats()
+        launches.append(n + 1)
+        return ms
 
     def step_e2e():
         h.set_members(site_h, scal_h, lay_h, u0_h)            # H2D from pinned host memory
@@ -236,7 +240,9 @@ def main():
     sampler.start()
     barrier()
     t0 = time.perf_counter()
+    launches.clear()
     kernel_ms = [step_resident() for _ in range(args.steps)]
+    n_launched = int(sum(launches))
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -291,18 +297,21 @@ def main():
             "config": {"workload": f"DAV2020-full isotope ensemble: {M} members per GPU x {world} GPU(s) "
                                    f"(= {8 * M:,} at 8 GPUs), N=5 layers, {nd} days, state length {L}, Philox seed 1234; "
                                    "per step: integrate + score kernel + score all-gather; adaptive placement "
-                                   "(members cost-sorted from the previous run of the handle, lwfb_set_placement)",
+                                   "(work quanta of 1024 block passes, members regrouped by progress between the "
+                                   "launches, lwfb_set_placement)",
                        "members_per_gpu": M, "n_days": nd, "n_layers": N,
                        "l2": "member blocks (%.0f MB) and daily record (%.1f GB) per launch exceed the 126 MB L2"
                              % (h2d / 1e6, M * (nd + 1) * L * 8 / 1e9),
                        "members_ok": n_ok, "mean_accepted_steps_per_day": float(cnt[:, 0].mean() / nd),
                        "rejected_fraction": float(cnt[:, 1].sum() / max(1, cnt[:, 0].sum() + cnt[:, 1].sum()))},
             "e2e": {"value": e2e_val, "unit": "site-days/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": int(2 * args.steps),
+            "gpu_launches": n_launched,
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": ach_tf / fp64_peak if fp64_peak else None, "traffic": None,
-                         "note": "integrate_kernel; achieved = counted FLOP-equivalents (SURVEY 8d) / CUDA-event time; "
+                         "note": "integrate_lanes; achieved = counted FLOP-equivalents of a step (SURVEY 8d) / CUDA-event "
+                                 "time from the first to the last integrator launch of the step (includes the host "
+                                 "regrouping between the launches); "
                                  "peak = DFMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                          "kernel_ms": kms},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

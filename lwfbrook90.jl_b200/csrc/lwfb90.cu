@@ -282,7 +282,7 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
     CK(cudaMalloc(&h->d_counters, (size_t)M * LWFB_NCOUNTERS * sizeof(long long)));
     CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
     CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
-    CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + N) * sizeof(double)));
+    CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + LWFB_CKL * N) * sizeof(double)));
     if (h->o.record_daily) {
       size_t bytes = (size_t)M * (h->o.n_days + 1) * L * sizeof(double);
       cudaError_t e = cudaMalloc(&h->d_rec, bytes);
@@ -308,7 +308,7 @@ static DevData make_dev(lwfb_handle* h) {
   d.rec = h->d_rec; d.fin = h->d_fin; d.status = h->d_status; d.counters = h->d_counters;
   d.reltol = h->o.reltol; d.abstol = h->o.abstol; d.dt_init = h->o.dt_init; d.dtmax = h->o.dtmax;
   d.maxiters = h->o.maxiters;
-  d.seg_day0 = h->o.t0_day; d.seg_day1 = h->o.t0_day + h->o.n_days; d.resume = 0; d.ck = h->d_ck;
+  d.iter_budget = 0; d.prio_blocks = 0; d.prio_budget = 0; d.n_slots = 0; d.resume = 0; d.ck = nullptr;
   return d;
 }
 
@@ -338,12 +338,12 @@ static int sort_members_by_cost(lwfb_handle* h) {
   return LWFB_OK;
 }
 
-// one launch of the integrator over the days (d.seg_day0, d.seg_day1]
+// one launch of the integrator over the slots [0, d.n_slots)
 static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) {
   if (use_lanes(h)) {
     // production path: one lane per soil layer, 32/N members per warp; per-thread constants in shared memory
     const int mpw = 32 / d.N;
-    const int64_t warps = (d.M + mpw - 1) / mpw;
+    const int64_t warps = ((d.n_slots > 0 ? d.n_slots : d.M) + mpw - 1) / mpw;
     const int wpb = LWFB_LANES_BLOCK / 32;
     const unsigned lgrid = (unsigned)((warps + wpb - 1) / wpb);
     size_t smem = ((size_t)KC_COUNT * LWFB_LANES_BLOCK + 3 * LWFB_LOG_TAB_N) * sizeof(double);   // constant columns + log table
@@ -398,44 +398,106 @@ extern "C" int lwfb_sync(lwfb_handle* h) {
   return LWFB_OK;
 }
 
-// Synchronous run.  A handle that has no cost information yet (first run, new member count) and enough members for
-// sorting to pay integrates the record in SEGMENTS of 4, 8, 16, ... up to LWFB_SEG_DAYS days (default 32): after each segment the members
-// are re-sorted by the RHS evaluations they needed so far, and the next launch resumes every member at the day boundary
-// from its state vector in HBM plus a small checkpoint (controller state, counters, du_NTFLI).  Results are identical
-// to a single launch.
+// placement := the unfinished members sorted by progress (simulation time reached, least first); returns their number.
+// Members of a block then are at the same day (they share the daily callback phases and step at a similar pace), the
+// finished ones drop out of the launch, and the front blocks hold the members that decide when the run ends.  (Sorting
+// by an estimate of the remaining steps instead was measured slower: it mixes days within a block.)
+static int regroup_by_progress(lwfb_handle* h, int64_t* n_left) {
+  const int64_t M = h->M;
+  std::vector<double> t((size_t)M);
+  std::vector<int32_t> st((size_t)M);
+  CK(cudaMemcpy(t.data(), h->d_ck + (size_t)LWFB_CK_T * M, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(st.data(), h->d_status, st.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  const double tend = (double)(h->o.t0_day + h->o.n_days), t0 = (double)h->o.t0_day;
+  std::vector<uint64_t> key;
+  key.reserve((size_t)M);
+  for (int64_t i = 0; i < M; i++) {
+    const double ti = t[(size_t)i];
+    if (st[(size_t)i] != LWFB_ST_OK || !(ti < tend)) continue;
+    const float f = (float)(ti - t0);                   // >= 0: the bit pattern orders like the value
+    uint32_t fb;
+    memcpy(&fb, &f, 4);
+    key.push_back(((uint64_t)fb << 32) | (uint32_t)i);
+  }
+  std::sort(key.begin(), key.end());
+  std::vector<int32_t> perm(key.size() ? key.size() : 1);
+  for (size_t k = 0; k < key.size(); k++) perm[k] = (int32_t)(key[k] & 0xffffffffu);
+  *n_left = (int64_t)key.size();
+  if (!key.empty()) CK(cudaMemcpy(h->d_perm, perm.data(), key.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  return LWFB_OK;
+}
+
+// Synchronous run.  With adaptive placement and enough members for regrouping to pay, the record is integrated in WORK
+// QUANTA: a block ends after LWFB_QUANTUM passes of its loop (default 1024; 0 = one launch to the end), every member
+// checkpoints where it is (fin + ck), the host regroups the unfinished members by progress and launches
+// again.  The front blocks of a launch (least progress) keep their slots for the whole launch while the other slots
+// turn over once per quantum, so the members that decide the end of the run never wait for a slot.  Nothing has to be
+// known about the members in advance; results are identical to a single launch.
 extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   if (!h || h->M < 1) return LWFB_ERR_ARG;
   CK(cudaSetDevice(h->o.device));
-  int seg = 32;
-  if (const char* e = getenv("LWFB_SEG_DAYS")) seg = atoi(e);
-  const bool segmented = use_lanes(h) && h->placement >= 1 && !h->cost_valid && seg > 0 && h->o.n_days > seg && many_waves(h);
-  if (!segmented) {
+  long long quantum = 1024;
+  if (const char* e = getenv("LWFB_QUANTUM")) quantum = atoll(e);
+  int prio_pct = 25;                                  // share of the resident slots given to the front blocks
+  if (const char* e = getenv("LWFB_PRIO_PCT")) prio_pct = atoi(e);
+  const bool quanta = use_lanes(h) && h->placement >= 1 && quantum > 0 && many_waves(h);
+  if (!quanta) {
     int rc = lwfb_run_async(h, cuda_stream);
     if (rc) return rc;
     return lwfb_sync(h);
   }
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  h->perm_valid = false;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->o.device);
+  const int64_t R = (int64_t)n_sm * LWFB_LANES_MINBLOCKS;                       // resident blocks
+  const int64_t mpb = (int64_t)(LWFB_LANES_BLOCK / 32) * (32 / h->o.n_layers);   // members per block
+  // first launch: sorted by the cost of the previous run of the handle if there was one, else as given
+  if (h->cost_valid) {
+    int rc = sort_members_by_cost(h);
+    if (rc) return rc;
+  } else h->perm_valid = false;
   h->n_launches = 0;
   CK(cudaEventRecord(h->ev0, st));
-  // segment lengths grow 4, 8, 16, ... up to `seg` days: the first re-sorts come early, when nothing is known yet
-  int len = seg < 4 ? seg : 4;
-  for (int d0 = 0; d0 < h->o.n_days;) {
-    const int d1 = d0 + len < h->o.n_days ? d0 + len : h->o.n_days;
+  int64_t n_left = h->M;
+  const bool cold = !h->cost_valid;
+  for (int launch = 0; n_left > 0; launch++) {
+    // a cold handle knows nothing about its members: the first quanta are short (128, 256, ... passes, no front blocks)
+    // so that the first regroupings come early
+    long long q = quantum;
+    if (cold && launch < 16 && (128LL << launch) < quantum) q = 128LL << launch;
+    const bool ramp = q < quantum;
     DevData d = make_dev(h);
-    d.seg_day0 = h->o.t0_day + d0;
-    d.seg_day1 = h->o.t0_day + d1;
-    d.resume = d0 > 0;
+    d.ck = h->d_ck;
+    d.resume = launch > 0;
+    d.n_slots = n_left;
+    const int64_t nb = (n_left + mpb - 1) / mpb;
+    if (nb <= R) {
+      // every block has a slot: longer quanta the emptier the device (regrouping only thins the blocks out)
+      int64_t f = R / nb;
+      d.iter_budget = q * (f > 16 ? 16 : f);
+    } else if (ramp) {
+      d.iter_budget = q;
+    } else {
+      // K front blocks keep their slots, the other R - K slots take W blocks each, one quantum per block; K is raised
+      // until the last of the W rounds is full
+      int64_t K = R * prio_pct / 100;
+      if (K > R - 1) K = R - 1;
+      if (K < 0) K = 0;
+      const int64_t W = (nb - K + (R - K) - 1) / (R - K);
+      if (K > 0 && W > 1) K += (W * (R - K) - (nb - K)) / (W - 1);
+      if (K > R - 1) K = R - 1;
+      d.iter_budget = quantum;
+      d.prio_blocks = K;
+      d.prio_budget = quantum * ((nb - K + (R - K) - 1) / (R - K));
+    }
     int rc = launch_integrator(h, d, st);
     if (rc) return rc;
-    if (d1 < h->o.n_days) {
-      CK(cudaStreamSynchronize(st));
-      if ((rc = sort_members_by_cost(h))) return rc;
-    }
-    d0 = d1;
-    len = 2 * len < seg ? 2 * len : seg;
+    CK(cudaStreamSynchronize(st));
+    if ((rc = regroup_by_progress(h, &n_left))) return rc;
+    h->perm_valid = true;
   }
   CK(cudaEventRecord(h->ev1, st));
+  h->perm_valid = false;       // d_perm now holds a partial order of the last launch
   h->ran = true;
   h->cost_valid = true;
   return lwfb_sync(h);

@@ -63,13 +63,21 @@ struct DevData {
   long long* __restrict__ counters;  // [LWFB_NCOUNTERS][M]
   double reltol, abstol, dt_init, dtmax;
   long long maxiters;
-  // segmented execution of the lane kernel (one launch per segment of days, state carried in fin + ck):
-  int seg_day0, seg_day1;            // this launch integrates (seg_day0, seg_day1]; seg_day0 == t0_day && !resume: fresh start
-  int resume;                        // 1: continue at the day boundary seg_day0 from fin / ck
-  double* __restrict__ ck;           // [LWFB_CK + N][M] member-level controller state + per-layer du_NTFLI (null: single launch)
+  // work-quantum execution of the lane kernel (lwfb_run): a launch ends after `iter_budget` passes of the block loop,
+  // every member checkpoints where it is (fin + ck, also in the middle of a day), the host regroups the unfinished
+  // members by progress and launches again with resume = 1.  Results do not depend on budget or grouping.
+  long long iter_budget;             // passes of the block loop per launch (0: run to the end)
+  long long prio_blocks, prio_budget;// the first prio_blocks blocks (the members with the most work left) get prio_budget
+                                     // passes: they run for the whole launch while the other slots turn over
+  long long n_slots;                 // slots in use: perm[0 .. n_slots) are the members of this launch (0: all M)
+  int resume;                        // 1: continue from fin / ck
+  double* __restrict__ ck;           // [LWFB_CK + LWFB_CKL * N][M] checkpoint block (null: single launch, nothing saved)
 };
-// rows of the checkpoint block
-enum { LWFB_CK_DT = 0, LWFB_CK_QOLD, LWFB_CK_ITER, LWFB_CK_NACCEPT, LWFB_CK_NREJECT, LWFB_CK_NF, LWFB_CK_REC, LWFB_CK_PAD, LWFB_CK };
+// rows of the checkpoint block: member level, then LWFB_CKL rows per layer
+enum { LWFB_CK_DT = 0, LWFB_CK_QOLD, LWFB_CK_ITER, LWFB_CK_NACCEPT, LWFB_CK_NREJECT, LWFB_CK_NF, LWFB_CK_REC, LWFB_CK_T,
+       LWFB_CK_TSTOP, LWFB_CK_FLAGS, LWFB_CK_RS, LWFB_CK_SLVP, LWFB_CK_SUMT, LWFB_CK_SUMT_V, LWFB_CK_D0_18O, LWFB_CK_D0_2H,
+       LWFB_CK_KFG, LWFB_CK };
+enum { LWFB_CKL_NTFLI = 0, LWFB_CKL_TRANI, LWFB_CKL_KFY, LWFB_CKL_NAN, LWFB_CKL_KFQ /* 3 rows */, LWFB_CKL = LWFB_CKL_KFQ + 3 };
 
 // state-vector offsets, src/func_DiffEq_definition_u0.jl:42-73
 struct SIdx {

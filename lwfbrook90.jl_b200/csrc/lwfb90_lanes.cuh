@@ -101,6 +101,11 @@ enum {
   KC_COUNT
 };
 #define LC(k) (*(const volatile double*)(cst + (k) * LWFB_LANES_BLOCK))
+#ifdef LWFB_SIMT_EMUL
+#define LWFB_BLOCK_OF_WARP(w) (w)                    // the emulator runs every warp as its own block
+#else
+#define LWFB_BLOCK_OF_WARP(w) ((w) / (LWFB_LANES_BLOCK / 32))
+#endif
 
 template <int NMAX, int EQ>
 __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, const int64_t warp_g, double* cst,
@@ -114,8 +119,9 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   if (!lane_valid) { g = 0; i = 0; }                 // surplus lanes shadow lane 0 and never commit
   const int base = g * N;
   const int64_t m_raw = warp_g * mpw + g;            // slot of the group
-  const bool live = lane_valid && m_raw < M;
-  const int64_t slot = (m_raw < M) ? m_raw : M - 1;
+  const int64_t n_slots = d.n_slots > 0 ? d.n_slots : M;
+  const bool live = lane_valid && m_raw < n_slots;
+  const int64_t slot = (m_raw < n_slots) ? m_raw : n_slots - 1;
   const int64_t m = d.perm ? (int64_t)__ldg(d.perm + slot) : slot;   // member placed in this slot
   const bool top = (i == 0), bot = (i == N - 1);
   const bool nodn = bot || !lane_valid, noup = top || !lane_valid;   // lanes without a real neighbour below / above
@@ -172,8 +178,9 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   const bool gw_feedback = __any_sync(LFULL, !(pv.S(LWFB_S_GSC) < 1.0e-8));   // GWAT enters the RHS only through GSC >= 1e-8
 
   // ---- live state: fin := u0 (then kept current at day boundaries); registers for what evolves per step
-  const bool resume = d.resume != 0;                 // continue at the day boundary d.seg_day0 (segmented execution)
+  const bool resume = d.resume != 0;                 // continue from the checkpoint of the previous launch
   auto CKP = [&](int r) -> double& { return d.ck[(int64_t)r * M + m]; };
+  auto CKL = [&](int r) -> double& { return d.ck[(int64_t)(LWFB_CK + r * N + i) * M + m]; };   // per-layer rows
   if (live && !resume) for (int j = i; j < L; j += N) FIN(j) = U0(j);
   __syncwarp(LFULL);
   double y = FIN(ix.SWATI + i), G = FIN(ix.GWAT);
@@ -183,18 +190,22 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   for (int j = 0; j < EQ; j++) {
     qe[j] = i + j * N;
     Q[j] = qe[j] < 8 ? FIN(ix.ACC + lAccPos[qe[j] & 7]) : 0.0;
-    kFQ[j] = 0;
+    kFQ[j] = resume ? CKL(LWFB_CKL_KFQ + j) : 0.0;
   }
-  double kFy = 0, kFG = 0;                           // FSAL derivative of SWATI / GWAT
+  double kFy = resume ? CKL(LWFB_CKL_KFY) : 0.0, kFG = resume ? CKP(LWFB_CK_KFG) : 0.0;   // FSAL derivative of SWATI / GWAT
   auto SETK = [&](int k, double v) { cst[k * LWFB_LANES_BLOCK] = v; };
   for (int s = 0; s < 2; s++) {
     SETK(KC_DS_18O + s, iso ? FIN(ix.SWATI + (s + 1) * N + i) : 0.0);
     SETK(KC_DG_18O + s, iso ? FIN(ix.GWAT + 1 + s) : 0.0);
     SETK(KC_DXY_18O + s, iso ? FIN(ix.XYLEM + 1 + s) : 0.0);
   }
-  double TRANI = NAN;                                // frozen uptake of the layer
-  double ntfli = resume ? CKP(LWFB_CK + i) : NAN;    // du_NTFLI of the previous RHS call (NaN on a fresh problem)
-  double RS = NAN, SLVP = NAN;                        // RNET + SMLT and SLVP of the day
+  double TRANI = resume ? CKL(LWFB_CKL_TRANI) : NAN; // frozen uptake of the layer
+  double ntfli = resume ? CKL(LWFB_CKL_NTFLI) : NAN; // du_NTFLI of the previous RHS call (NaN on a fresh problem)
+  double RS = resume ? CKP(LWFB_CK_RS) : NAN, SLVP = resume ? CKP(LWFB_CK_SLVP) : NAN;   // RNET + SMLT and SLVP of the day
+  if (resume) {                                      // day constants of the callback
+    SETK(KC_SUMT, CKP(LWFB_CK_SUMT)); SETK(KC_SUMT_V, CKP(LWFB_CK_SUMT_V));
+    SETK(KC_D0_18O, CKP(LWFB_CK_D0_18O)); SETK(KC_D0_2H, CKP(LWFB_CK_D0_2H));
+  }
   double VV = 0, INFLI = 0, DSFLI = 0;               // flux caches of the last RHS (isotope step)
 
   // value of accumulator e (held by lane e % N in slot e / N), broadcast to the group
@@ -226,8 +237,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 
   const double qmin = 0.2, qmax = 10.0, gamma = 0.9, beta1 = 0.14, beta2 = 0.08, qoldinit = 1e-4;
   const double t0 = (double)d.t0_day, tend = (double)(d.t0_day + d.n_days);
-  const double tend_seg = (double)d.seg_day1;        // this launch stops at this day boundary (== tend without segments)
-  double t = resume ? (double)d.seg_day0 : t0, tstop = t;
+  double t = resume ? CKP(LWFB_CK_T) : t0, tstop = resume ? CKP(LWFB_CK_TSTOP) : t0;
   double dt = resume ? CKP(LWFB_CK_DT) : d.dt_init, qold = resume ? CKP(LWFB_CK_QOLD) : qoldinit;
   const double dtmin_opt = fmax(eps_of(tend), eps_of(t0));
   const unsigned maxiters = d.maxiters > 0x7fffffffLL ? 0x7fffffffu : (unsigned)d.maxiters;
@@ -239,8 +249,13 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   if (resume) {
     iter = (unsigned)CKP(LWFB_CK_ITER); naccept = (unsigned)CKP(LWFB_CK_NACCEPT); nreject = (unsigned)CKP(LWFB_CK_NREJECT);
     nf = (unsigned)CKP(LWFB_CK_NF); rec = (int)CKP(LWFB_CK_REC); status = d.status[m];
+    const int fl = (int)CKP(LWFB_CK_FLAGS);
+    reeval = (fl & 1) != 0; at_boundary = (fl & 2) != 0;
+    cand_nan = CKL(LWFB_CKL_NAN) != 0.0;
   }
   const int status_in = status;
+  // block-uniform: every thread of a block makes the same passes
+  long long passes_left = d.iter_budget > 0 ? (LWFB_BLOCK_OF_WARP(warp_g) < d.prio_blocks ? d.prio_budget : d.iter_budget) : -1;
 #ifdef LWFB_DEBUG_ITERS
   unsigned dbg_iters = 0;          // step-phase iterations of the block (profiling: lock-step waiting overhead)
   unsigned dbg_day_iter0 = 0;
@@ -250,7 +265,9 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   __syncwarp(LFULL);
 
   for (;;) {
-    const bool active = (status == LWFB_ST_OK) && (t < tend_seg);
+    const bool active = (status == LWFB_ST_OK) && (t < tend);
+    if (passes_left == 0) break;                     // quantum used up: checkpoint, the host regroups and relaunches
+    if (passes_left > 0) passes_left--;
     if (!LWFB_VOTE_ANY(active && live)) break;
     const bool can_step = active && !at_boundary;
     const bool at_cb = active && at_boundary;        // waits for (or is about to get) its daily callback
@@ -793,12 +810,19 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
   }
   if (live) {
     if (d.ck) {
-      // checkpoint for the next segment: controller state and counters of the member, du_NTFLI of the layer
-      CKP(LWFB_CK + i) = ntfli;
+      // checkpoint for the next launch: everything the loop keeps in registers / shared memory and flush_state does
+      // not put into fin (controller, counters, clock, FSAL derivatives, day constants)
+      CKL(LWFB_CKL_NTFLI) = ntfli; CKL(LWFB_CKL_TRANI) = TRANI; CKL(LWFB_CKL_KFY) = kFy; CKL(LWFB_CKL_NAN) = cand_nan ? 1.0 : 0.0;
+#pragma unroll
+      for (int j = 0; j < EQ; j++) CKL(LWFB_CKL_KFQ + j) = kFQ[j];
       if (top) {
         CKP(LWFB_CK_DT) = dt; CKP(LWFB_CK_QOLD) = qold; CKP(LWFB_CK_ITER) = (double)iter;
         CKP(LWFB_CK_NACCEPT) = (double)naccept; CKP(LWFB_CK_NREJECT) = (double)nreject; CKP(LWFB_CK_NF) = (double)nf;
-        CKP(LWFB_CK_REC) = (double)rec;
+        CKP(LWFB_CK_REC) = (double)rec; CKP(LWFB_CK_T) = t; CKP(LWFB_CK_TSTOP) = tstop;
+        CKP(LWFB_CK_FLAGS) = (double)((reeval ? 1 : 0) | (at_boundary ? 2 : 0));
+        CKP(LWFB_CK_RS) = RS; CKP(LWFB_CK_SLVP) = SLVP; CKP(LWFB_CK_KFG) = kFG;
+        CKP(LWFB_CK_SUMT) = LC(KC_SUMT); CKP(LWFB_CK_SUMT_V) = LC(KC_SUMT_V);
+        CKP(LWFB_CK_D0_18O) = LC(KC_D0_18O); CKP(LWFB_CK_D0_2H) = LC(KC_D0_2H);
       }
     }
     if (d.rec && status != LWFB_ST_OK && status_in == LWFB_ST_OK) {

@@ -54,7 +54,8 @@ def _p(a, t=_dp):
 def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, *, reltol=1e-5, abstol=1e-6,
         dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000, n_threads=8, perm=None, seg_len=0, resort=False):
     """Same shapes and return values as oracle.run.  perm: optional placement (slot -> member) of the lane kernel;
-    seg_len > 0: segmented execution (one launch per seg_len days), resort: re-sort the members between segments."""
+    seg_len > 0: work-quantum execution (a launch ends after seg_len passes of the warp loop), resort: regroup the
+    unfinished members by progress between the launches."""
     forcing = np.ascontiguousarray(forcing, dtype=np.float64)
     if forcing.ndim == 2:
         forcing = forcing[None]

@@ -190,25 +190,37 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   if (kernel == 0) { const int mpw = 32 / N; job.n_units = (M + mpw - 1) / mpw; }
   else job.n_units = M;
   if (n_threads < 1) n_threads = 1;
-  // segmented execution as in lwfb_run: one "launch" per segment, members re-sorted by their RHS count so far
-  std::vector<double> ck((size_t)(lwfb::LWFB_CK + N) * M);
+  // work-quantum execution as in lwfb_run: a launch ends after `seg_len` passes of the block loop (here: of the warp
+  // loop), the unfinished members are regrouped by progress (resort) and the next launch resumes them from fin + ck
+  std::vector<double> ck((size_t)(lwfb::LWFB_CK + lwfb::LWFB_CKL * N) * M);
   std::vector<int32_t> perm2((size_t)M);
-  if (kernel != 0 || seg_len <= 0 || seg_len >= n_days) seg_len = n_days;
-  d.ck = ck.data();
-  for (int d0 = 0; d0 < n_days; d0 += seg_len) {
-    d.seg_day0 = t0_day + d0;
-    d.seg_day1 = t0_day + (d0 + seg_len < n_days ? d0 + seg_len : n_days);
-    d.resume = d0 > 0;
-    if (d0 > 0 && resort) {
-      for (int64_t i = 0; i < M; i++) perm2[(size_t)i] = (int32_t)i;
-      std::stable_sort(perm2.begin(), perm2.end(), [&](int32_t a, int32_t b) {
-        return cnt[(size_t)LWFB_C_NF * M + a] > cnt[(size_t)LWFB_C_NF * M + b]; });
-      d.perm = perm2.data();
-    }
+  const bool quanta = kernel == 0 && seg_len > 0;
+  d.ck = quanta ? ck.data() : nullptr;
+  d.iter_budget = quanta ? seg_len : 0;
+  d.n_slots = 0;
+  d.resume = 0;
+  d.prio_blocks = quanta && resort ? 1 : 0;          // the first warp runs three times as long as the others
+  d.prio_budget = 3 * (long long)seg_len;
+  const double tend = (double)(t0_day + n_days);
+  for (int launch = 0;; launch++) {
+    if (launch > 100000) return 3;
     job.next = 0;
+    if (kernel == 0) { const int mpw = 32 / N; const int64_t ns = d.n_slots > 0 ? d.n_slots : M; job.n_units = (ns + mpw - 1) / mpw; }
     std::vector<pthread_t> th(n_threads);
     for (int i = 0; i < n_threads; i++) pthread_create(&th[i], nullptr, worker, &job);
     for (int i = 0; i < n_threads; i++) pthread_join(th[i], nullptr);
+    if (!quanta) break;
+    int64_t left = 0;
+    for (int64_t i = 0; i < M; i++)
+      if (status[i] == LWFB_ST_OK && ck[(size_t)lwfb::LWFB_CK_T * M + i] < tend) perm2[(size_t)left++] = (int32_t)i;
+    if (left == 0) break;
+    d.resume = 1;
+    if (resort) {
+      std::stable_sort(perm2.begin(), perm2.begin() + left, [&](int32_t a, int32_t b) {
+        return ck[(size_t)lwfb::LWFB_CK_T * M + a] < ck[(size_t)lwfb::LWFB_CK_T * M + b]; });
+      d.perm = perm2.data();
+      d.n_slots = left;
+    }
   }
   // [day][L][M] -> [M][day][L]
   const int64_t K = (int64_t)(n_days + 1) * L;

@@ -206,18 +206,37 @@ def test_adaptive_placement_is_result_neutral(dav_full):
     h.close()
 
 
-def test_segmented_cold_run_is_result_neutral(dav_full, monkeypatch):
-    """A handle without cost information integrates the record in segments (one launch per LWFB_SEG_DAYS days) and
-    re-sorts the members between the launches; every member resumes at the day boundary from its state vector plus a
-    small checkpoint.  Records, status and counters must equal the oracle's single pass."""
-    monkeypatch.setenv("LWFB_SEG_DAYS", "7")
+@pytest.mark.parametrize("quantum", [60, 9, 2])
+def test_work_quanta_with_regrouping_are_result_neutral(dav_full, monkeypatch, quantum):
+    """lwfb_run integrates in work quanta: a launch ends after LWFB_QUANTUM passes of the block loop, every member
+    checkpoints where it is (also mid-day), the unfinished members are regrouped by progress and resumed.  Records,
+    status and counters must equal the oracle's single pass, for a cold handle and for a warm one (first launch
+    cost-sorted)."""
+    monkeypatch.setenv("LWFB_QUANTUM", str(quantum))
     ens = en.make_ensemble(dav_full, 200)
     nd = 60
     h = capi.Handle(ens.N, ens.iso, ens.t0_day, nd)
-    h.set_placement(2)                        # segment + sort regardless of the launch size
+    h.set_placement(2)                        # quanta + regrouping regardless of the launch size
     h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
     h.run()
-    assert h.last_run_stats()[0] == 9         # segments of 4, 7, 7, ... days
+    assert h.last_run_stats()[0] >= 60 * 20 // (16 * quantum)   # few blocks: quanta stretched up to 16 times
+    assert_bit_identical(h, ens, nd)
+    h.run()                                   # warm
+    assert_bit_identical(h, ens, nd)
+    h.close()
+
+
+def test_work_quanta_priority_blocks_many_members(dav_full, monkeypatch):
+    """More blocks than resident slots: the front blocks (least progress) keep their slots for a whole launch while the
+    others turn over once per quantum; members of one ensemble end up with very different numbers of launches."""
+    monkeypatch.setenv("LWFB_QUANTUM", "24")
+    ens = en.make_ensemble(dav_full, 20000)
+    nd = 6
+    h = capi.Handle(ens.N, ens.iso, ens.t0_day, nd)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    h.set_placement(2)
+    h.run()
+    assert h.last_run_stats()[0] >= 3
     assert_bit_identical(h, ens, nd)
     h.close()
 

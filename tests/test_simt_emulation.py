@@ -103,16 +103,17 @@ def test_lane_kernel_placement_does_not_change_results(dav_full):
     assert np.array_equal(got, ref, equal_nan=True)
 
 
-def test_lane_kernel_segmented_execution_with_resorting(dav_full, isobea):
-    """One launch per segment of days, members re-sorted by their RHS count between the launches (what lwfb_run does
-    for a handle without cost information): every member resumes at the day boundary from its state vector plus the
-    checkpoint block.  Must equal the oracle's single pass, also with one-day segments."""
-    for sim, M, nd, seg in ((dav_full, 14, 11, 3), (dav_full, 7, 5, 1), (isobea, 5, 7, 2)):
+def test_lane_kernel_work_quanta_with_regrouping(dav_full, isobea):
+    """A launch ends after a fixed number of passes of the block loop; every member checkpoints where it is (also in
+    the middle of a day or between a rejected step and its retry), the unfinished members are regrouped by progress
+    and resumed (what lwfb_run does).  Must equal the oracle's single pass for any quantum, down to one pass."""
+    for sim, M, nd, quantum, resort in ((dav_full, 14, 11, 37, True), (dav_full, 7, 4, 1, True), (isobea, 5, 7, 16, True),
+                                        (dav_full, 13, 6, 5, False)):
         e = en.make_ensemble(sim, M)
         orc.use("elem")
         ref, st_o, cnt_o = orc.run(e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, n_threads=8)
         got, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
-                                seg_len=seg, resort=True)
+                                seg_len=quantum, resort=resort)
         assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
         assert np.array_equal(got, ref, equal_nan=True)
 
