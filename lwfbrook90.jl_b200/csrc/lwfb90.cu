@@ -148,7 +148,8 @@ struct lwfb_handle {
   // placement of members in the lane kernel's slots (lwfb_set_placement)
   int placement = 1;           // 0 identity, 1 adaptive (cost-sorted from the previous run), 2 the same for any launch size
   int32_t* d_perm = nullptr;
-  double* d_ck = nullptr;      // checkpoint block of the segmented execution [LWFB_CK + N][M]
+  double* d_ck = nullptr;      // checkpoint block of the work-quantum execution [LWFB_CK + LWFB_CKL * N][M]
+  int* d_stop = nullptr;       // {blocks exited, stop flag} of the current launch
   bool perm_valid = false;     // d_perm holds a permutation for the current member count
   bool cost_valid = false;     // d_counters holds the RHS-evaluation counts of a completed lane-kernel run
   std::string err;
@@ -197,8 +198,8 @@ extern "C" int lwfb_create(lwfb_handle** out, const lwfb_opts* opts) {
 
 static void free_members(lwfb_handle* h) {
   cudaFree(h->d_scal); cudaFree(h->d_lay); cudaFree(h->d_u0); cudaFree(h->d_rec); cudaFree(h->d_fin);
-  cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm); cudaFree(h->d_ck);
-  h->d_perm = nullptr; h->d_ck = nullptr; h->perm_valid = false; h->cost_valid = false;
+  cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm); cudaFree(h->d_ck); cudaFree(h->d_stop);
+  h->d_perm = nullptr; h->d_ck = nullptr; h->d_stop = nullptr; h->perm_valid = false; h->cost_valid = false;
   h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
   h->d_site = h->d_status = nullptr; h->d_counters = nullptr;
   h->M = 0; h->ran = false;
@@ -283,6 +284,7 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
     CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
     CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
     CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + LWFB_CKL * N) * sizeof(double)));
+    CK(cudaMalloc(&h->d_stop, 2 * sizeof(int)));
     if (h->o.record_daily) {
       size_t bytes = (size_t)M * (h->o.n_days + 1) * L * sizeof(double);
       cudaError_t e = cudaMalloc(&h->d_rec, bytes);
@@ -309,6 +311,8 @@ static DevData make_dev(lwfb_handle* h) {
   d.reltol = h->o.reltol; d.abstol = h->o.abstol; d.dt_init = h->o.dt_init; d.dtmax = h->o.dtmax;
   d.maxiters = h->o.maxiters;
   d.iter_budget = 0; d.prio_blocks = 0; d.prio_budget = 0; d.n_slots = 0; d.resume = 0; d.ck = nullptr;
+  d.stop = nullptr; d.resident = 0; d.cb_wait = 0;
+  if (const char* e = getenv("LWFB_CB_WAIT")) d.cb_wait = atoi(e);
   return d;
 }
 
@@ -440,6 +444,8 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   if (const char* e = getenv("LWFB_QUANTUM")) quantum = atoll(e);
   int prio_pct = 25;                                  // share of the resident slots given to the front blocks
   if (const char* e = getenv("LWFB_PRIO_PCT")) prio_pct = atoi(e);
+  bool stop_flag = true;                              // end a launch when its first slot runs out of work
+  if (const char* e = getenv("LWFB_STOP_FLAG")) stop_flag = atoi(e) != 0;
   const bool quanta = use_lanes(h) && h->placement >= 1 && quantum > 0 && many_waves(h);
   if (!quanta) {
     int rc = lwfb_run_async(h, cuda_stream);
@@ -478,17 +484,23 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
     } else if (ramp) {
       d.iter_budget = q;
     } else {
-      // K front blocks keep their slots, the other R - K slots take W blocks each, one quantum per block; K is raised
-      // until the last of the W rounds is full
+      // K front blocks keep their slots for the whole launch, the other R - K slots take the other blocks, one quantum
+      // per block
       int64_t K = R * prio_pct / 100;
       if (K > R - 1) K = R - 1;
       if (K < 0) K = 0;
       const int64_t W = (nb - K + (R - K) - 1) / (R - K);
-      if (K > 0 && W > 1) K += (W * (R - K) - (nb - K)) / (W - 1);
+      if (!stop_flag && K > 0 && W > 1) K += (W * (R - K) - (nb - K)) / (W - 1);   // the last of the W rounds is full
       if (K > R - 1) K = R - 1;
       d.iter_budget = quantum;
       d.prio_blocks = K;
-      d.prio_budget = quantum * ((nb - K + (R - K) - 1) / (R - K));
+      d.prio_budget = stop_flag ? (1LL << 60) : quantum * ((nb - K + (R - K) - 1) / (R - K));
+    }
+    if (stop_flag) {
+      // the launch ends when the first slot runs out of work (see DevData::stop)
+      CK(cudaMemsetAsync(h->d_stop, 0, 2 * sizeof(int), st));
+      d.stop = h->d_stop;
+      d.resident = R;
     }
     int rc = launch_integrator(h, d, st);
     if (rc) return rc;

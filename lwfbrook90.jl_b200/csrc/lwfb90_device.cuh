@@ -69,6 +69,12 @@ struct DevData {
   long long iter_budget;             // passes of the block loop per launch (0: run to the end)
   long long prio_blocks, prio_budget;// the first prio_blocks blocks (the members with the most work left) get prio_budget
                                      // passes: they run for the whole launch while the other slots turn over
+  int* stop;                         // [2] device words {blocks that have exited, stop flag} (null: no early end).  The
+                                     // first block that uses up its budget when no block is left to take its slot
+                                     // raises the flag, and every block checkpoints at its next pass: no slot idles
+                                     // at the end of a launch, front blocks need no budget of their own
+  long long resident;                // blocks the device holds at a time (for the "no block left" test)
+  int cb_wait;                       // bounded waiting at the day boundary, in passes (LWFB_CB_WAIT)
   long long n_slots;                 // slots in use: perm[0 .. n_slots) are the members of this launch (0: all M)
   int resume;                        // 1: continue from fin / ck
   double* __restrict__ ck;           // [LWFB_CK + LWFB_CKL * N][M] checkpoint block (null: single launch, nothing saved)

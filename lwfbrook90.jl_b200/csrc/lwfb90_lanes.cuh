@@ -108,7 +108,7 @@ enum {
 #endif
 
 template <int NMAX, int EQ>
-__device__ __forceinline__ void lanes_body(const DevData& d, const int lane, const int64_t warp_g, double* cst,
+__device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, const int64_t warp_g, double* cst,
                                            const double* ltab /* log table (shared-memory copy on the device) */) {
   const int N = d.N;
   const int mpw = 32 / N;                            // members per warp
@@ -254,6 +254,8 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     cand_nan = CKL(LWFB_CKL_NAN) != 0.0;
   }
   const int status_in = status;
+  bool by_budget = false;
+  const int cb_wait = d.cb_wait > 0 ? d.cb_wait : LWFB_CB_WAIT;
   // block-uniform: every thread of a block makes the same passes
   long long passes_left = d.iter_budget > 0 ? (LWFB_BLOCK_OF_WARP(warp_g) < d.prio_blocks ? d.prio_budget : d.iter_budget) : -1;
 #ifdef LWFB_DEBUG_ITERS
@@ -266,14 +268,16 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
 
   for (;;) {
     const bool active = (status == LWFB_ST_OK) && (t < tend);
-    if (passes_left == 0) break;                     // quantum used up: checkpoint, the host regroups and relaunches
+    if (passes_left == 0) { by_budget = true; break; }   // quantum used up: checkpoint, the host regroups and relaunches
     if (passes_left > 0) passes_left--;
-    if (!LWFB_VOTE_ANY(active && live)) break;
+    // (a raised stop flag ends the launch for everybody; threads may see it one pass apart, the vote decides)
+    const bool go_on = d.stop ? (*(volatile const int*)(d.stop + 1) == 0) : true;
+    if (!LWFB_VOTE_ANY(active && live && go_on)) break;
     const bool can_step = active && !at_boundary;
     const bool at_cb = active && at_boundary;        // waits for (or is about to get) its daily callback
     // (two votes: __syncthreads_or returns a truth value, not the OR of the arguments)
     const bool any_step = LWFB_VOTE_ANY(can_step && live);
-    const bool any_overdue = LWFB_VOTE_ANY(at_cb && live && waited >= LWFB_CB_WAIT);
+    const bool any_overdue = LWFB_VOTE_ANY(at_cb && live && waited >= cb_wait);
 
     if (!any_step || any_overdue) {
       if (!__any_sync(LFULL, at_cb)) continue;       // nothing to do in this warp
@@ -678,7 +682,12 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
     // ---- commit
     if (can_step) {
       iter = iter + 1u;
-      if (st_s != LWFB_ST_OK) status = st_s;
+      if (st_s != LWFB_ST_OK) {
+        status = st_s;
+        // the reference re-evaluates f right after a modifying callback, i.e. before the check that stopped the member;
+        // here that evaluation is stage 0 of the step that is not taken: count it
+        if (reeval) { nf = nf + 1u; reeval = false; }
+      }
     }
     const bool accepted = do_step && acc_s;
     double dtt = 0;
@@ -844,6 +853,7 @@ __device__ __forceinline__ void lanes_body(const DevData& d, const int lane, con
       d.counters[(int64_t)LWFB_C_NF * M + m] = nf;
     }
   }
+  return by_budget;
 }
 
 #ifdef __CUDACC__
@@ -856,7 +866,16 @@ __global__ void __launch_bounds__(LWFB_LANES_BLOCK, LWFB_LANES_MINBLOCKS) integr
   unsigned tid = threadIdx.x;
   asm volatile("" : "+r"(tid));     // opaque copy of %tid: the column address stays in a register (it would be re-derived
                                     // from %tid at every use otherwise) and is still known to point to shared memory
-  lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + tid, ltab);
+  const bool by_budget =
+      lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + tid, ltab);
+  if (d.stop) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long long n_exited = atomicAdd(d.stop, 1) + 1;
+      // this block used up its quantum and no block is waiting for its slot: end the launch for everybody
+      if (by_budget && n_exited + d.resident > (long long)gridDim.x) atomicExch(d.stop + 1, 1);
+    }
+  }
 }
 #endif
 

@@ -199,6 +199,8 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   d.iter_budget = quanta ? seg_len : 0;
   d.n_slots = 0;
   d.resume = 0;
+  static int never_stop[2] = {0, 0};                 // the stop flag is raised by the __global__ wrapper only (GPU tests)
+  d.stop = never_stop; d.resident = 0; d.cb_wait = 0;
   d.prio_blocks = quanta && resort ? 1 : 0;          // the first warp runs three times as long as the others
   d.prio_budget = 3 * (long long)seg_len;
   const double tend = (double)(t0_day + n_days);

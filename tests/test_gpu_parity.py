@@ -241,6 +241,28 @@ def test_work_quanta_priority_blocks_many_members(dav_full, monkeypatch):
     h.close()
 
 
+@pytest.mark.parametrize("quantum", [0, 7])
+def test_aborting_members(dav_full, monkeypatch, quantum):
+    """retcode MaxIters (120 attempted steps) and Unstable (NaN in the initial state): records reached so far are kept,
+    the rest is NaN, counters as the oracle's - in one launch and across work quanta."""
+    monkeypatch.setenv("LWFB_QUANTUM", str(quantum))
+    ens = en.make_ensemble(dav_full, 60)
+    ens.u0[4, lo.StateIndex(ens.N, ens.iso).SWATI_mm.start + 2] = np.nan
+    nd = 9
+    h = capi.Handle(ens.N, ens.iso, ens.t0_day, nd, maxiters=120)
+    h.set_placement(2)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    h.run()
+    gpu = h.get_daily(); st, cnt = h.get_status()
+    orc.use("elem")
+    ref, st_o, cnt_o = orc.run(ens.N, ens.iso, ens.t0_day, nd, ens.forcing, ens.site_of_member, ens.scal, ens.lay, ens.u0,
+                               n_threads=8, maxiters=120)
+    assert st_o[4] == 1 and (st_o == 3).sum() >= 50
+    assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
+    assert np.array_equal(gpu, ref, equal_nan=True)
+    h.close()
+
+
 def test_nonzero_start_day_and_short_span(dav_full):
     """tspan not starting at 0 (initial conditions applied at t0, forcing taken from the right rows)."""
     e = en.make_ensemble(dav_full, 16)

@@ -118,6 +118,26 @@ def test_lane_kernel_work_quanta_with_regrouping(dav_full, isobea):
         assert np.array_equal(got, ref, equal_nan=True)
 
 
+def test_lane_kernel_aborting_members(dav_full):
+    """Members that stop early (retcode MaxIters after 120 attempted steps, Unstable from a NaN state) keep the records
+    they reached and report NaN afterwards, in a single launch and across work quanta (the abort happens in one launch,
+    later launches must leave the member alone)."""
+    e = en.make_ensemble(dav_full, 13)
+    e.u0[4, lo.StateIndex(e.N, e.iso).SWATI_mm.start + 2] = np.nan
+    orc.use("elem")
+    kw = dict(maxiters=120)
+    ref, st_o, cnt_o = orc.run(e.N, e.iso, e.t0_day, 9, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, n_threads=8, **kw)
+    assert (st_o == 3).sum() >= 10 and st_o[4] == 1, st_o            # LWFB_ST_MAXITERS / LWFB_ST_UNSTABLE
+    assert np.isnan(ref[:, -1]).all() and not np.isnan(ref[0, 2]).any()
+    for quantum, resort in ((0, False), (23, True), (1, True)):
+        got, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, 9, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
+                                seg_len=quantum, resort=resort, **kw)
+        assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
+        assert np.array_equal(got, ref, equal_nan=True)
+    got, st, cnt = emul.run(emul.MEMBER, e.N, e.iso, e.t0_day, 9, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, **kw)
+    assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o) and np.array_equal(got, ref, equal_nan=True)
+
+
 def test_emulator_rejects_divergent_warp_primitives():
     """The emulator aborts when lanes meet at different warp primitives; a well-formed run reports none.  (The
     abort path itself is exercised by the build of every kernel change: a divergent shuffle never gets here.)"""
