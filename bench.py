@@ -297,7 +297,7 @@ def main():
             "config": {"workload": f"DAV2020-full isotope ensemble: {M} members per GPU x {world} GPU(s) "
                                    f"(= {8 * M:,} at 8 GPUs), N=5 layers, {nd} days, state length {L}, Philox seed 1234; "
                                    "per step: integrate + score kernel + score all-gather; adaptive placement "
-                                   "(work quanta of 1024 block passes, members regrouped by progress between the "
+                                   "(work quanta of 128 block passes, members regrouped by progress between the "
                                    "launches, lwfb_set_placement)",
                        "members_per_gpu": M, "n_days": nd, "n_layers": N,
                        "l2": "member blocks (%.0f MB) and daily record (%.1f GB) per launch exceed the 126 MB L2"

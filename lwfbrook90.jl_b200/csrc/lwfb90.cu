@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "lwfb90_device.cuh"
 #include "lwfb90_lanes.cuh"
 #include "lwfb90_launch.h"
@@ -40,6 +42,32 @@ __global__ void soa_to_aos(const double* __restrict__ src, double* __restrict__ 
     int kk = k0 + threadIdx.x;
     if (mm < cnt && kk < K) dst[mm * K + kk] = tile[threadIdx.x][r];
   }
+}
+
+// sort keys of the placement (ascending radix sort, stable: ties keep the member order)
+//   by_cost: RHS evaluations of the previous run, most first
+//   else   : progress of the unfinished members (simulation time reached, least first); finished members get the
+//            largest key and are counted out of *n_left
+__global__ void placement_keys(const double* __restrict__ t, const int32_t* __restrict__ status,
+                               const long long* __restrict__ nf, int64_t M, double t0, double tend, int by_cost,
+                               uint32_t* __restrict__ key, int32_t* __restrict__ idx, int* __restrict__ n_left) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool unfinished = false;
+  if (i < M) {
+    uint32_t k;
+    if (by_cost) {
+      const long long c = nf[i];
+      k = 0xffffffffu - (uint32_t)(c < 0 ? 0 : (c > 0xfffffffeLL ? 0xfffffffeLL : c));
+    } else {
+      const double ti = t[i];
+      unfinished = status[i] == LWFB_ST_OK && ti < tend;
+      k = unfinished ? __float_as_uint((float)(ti - t0)) : 0xffffffffu;   // >= 0: the bit pattern orders like the value
+    }
+    key[i] = k;
+    idx[i] = (int32_t)i;
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, unfinished);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_left, __popc(b));
 }
 
 // per-member goodness of fit against observed theta / delta18O (RMSE, KGE)
@@ -150,6 +178,13 @@ struct lwfb_handle {
   int32_t* d_perm = nullptr;
   double* d_ck = nullptr;      // checkpoint block of the work-quantum execution [LWFB_CK + LWFB_CKL * N][M]
   int* d_stop = nullptr;       // {blocks exited, stop flag} of the current launch
+  // device-side sorting of the placement: keys in/out, member indices in (out = d_perm), cub scratch, unfinished count
+  uint32_t* d_key = nullptr;
+  uint32_t* d_key2 = nullptr;
+  int32_t* d_idx = nullptr;
+  void* d_sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  int* d_nleft = nullptr;
   bool perm_valid = false;     // d_perm holds a permutation for the current member count
   bool cost_valid = false;     // d_counters holds the RHS-evaluation counts of a completed lane-kernel run
   std::string err;
@@ -199,6 +234,8 @@ extern "C" int lwfb_create(lwfb_handle** out, const lwfb_opts* opts) {
 static void free_members(lwfb_handle* h) {
   cudaFree(h->d_scal); cudaFree(h->d_lay); cudaFree(h->d_u0); cudaFree(h->d_rec); cudaFree(h->d_fin);
   cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm); cudaFree(h->d_ck); cudaFree(h->d_stop);
+  cudaFree(h->d_key); cudaFree(h->d_key2); cudaFree(h->d_idx); cudaFree(h->d_sort_tmp); cudaFree(h->d_nleft);
+  h->d_key = h->d_key2 = nullptr; h->d_idx = nullptr; h->d_sort_tmp = nullptr; h->d_nleft = nullptr; h->sort_tmp_bytes = 0;
   h->d_perm = nullptr; h->d_ck = nullptr; h->d_stop = nullptr; h->perm_valid = false; h->cost_valid = false;
   h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
   h->d_site = h->d_status = nullptr; h->d_counters = nullptr;
@@ -285,6 +322,13 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
     CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
     CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + LWFB_CKL * N) * sizeof(double)));
     CK(cudaMalloc(&h->d_stop, 2 * sizeof(int)));
+    CK(cudaMalloc(&h->d_key, (size_t)M * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->d_key2, (size_t)M * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->d_idx, (size_t)M * sizeof(int32_t)));
+    CK(cudaMalloc(&h->d_nleft, sizeof(int)));
+    h->sort_tmp_bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_tmp_bytes, h->d_key, h->d_key2, h->d_idx, h->d_perm, (int)M));
+    CK(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes ? h->sort_tmp_bytes : 16));
     if (h->o.record_daily) {
       size_t bytes = (size_t)M * (h->o.n_days + 1) * L * sizeof(double);
       cudaError_t e = cudaMalloc(&h->d_rec, bytes);
@@ -329,18 +373,29 @@ static bool many_waves(const lwfb_handle* h) {
   return n_blocks >= 3 * (int64_t)n_sm * LWFB_LANES_MINBLOCKS;
 }
 
-// placement := members sorted by the number of RHS evaluations counted so far (most expensive first), so that the
-// members that share a block (and wait for each other at every step) have similar step counts
-static int sort_members_by_cost(lwfb_handle* h) {
-  std::vector<long long> nf((size_t)h->M);
-  CK(cudaMemcpy(nf.data(), h->d_counters + (size_t)LWFB_C_NF * h->M, nf.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-  std::vector<int32_t> perm((size_t)h->M);
-  for (int64_t i = 0; i < h->M; i++) perm[(size_t)i] = (int32_t)i;
-  std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return nf[(size_t)a] > nf[(size_t)b]; });
-  CK(cudaMemcpy(h->d_perm, perm.data(), perm.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+// placement (d_perm) := the members sorted on the device, see placement_keys; *n_left (optional): unfinished members
+static int sort_placement(lwfb_handle* h, bool by_cost, cudaStream_t st, int64_t* n_left) {
+  const int64_t M = h->M;
+  if (M > 0x7fffffffLL) { h->err = "more than 2^31 members per handle"; return LWFB_ERR_ARG; }
+  CK(cudaMemsetAsync(h->d_nleft, 0, sizeof(int), st));
+  placement_keys<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(
+      h->d_ck + (size_t)LWFB_CK_T * M, h->d_status, h->d_counters + (size_t)LWFB_C_NF * M, M, (double)h->o.t0_day,
+      (double)(h->o.t0_day + h->o.n_days), by_cost ? 1 : 0, h->d_key, h->d_idx, h->d_nleft);
+  CK(cudaGetLastError());
+  CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, h->sort_tmp_bytes, h->d_key, h->d_key2, h->d_idx, h->d_perm, (int)M, 0, 32, st));
+  if (n_left) {
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, h->d_nleft, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_left = n;
+  }
   h->perm_valid = true;
   return LWFB_OK;
 }
+
+// placement := members sorted by the number of RHS evaluations counted so far (most expensive first), so that the
+// members that share a block (and wait for each other at every step) have similar step counts
+static int sort_members_by_cost(lwfb_handle* h, cudaStream_t st) { return sort_placement(h, true, st, nullptr); }
 
 // one launch of the integrator over the slots [0, d.n_slots)
 static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) {
@@ -379,7 +434,7 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
   const bool sortable = lanes && h->placement >= 1 && many_waves(h);
   if (lanes && !sortable) h->perm_valid = false;
   if (sortable && h->cost_valid) {
-    int rc = sort_members_by_cost(h);
+    int rc = sort_members_by_cost(h, st);
     if (rc) return rc;
     h->cost_valid = false;
   }
@@ -406,33 +461,10 @@ extern "C" int lwfb_sync(lwfb_handle* h) {
 // Members of a block then are at the same day (they share the daily callback phases and step at a similar pace), the
 // finished ones drop out of the launch, and the front blocks hold the members that decide when the run ends.  (Sorting
 // by an estimate of the remaining steps instead was measured slower: it mixes days within a block.)
-static int regroup_by_progress(lwfb_handle* h, int64_t* n_left) {
-  const int64_t M = h->M;
-  std::vector<double> t((size_t)M);
-  std::vector<int32_t> st((size_t)M);
-  CK(cudaMemcpy(t.data(), h->d_ck + (size_t)LWFB_CK_T * M, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(st.data(), h->d_status, st.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  const double tend = (double)(h->o.t0_day + h->o.n_days), t0 = (double)h->o.t0_day;
-  std::vector<uint64_t> key;
-  key.reserve((size_t)M);
-  for (int64_t i = 0; i < M; i++) {
-    const double ti = t[(size_t)i];
-    if (st[(size_t)i] != LWFB_ST_OK || !(ti < tend)) continue;
-    const float f = (float)(ti - t0);                   // >= 0: the bit pattern orders like the value
-    uint32_t fb;
-    memcpy(&fb, &f, 4);
-    key.push_back(((uint64_t)fb << 32) | (uint32_t)i);
-  }
-  std::sort(key.begin(), key.end());
-  std::vector<int32_t> perm(key.size() ? key.size() : 1);
-  for (size_t k = 0; k < key.size(); k++) perm[k] = (int32_t)(key[k] & 0xffffffffu);
-  *n_left = (int64_t)key.size();
-  if (!key.empty()) CK(cudaMemcpy(h->d_perm, perm.data(), key.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  return LWFB_OK;
-}
+static int regroup_by_progress(lwfb_handle* h, cudaStream_t st, int64_t* n_left) { return sort_placement(h, false, st, n_left); }
 
 // Synchronous run.  With adaptive placement and enough members for regrouping to pay, the record is integrated in WORK
-// QUANTA: a block ends after LWFB_QUANTUM passes of its loop (default 1024; 0 = one launch to the end), every member
+// QUANTA: a block ends after LWFB_QUANTUM passes of its loop (default 128; 0 = one launch to the end), every member
 // checkpoints where it is (fin + ck), the host regroups the unfinished members by progress and launches
 // again.  The front blocks of a launch (least progress) keep their slots for the whole launch while the other slots
 // turn over once per quantum, so the members that decide the end of the run never wait for a slot.  Nothing has to be
@@ -440,9 +472,9 @@ static int regroup_by_progress(lwfb_handle* h, int64_t* n_left) {
 extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   if (!h || h->M < 1) return LWFB_ERR_ARG;
   CK(cudaSetDevice(h->o.device));
-  long long quantum = 1024;
+  long long quantum = 128;
   if (const char* e = getenv("LWFB_QUANTUM")) quantum = atoll(e);
-  int prio_pct = 25;                                  // share of the resident slots given to the front blocks
+  int prio_pct = 15;                                  // share of the resident slots given to the front blocks
   if (const char* e = getenv("LWFB_PRIO_PCT")) prio_pct = atoi(e);
   bool stop_flag = true;                              // end a launch when its first slot runs out of work
   if (const char* e = getenv("LWFB_STOP_FLAG")) stop_flag = atoi(e) != 0;
@@ -459,7 +491,7 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   const int64_t mpb = (int64_t)(LWFB_LANES_BLOCK / 32) * (32 / h->o.n_layers);   // members per block
   // first launch: sorted by the cost of the previous run of the handle if there was one, else as given
   if (h->cost_valid) {
-    int rc = sort_members_by_cost(h);
+    int rc = sort_members_by_cost(h, st);
     if (rc) return rc;
   } else h->perm_valid = false;
   h->n_launches = 0;
@@ -504,9 +536,7 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
     }
     int rc = launch_integrator(h, d, st);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(st));
-    if ((rc = regroup_by_progress(h, &n_left))) return rc;
-    h->perm_valid = true;
+    if ((rc = regroup_by_progress(h, st, &n_left))) return rc;
   }
   CK(cudaEventRecord(h->ev1, st));
   h->perm_valid = false;       // d_perm now holds a partial order of the last launch
