@@ -214,14 +214,16 @@ def main():
         t = torch.as_tensor(DeviceArray(ptr, (M, lo.NSCORES)), device=f"cuda:{local_rank}")
         return allgather_scores(t, M * world, rank, world)
 
-    launches = []                                             # kernels launched per step (integrator launches + score)
+    # our kernels launched per step: n integrator launches, one placement_keys kernel after each of them (regrouping)
+    # and one before the first (cost sort of a warm handle), one score kernel; cub's radix-sort kernels are not counted
+    launches = []
 
     def step_resident():
         h.run()
         ptr = h.scores_device(obs_day, obs_layer, obs_th, obs_d18)
         gather(ptr)
         n, ms = h.last_run_stats()
-        launches.append(n + 1)
+        launches.append(2 * n + 2 if n > 1 else n + 1)
         return ms
 
     def step_e2e():
