@@ -147,6 +147,11 @@ enum { LWFB_C_NACCEPT = 0, LWFB_C_NREJECT, LWFB_C_NF, LWFB_NCOUNTERS };
 /* per-member goodness-of-fit scores (lwfb_scores) */
 enum { LWFB_SC_RMSE_THETA = 0, LWFB_SC_KGE_THETA, LWFB_SC_RMSE_D18O, LWFB_SC_KGE_D18O, LWFB_NSCORES };
 
+/* columns of the water partitioning, get_water_partitioning (src/func_postprocess.jl:1310-1364): sums per period of
+ * ETa, Esoil, Esnow, Einterception, Ta, Precip, Td, D, R (mm) and the period mean of Swat (mm) */
+enum { LWFB_WP_ETA = 0, LWFB_WP_ESOIL, LWFB_WP_ESNOW, LWFB_WP_EINTERCEPTION, LWFB_WP_TA, LWFB_WP_PRECIP, LWFB_WP_TD,
+       LWFB_WP_D, LWFB_WP_R, LWFB_WP_SWAT, LWFB_NWP };
+
 /* ---------------------------------------------------------------- options
  * Defaults mirror the solve() keyword arguments fixed in setup(),
  * src/LWFBrook90.jl:552-567: Tsit5, reltol 1e-5, abstol 1e-6 (default), dt 1e-3, dtmax 1/24 d. */
@@ -222,6 +227,13 @@ int lwfb_scores(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_day,
 int lwfb_scores_device(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_day,
                        int32_t n_obs_layers, const int32_t* obs_layer,
                        const double* obs_theta, const double* obs_d18o, double** d_scores);
+
+/* replaces get_water_partitioning (src/func_postprocess.jl:1310-1364) for the whole ensemble, on the device: the daily
+ * record stays in HBM, only the aggregates come back.
+ *   group_of_record [n_days+1]   period index (0..n_groups-1) of each daily record, < 0 = record not used; the
+ *                                records of a period are expected to be contiguous (months, years)
+ *   out [n_members][n_groups][LWFB_NWP]   sums in record order (Swat: mean over the records of the period) */
+int lwfb_water_partitioning(lwfb_handle* h, int32_t n_groups, const int32_t* group_of_record, double* out);
 
 /* one evaluation of the right-hand side f(u,p,t) for every member, for unit parity tests
  * (replaces f_LWFBrook90!, src/func_DiffEq_definition_f.jl:7-243):

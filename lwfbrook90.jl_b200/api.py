@@ -184,6 +184,19 @@ class EnsembleResult:
     def scores(self, obs_day, obs_layer, obs_theta=None, obs_d18o=None):
         return self.handle.scores(obs_day, obs_layer, obs_theta, obs_d18o)
 
+    def water_partitioning(self, reference_date, period: str = "month"):
+        """Ensemble form of get_water_partitioning (src/func_postprocess.jl:1310-1364), aggregated on the GPU: returns
+        (labels, table) with labels = the (year, month) / (year,) of each period and table [M, n_periods, NWP] in
+        layout.WP column order (sums; Swat: mean).  The daily record stays on the device."""
+        dates = [reference_date + _dt.timedelta(days=float(t)) for t in range(self.ens.t0_day, self.ens.t0_day + self.handle.n_days + 1)]
+        lab = [(d.year, d.month) if period == "month" else (d.year,) for d in dates]
+        uniq = []
+        for l in lab:
+            if l not in uniq:
+                uniq.append(l)
+        group = np.array([uniq.index(l) for l in lab], dtype=np.int32)
+        return uniq, self.handle.water_partitioning(group, len(uniq))
+
     def close(self):
         self.handle.close()
 

@@ -48,5 +48,7 @@ def build_library(force: bool = False, verbose: bool = False, extra=()) -> str:
         for cmd, p in procs:
             if p.wait() != 0:
                 raise subprocess.CalledProcessError(p.returncode, cmd)
-        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT] + objs, cwd=_CSRC)
+        tmp = OUT + ".tmp"      # link beside the target and rename: a reader never sees a half-written library
+        subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp] + objs, cwd=_CSRC)
+        os.replace(tmp, OUT)
     return OUT

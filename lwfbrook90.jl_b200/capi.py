@@ -37,7 +37,8 @@ _lib = None
 SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error", "lwfb_set_sites",
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
            "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
-           "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy", "lwfb_set_placement"]
+           "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy", "lwfb_set_placement",
+           "lwfb_water_partitioning"]
 
 
 def lib():
@@ -66,6 +67,7 @@ def lib():
         L.lwfb_eval_rhs.argtypes = [vp, C.c_double, _dp, _dp, _dp, _dp, _dp]; L.lwfb_eval_rhs.restype = C.c_int
         L.lwfb_last_run_stats.argtypes = [vp, _ip, C.POINTER(C.c_float)]; L.lwfb_last_run_stats.restype = C.c_int
         L.lwfb_elem_eval.argtypes = [C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp]; L.lwfb_elem_eval.restype = C.c_int
+        L.lwfb_water_partitioning.argtypes = [vp, C.c_int32, _ip, _dp]; L.lwfb_water_partitioning.restype = C.c_int
         _lib = L
     return _lib
 
@@ -203,6 +205,18 @@ class Handle:
                                             None if th is None else _p(th), None if d18 is None else _p(d18),
                                             C.byref(ptr)))
         return int(ptr.value)
+
+    def water_partitioning(self, group_of_record, n_groups=None):
+        """Per member and period: sums of ETa, Esoil, Esnow, Einterception, Ta, Precip, Td, D, R and the mean of Swat
+        (lo.WP columns), aggregated on the GPU from the daily record.  group_of_record [n_days+1]: period index of every
+        daily record (< 0: skip).  Returns [M, n_groups, NWP]."""
+        g = np.ascontiguousarray(group_of_record, dtype=np.int32)
+        if g.shape != (self.n_days + 1,):
+            raise LwfbError(f"group_of_record must have n_days + 1 = {self.n_days + 1} entries")
+        ng = int(g.max()) + 1 if n_groups is None else int(n_groups)
+        out = np.empty((self.M, ng, lo.NWP))
+        self._ck(self._L.lwfb_water_partitioning(self._h, ng, _p(g, _ip), _p(out)))
+        return out
 
     def eval_rhs(self, t, swati, gwat, frozen, ntfli_prev):
         sw, gw, fr, nt = _f64(swati), _f64(gwat), _f64(frozen), _f64(ntfli_prev)

@@ -22,6 +22,7 @@
 #include "lwfb90_device.cuh"
 #include "lwfb90_lanes.cuh"
 #include "lwfb90_launch.h"
+#include "lwfb90_post.cuh"
 
 using namespace lwfb;
 
@@ -543,6 +544,33 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   h->ran = true;
   h->cost_valid = true;
   return lwfb_sync(h);
+}
+
+extern "C" int lwfb_water_partitioning(lwfb_handle* h, int32_t n_groups, const int32_t* group_of_record, double* out) {
+  if (!h || !out || !group_of_record || n_groups < 1 || !h->ran) return LWFB_ERR_ARG;
+  if (!h->d_rec) { h->err = "handle was created with record_daily = 0"; return LWFB_ERR_ARG; }
+  CK(cudaSetDevice(h->o.device));
+  const int n_rec = h->o.n_days + 1;
+  std::vector<int32_t> n_in((size_t)n_groups, 0);
+  for (int r = 0; r < n_rec; r++)
+    if (group_of_record[r] >= 0 && group_of_record[r] < n_groups) n_in[(size_t)group_of_record[r]]++;
+  int32_t* d_grp = nullptr;
+  double* d_out = nullptr;
+  const size_t out_bytes = (size_t)h->M * n_groups * LWFB_NWP * sizeof(double);
+  CK(cudaMalloc(&d_grp, (size_t)(n_rec + n_groups) * sizeof(int32_t)));
+  cudaError_t e = cudaMalloc(&d_out, out_bytes);
+  if (e != cudaSuccess) { cudaFree(d_grp); h->err = "cannot allocate the aggregate block"; return LWFB_ERR_NOMEM; }
+  cudaMemcpy(d_grp, group_of_record, (size_t)n_rec * sizeof(int32_t), cudaMemcpyHostToDevice);
+  cudaMemcpy(d_grp + n_rec, n_in.data(), (size_t)n_groups * sizeof(int32_t), cudaMemcpyHostToDevice);
+  const SIdx ix(h->o.n_layers, h->o.simulate_isotopes);
+  water_partitioning_kernel<<<(unsigned)((h->M + 127) / 128), 128>>>(h->d_rec, h->M, h->L, ix.ACC, n_rec, d_grp, n_groups, d_out);
+  const int64_t n_cells = h->M * (int64_t)n_groups;
+  water_partitioning_mean<<<(unsigned)((n_cells + 255) / 256), 256>>>(d_out, h->M, n_groups, d_grp + n_rec);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_grp); cudaFree(d_out);
+  if (e != cudaSuccess) { h->err = std::string("lwfb_water_partitioning: ") + cudaGetErrorString(e); return LWFB_ERR_CUDA; }
+  return LWFB_OK;
 }
 
 extern "C" int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* device_ms) {

@@ -58,6 +58,7 @@ A = _NS("LWFB_A_", "LWFB_NACCUM")   # accumulators
 C = _NS("LWFB_C_", "LWFB_NCOUNTERS")
 SC = _NS("LWFB_SC_", "LWFB_NSCORES")
 ST = _NS("LWFB_ST_", None)
+WP = _NS("LWFB_WP_", "LWFB_NWP")     # water-partitioning columns
 
 NF = _E["LWFB_F"]
 NPS = _E["LWFB_PS"]
@@ -65,6 +66,7 @@ NPL = _E["LWFB_PL"]
 NACCUM = _E["LWFB_NACCUM"]
 NCOUNTERS = _E["LWFB_NCOUNTERS"]
 NSCORES = _E["LWFB_NSCORES"]
+NWP = _E["LWFB_NWP"]
 
 ACCUM_NAMES = (
     "cum_d_prec", "cum_d_rfal", "cum_d_sfal", "cum_d_rint", "cum_d_sint", "cum_d_rsno",

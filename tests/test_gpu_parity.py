@@ -418,3 +418,59 @@ def test_abi_error_handling(dav_full):
         h.get_daily()
     assert h.get_final().shape == (4, ens.u0.shape[1])
     h.close()
+
+
+def water_partitioning_numpy(rec, ix, group, n_groups):
+    """Sequential-order restatement of get_water_partitioning (src/func_postprocess.jl:1310-1364) for a block of members:
+    rec [M, n_rec, L] -> [M, n_groups, NWP].  np.cumsum adds in record order, like the device kernel."""
+    A = lambda n: rec[:, :, ix.acc(n)]
+    daily = np.empty(rec.shape[:2] + (lo.NWP,))
+    daily[..., lo.WP.ETA] = A("cum_d_evap"); daily[..., lo.WP.ESOIL] = A("cum_d_slvp"); daily[..., lo.WP.ESNOW] = A("cum_d_snvp")
+    daily[..., lo.WP.EINTERCEPTION] = A("cum_d_irvp") + A("cum_d_isvp")
+    daily[..., lo.WP.TA] = A("cum_d_tran"); daily[..., lo.WP.PRECIP] = A("cum_d_prec")
+    daily[..., lo.WP.TD] = A("cum_d_ptran") - A("cum_d_tran")
+    daily[..., lo.WP.D] = -A("vrfln"); daily[..., lo.WP.R] = -(A("srfl") + A("byfl") + A("dsfl"))
+    daily[..., lo.WP.SWAT] = A("StorageSWAT")
+    out = np.full((rec.shape[0], n_groups, lo.NWP), np.nan)
+    for g in range(n_groups):
+        sel = np.flatnonzero(group == g)
+        if sel.size == 0:
+            out[:, g, :lo.WP.SWAT] = 0.0
+            continue
+        out[:, g] = np.cumsum(daily[:, sel], axis=1)[:, -1]
+        out[:, g, lo.WP.SWAT] /= sel.size
+    return out
+
+
+def test_water_partitioning_on_device(dav_full):
+    """N3 of SURVEY 8f: monthly / yearly water partitioning of every member aggregated on the GPU from the resident
+    daily record — bit-identical to the sequential numpy restatement, and equal (1e-12) to the reference-facing
+    get_water_partitioning of the single-member API on member 0."""
+    import datetime as dt
+    ens = en.make_ensemble(dav_full, 70)
+    nd = 100
+    res = api.simulate_ensemble(ens, n_days=nd)
+    rec = res.daily()
+    ix = lo.StateIndex(ens.N, ens.iso)
+    ref_date = dav_full.parametrizedSPAC.reference_date
+    for period in ("month", "year"):
+        labels, tab = res.water_partitioning(ref_date, period)
+        dates = [ref_date + dt.timedelta(days=float(t)) for t in range(ens.t0_day, ens.t0_day + nd + 1)]
+        lab = [(d.year, d.month) if period == "month" else (d.year,) for d in dates]
+        group = np.array([labels.index(l) for l in lab], dtype=np.int32)
+        assert tab.shape == (ens.M, len(labels), lo.NWP)
+        assert np.array_equal(tab, water_partitioning_numpy(rec, ix, group, len(labels)))
+    # records that are not used (group < 0) and an empty period
+    group = np.full(nd + 1, -1, dtype=np.int32); group[10:40] = 0; group[40:41] = 2
+    tab = res.handle.water_partitioning(group, 3)
+    want = water_partitioning_numpy(rec, ix, group, 3)
+    assert np.array_equal(tab, want, equal_nan=True) and np.isnan(tab[:, 1, lo.WP.SWAT]).all()
+    # against the reference-facing single-member function (numpy pairwise sums): member 0 = the unmodified site
+    import copy
+    sim = copy.deepcopy(dav_full)             # fresh object: simulate_ stores its solution in it
+    api.simulate_(sim, tspan=(ens.t0_day, ens.t0_day + nd))
+    _, monthly, _ = api.get_water_partitioning(sim)
+    labels, tab = res.water_partitioning(ref_date, "month")
+    for c, name in ((lo.WP.ETA, "ETa"), (lo.WP.TD, "Td"), (lo.WP.D, "D"), (lo.WP.R, "R"), (lo.WP.PRECIP, "Precip"), (lo.WP.SWAT, "Swat")):
+        np.testing.assert_allclose(tab[0, :, c], monthly[name], rtol=1e-12, atol=1e-12)
+    res.close()
