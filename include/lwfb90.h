@@ -235,6 +235,17 @@ int lwfb_scores_device(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_da
  *   out [n_members][n_groups][LWFB_NWP]   sums in record order (Swat: mean over the records of the period) */
 int lwfb_water_partitioning(lwfb_handle* h, int32_t n_groups, const int32_t* group_of_record, double* out);
 
+/* soil variables of get_soil_ (src/func_postprocess.jl:1025-1045; derive_auxiliary_SOILVAR, src/module_KPT.jl:432-443) */
+enum { LWFB_SV_THETA = 0, LWFB_SV_PSI /* kPa */, LWFB_SV_W, LWFB_SV_SWATI /* mm */, LWFB_SV_K /* mm/day */,
+       LWFB_SV_D18O, LWFB_SV_D2H /* permil, NaN without isotopes */, LWFB_NSV };
+
+/* replaces get_soil_ (src/func_postprocess.jl:1025-1045) for the whole ensemble, on the device:
+ *   rec_idx   [n_rec_sel]   daily records to read (0..n_days)
+ *   layer_idx [n_lay_sel]   0-based layers (the depth -> layer lookup, get_soil_idx, stays on the host)
+ *   out [n_members][n_rec_sel][n_lay_sel][LWFB_NSV] */
+int lwfb_soil_state(lwfb_handle* h, int32_t n_rec_sel, const int32_t* rec_idx, int32_t n_lay_sel,
+                    const int32_t* layer_idx, double* out);
+
 /* one evaluation of the right-hand side f(u,p,t) for every member, for unit parity tests
  * (replaces f_LWFBrook90!, src/func_DiffEq_definition_f.jl:7-243):
  *   swati [n_members][N], gwat [n_members], t scalar, daily-frozen fluxes as set by the

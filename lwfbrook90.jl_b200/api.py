@@ -197,6 +197,15 @@ class EnsembleResult:
         group = np.array([uniq.index(l) for l in lab], dtype=np.int32)
         return uniq, self.handle.water_partitioning(group, len(uniq))
 
+    def soil_state(self, days_to_read_out_d, *, depths_to_read_out_mm=None, layers=None):
+        """Ensemble form of get_soil_ (src/func_postprocess.jl:1025-1045), computed on the GPU: [M, n_days, n_layers,
+        NSV] in layout.SV column order for the given days (record indices relative to the start of the run) and either
+        depths (mm, looked up in the shared grid as get_soil_idx does) or 0-based layer indices."""
+        if layers is None:
+            lower = np.cumsum(self.ens.lay[0, lo.L.THICK])
+            layers = [int(np.nonzero(d <= lower)[0][0]) for d in depths_to_read_out_mm if 0 < d <= lower.max()]
+        return self.handle.soil_state(np.asarray(days_to_read_out_d, dtype=np.int32), np.asarray(layers, dtype=np.int32))
+
     def close(self):
         self.handle.close()
 

@@ -38,7 +38,7 @@ SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error"
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
            "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
            "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy", "lwfb_set_placement",
-           "lwfb_water_partitioning"]
+           "lwfb_water_partitioning", "lwfb_soil_state"]
 
 
 def lib():
@@ -68,6 +68,7 @@ def lib():
         L.lwfb_last_run_stats.argtypes = [vp, _ip, C.POINTER(C.c_float)]; L.lwfb_last_run_stats.restype = C.c_int
         L.lwfb_elem_eval.argtypes = [C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp]; L.lwfb_elem_eval.restype = C.c_int
         L.lwfb_water_partitioning.argtypes = [vp, C.c_int32, _ip, _dp]; L.lwfb_water_partitioning.restype = C.c_int
+        L.lwfb_soil_state.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp]; L.lwfb_soil_state.restype = C.c_int
         _lib = L
     return _lib
 
@@ -216,6 +217,15 @@ class Handle:
         ng = int(g.max()) + 1 if n_groups is None else int(n_groups)
         out = np.empty((self.M, ng, lo.NWP))
         self._ck(self._L.lwfb_water_partitioning(self._h, ng, _p(g, _ip), _p(out)))
+        return out
+
+    def soil_state(self, rec_idx, layer_idx):
+        """theta, psi, W, SWATI, K, delta18O, delta2H (lo.SV columns) of the given daily records and 0-based layers for
+        every member, computed on the GPU.  Returns [M, len(rec_idx), len(layer_idx), NSV]."""
+        r = np.ascontiguousarray(rec_idx, dtype=np.int32).ravel()
+        l = np.ascontiguousarray(layer_idx, dtype=np.int32).ravel()
+        out = np.empty((self.M, len(r), len(l), lo.NSV))
+        self._ck(self._L.lwfb_soil_state(self._h, len(r), _p(r, _ip), len(l), _p(l, _ip), _p(out)))
         return out
 
     def eval_rhs(self, t, swati, gwat, frozen, ntfli_prev):

@@ -573,6 +573,33 @@ extern "C" int lwfb_water_partitioning(lwfb_handle* h, int32_t n_groups, const i
   return LWFB_OK;
 }
 
+extern "C" int lwfb_soil_state(lwfb_handle* h, int32_t n_rec_sel, const int32_t* rec_idx, int32_t n_lay_sel,
+                               const int32_t* layer_idx, double* out) {
+  if (!h || !out || !rec_idx || !layer_idx || n_rec_sel < 1 || n_lay_sel < 1 || !h->ran) return LWFB_ERR_ARG;
+  if (!h->d_rec) { h->err = "handle was created with record_daily = 0"; return LWFB_ERR_ARG; }
+  for (int k = 0; k < n_rec_sel; k++)
+    if (rec_idx[k] < 0 || rec_idx[k] > h->o.n_days) { h->err = "record index out of range"; return LWFB_ERR_ARG; }
+  for (int q = 0; q < n_lay_sel; q++)
+    if (layer_idx[q] < 0 || layer_idx[q] >= h->o.n_layers) { h->err = "layer index out of range"; return LWFB_ERR_ARG; }
+  CK(cudaSetDevice(h->o.device));
+  int32_t* d_idx = nullptr;
+  double* d_out = nullptr;
+  const size_t out_bytes = (size_t)h->M * n_rec_sel * n_lay_sel * LWFB_NSV * sizeof(double);
+  CK(cudaMalloc(&d_idx, (size_t)(n_rec_sel + n_lay_sel) * sizeof(int32_t)));
+  cudaError_t e = cudaMalloc(&d_out, out_bytes);
+  if (e != cudaSuccess) { cudaFree(d_idx); h->err = "cannot allocate the soil-state block"; return LWFB_ERR_NOMEM; }
+  cudaMemcpy(d_idx, rec_idx, (size_t)n_rec_sel * sizeof(int32_t), cudaMemcpyHostToDevice);
+  cudaMemcpy(d_idx + n_rec_sel, layer_idx, (size_t)n_lay_sel * sizeof(int32_t), cudaMemcpyHostToDevice);
+  soil_state_kernel<<<(unsigned)((h->M + 127) / 128), 128>>>(h->d_rec, h->d_lay, h->M, h->o.n_layers, h->L,
+                                                             h->o.simulate_isotopes, n_rec_sel, d_idx, n_lay_sel,
+                                                             d_idx + n_rec_sel, d_out);
+  e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d_idx); cudaFree(d_out);
+  if (e != cudaSuccess) { h->err = std::string("lwfb_soil_state: ") + cudaGetErrorString(e); return LWFB_ERR_CUDA; }
+  return LWFB_OK;
+}
+
 extern "C" int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* device_ms) {
   if (!h) return LWFB_ERR_ARG;
   if (n_launches) *n_launches = h->n_launches;

@@ -65,4 +65,43 @@ __global__ void water_partitioning_mean(double* __restrict__ out, int64_t M, int
   *v = n > 0 ? *v / (double)n : NAN;
 }
 
+// soil_state_kernel: the ensemble form of get_soil_ (src/func_postprocess.jl:1025-1045 with the soil variables of
+// derive_auxiliary_SOILVAR, src/module_KPT.jl:432-443): for every member, selected daily records and selected layers
+//   theta (-), psi (kPa), W (-), SWATI (mm), K (mm/day), delta18O, delta2H (permil; NaN without isotopes)
+// out [M][n_rec_sel][n_lay_sel][LWFB_NSV].  Same expressions as the daily callback of the integrator.
+__global__ void soil_state_kernel(const double* __restrict__ rec, const double* __restrict__ lay, int64_t M, int N, int L,
+                                  int iso, int n_rec_sel, const int32_t* __restrict__ rec_idx, int n_lay_sel,
+                                  const int32_t* __restrict__ lay_idx, double* __restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  auto LP = [&](int field, int i) { return __ldg(lay + ((int64_t)field * N + i) * M + m); };
+  for (int q = 0; q < n_lay_sel; q++) {
+    const int i = lay_idx[q];
+    const double THSAT = LP(LWFB_L_THSAT, i), THR = LP(LWFB_L_THR, i), SWATMAX = LP(LWFB_L_SWATMAX, i);
+    const double NPAR = LP(LWFB_L_NPAR, i), MPAR = LP(LWFB_L_MPAR, i);
+    const double DTH = THSAT - THR, E1 = -1.0 / MPAR, E2 = 1.0 / NPAR, E3 = NPAR / (NPAR - 1.0);
+    const double CPSI = 9.81 * (-1.0 / LP(LWFB_L_ALPHA, i)), KSAT = LP(LWFB_L_KSAT, i), TORT = LP(LWFB_L_TORT, i);
+    for (int k = 0; k < n_rec_sel; k++) {
+      const double* r = rec + (int64_t)rec_idx[k] * L * M;
+      const double sw = r[(int64_t)i * M + m];
+      const double w = jminc((THSAT * sw / SWATMAX - THR) / DTH, 1.0);
+      const double a = jmaxc(w, 1.e-6);
+      const double la = lwfb_log(a);
+      const double p1 = lwfb_pow_from_log(a, la, E1);
+      const double psim = CPSI * lwfb_pow(p1 - 1.0, E2);
+      const double p3 = lwfb_pow_from_log(a, la, E3);
+      const double inner = 1.0 - lwfb_pow(1.0 - p3, 1.0 - E2);
+      const double kk = KSAT * lwfb_pow_from_log(a, la, TORT) * (inner * inner);
+      double* o = out + ((m * n_rec_sel + k) * (int64_t)n_lay_sel + q) * LWFB_NSV;
+      o[LWFB_SV_THETA] = w * DTH + THR;
+      o[LWFB_SV_PSI] = psim;
+      o[LWFB_SV_W] = w;
+      o[LWFB_SV_SWATI] = sw;
+      o[LWFB_SV_K] = kk;
+      o[LWFB_SV_D18O] = iso ? r[(int64_t)(N + i) * M + m] : NAN;
+      o[LWFB_SV_D2H] = iso ? r[(int64_t)(2 * N + i) * M + m] : NAN;
+    }
+  }
+}
+
 }  // namespace lwfb

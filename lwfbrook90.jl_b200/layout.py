@@ -59,6 +59,7 @@ C = _NS("LWFB_C_", "LWFB_NCOUNTERS")
 SC = _NS("LWFB_SC_", "LWFB_NSCORES")
 ST = _NS("LWFB_ST_", None)
 WP = _NS("LWFB_WP_", "LWFB_NWP")     # water-partitioning columns
+SV = _NS("LWFB_SV_", "LWFB_NSV")     # soil variables of get_soil_
 
 NF = _E["LWFB_F"]
 NPS = _E["LWFB_PS"]
@@ -67,6 +68,7 @@ NACCUM = _E["LWFB_NACCUM"]
 NCOUNTERS = _E["LWFB_NCOUNTERS"]
 NSCORES = _E["LWFB_NSCORES"]
 NWP = _E["LWFB_NWP"]
+NSV = _E["LWFB_NSV"]
 
 ACCUM_NAMES = (
     "cum_d_prec", "cum_d_rfal", "cum_d_sfal", "cum_d_rint", "cum_d_sint", "cum_d_rsno",

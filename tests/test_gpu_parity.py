@@ -474,3 +474,37 @@ def test_water_partitioning_on_device(dav_full):
     for c, name in ((lo.WP.ETA, "ETa"), (lo.WP.TD, "Td"), (lo.WP.D, "D"), (lo.WP.R, "R"), (lo.WP.PRECIP, "Precip"), (lo.WP.SWAT, "Swat")):
         np.testing.assert_allclose(tab[0, :, c], monthly[name], rtol=1e-12, atol=1e-12)
     res.close()
+
+
+def test_soil_state_on_device(dav_full, bea):
+    """N3 of SURVEY 8f: get_soil_ for every member on the GPU.  theta, W, SWATI and the deltas are bit-identical to the
+    host post-processing (same IEEE operations); psi and K go through pow and agree to 1e-9 with the numpy twin of
+    derive_auxiliary_SOILVAR (src/module_KPT.jl:432-443)."""
+    from lwfbrook90.jl_b200 import kpt
+    for sim in (dav_full, bea):
+        ens = en.make_ensemble(sim, 40)
+        nd = 30
+        res = api.simulate_ensemble(ens, n_days=nd)
+        rec = res.daily()
+        ix = lo.StateIndex(ens.N, ens.iso)
+        days = np.array([0, 1, 7, 30])
+        layers = np.array([0, ens.N - 1, 2])
+        got = res.soil_state(days, layers=layers)
+        assert got.shape == (ens.M, 4, 3, lo.NSV)
+        S = rec[:, days][:, :, ix.SWATI_mm][:, :, layers]
+        P = lambda k: ens.lay[:, k][:, None, layers]
+        W = np.minimum(1.0, (P(lo.L.THSAT) * S / P(lo.L.SWATMAX) - P(lo.L.THR)) / (P(lo.L.THSAT) - P(lo.L.THR)))
+        assert np.array_equal(got[..., lo.SV.SWATI], S) and np.array_equal(got[..., lo.SV.W], W)
+        assert np.array_equal(got[..., lo.SV.THETA], kpt.FTheta_MvG(W, P(lo.L.THSAT), P(lo.L.THR)))
+        np.testing.assert_allclose(got[..., lo.SV.PSI], kpt.FPSIM_MvG(W, P(lo.L.ALPHA), P(lo.L.NPAR), P(lo.L.MPAR)), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(got[..., lo.SV.K], kpt.FK_MvG(W, P(lo.L.KSAT), P(lo.L.TORT), P(lo.L.NPAR)), rtol=1e-9, atol=1e-300)
+        if ens.iso:
+            assert np.array_equal(got[..., lo.SV.D18O], rec[:, days][:, :, ix.SWATI_d18O][:, :, layers], equal_nan=True)
+            assert np.array_equal(got[..., lo.SV.D2H], rec[:, days][:, :, ix.SWATI_d2H][:, :, layers], equal_nan=True)
+        else:
+            assert np.isnan(got[..., lo.SV.D18O]).all()
+        # depth lookup as get_soil_idx: 100 mm and 500 mm of the shared grid
+        by_depth = res.soil_state(days, depths_to_read_out_mm=[100, 500])
+        idx = api.get_soil_idx(sim, [100, 500], only_valid_idxs=True)
+        assert np.array_equal(by_depth, res.soil_state(days, layers=[i - 1 for i in idx]), equal_nan=True)
+        res.close()
