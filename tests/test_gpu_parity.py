@@ -497,7 +497,7 @@ def test_soil_state_on_device(dav_full, bea):
         assert np.array_equal(got[..., lo.SV.SWATI], S) and np.array_equal(got[..., lo.SV.W], W)
         assert np.array_equal(got[..., lo.SV.THETA], kpt.FTheta_MvG(W, P(lo.L.THSAT), P(lo.L.THR)))
         np.testing.assert_allclose(got[..., lo.SV.PSI], kpt.FPSIM_MvG(W, P(lo.L.ALPHA), P(lo.L.NPAR), P(lo.L.MPAR)), rtol=1e-9, atol=1e-12)
-        np.testing.assert_allclose(got[..., lo.SV.K], kpt.FK_MvG(W, P(lo.L.KSAT), P(lo.L.TORT), P(lo.L.NPAR)), rtol=1e-9, atol=1e-300)
+        np.testing.assert_allclose(got[..., lo.SV.K], kpt.FK_MvG(W, P(lo.L.KSAT), P(lo.L.TORT), P(lo.L.NPAR)), rtol=1e-7)   # 1 - (1 - A^..)^.. cancels in both implementations
         if ens.iso:
             assert np.array_equal(got[..., lo.SV.D18O], rec[:, days][:, :, ix.SWATI_d18O][:, :, layers], equal_nan=True)
             assert np.array_equal(got[..., lo.SV.D2H], rec[:, days][:, :, ix.SWATI_d2H][:, :, layers], equal_nan=True)
