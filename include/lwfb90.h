@@ -277,8 +277,9 @@ int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on);
  * it is, the unfinished members are regrouped by progress (least first) and resumed; the front blocks of a launch keep
  * their slots for the whole launch (LWFB_PRIO_PCT % of the resident slots, default 15).  Nothing needs to be known
  * about the members in advance; if the handle has run before (same member count), the first launch is sorted by the
- * RHS evaluations of that run.  Launches of fewer than three waves of blocks are not regrouped (nothing to balance)
- * and lwfb_run_async is always a single launch (cost-sorted if the handle has run before).
+ * RHS evaluations of that run.  When the unfinished members no longer fill the device they are dealt thinly to all
+ * resident slots (LWFB_SPREAD, default 1).  Ensembles that do not fill the device once (LWFB_MIN_WAVES, default 1) run
+ * in one launch, and lwfb_run_async is always a single launch (cost-sorted if the handle has run before).
  * mode 0: one launch, members as given.  mode 2: like 1 but also for small launches (testing). */
 int lwfb_set_placement(lwfb_handle* h, int32_t mode);
 

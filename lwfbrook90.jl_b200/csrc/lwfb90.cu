@@ -71,6 +71,14 @@ __global__ void placement_keys(const double* __restrict__ t, const int32_t* __re
   if ((threadIdx.x & 31) == 0 && b) atomicAdd(n_left, __popc(b));
 }
 
+// thin placement for a device that is not full: sorted member j goes to slot (j / per_block) * slots_per_block +
+// (j % per_block), i.e. every block gets members for its first per_block slots only and the rest stays empty (-1)
+__global__ void spread_placement(const int32_t* __restrict__ sorted, int64_t n, int per_block, int slots_per_block,
+                                 int32_t* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[(j / per_block) * slots_per_block + (j % per_block)] = sorted[j];
+}
+
 // per-member goodness of fit against observed theta / delta18O (RMSE, KGE)
 __global__ void score_kernel(DevData d, int n_obs_days, const int32_t* __restrict__ obs_day, int n_obs_layers,
                              const int32_t* __restrict__ obs_layer, const double* __restrict__ obs_theta,
@@ -186,6 +194,7 @@ struct lwfb_handle {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int* d_nleft = nullptr;
+  int32_t* d_perm_thin = nullptr;   // placement with empty slots (spread_placement), [resident blocks x slots per block]
   bool perm_valid = false;     // d_perm holds a permutation for the current member count
   bool cost_valid = false;     // d_counters holds the RHS-evaluation counts of a completed lane-kernel run
   std::string err;
@@ -236,6 +245,7 @@ static void free_members(lwfb_handle* h) {
   cudaFree(h->d_scal); cudaFree(h->d_lay); cudaFree(h->d_u0); cudaFree(h->d_rec); cudaFree(h->d_fin);
   cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm); cudaFree(h->d_ck); cudaFree(h->d_stop);
   cudaFree(h->d_key); cudaFree(h->d_key2); cudaFree(h->d_idx); cudaFree(h->d_sort_tmp); cudaFree(h->d_nleft);
+  cudaFree(h->d_perm_thin); h->d_perm_thin = nullptr;
   h->d_key = h->d_key2 = nullptr; h->d_idx = nullptr; h->d_sort_tmp = nullptr; h->d_nleft = nullptr; h->sort_tmp_bytes = 0;
   h->d_perm = nullptr; h->d_ck = nullptr; h->d_stop = nullptr; h->perm_valid = false; h->cost_valid = false;
   h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
@@ -479,17 +489,24 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   if (const char* e = getenv("LWFB_PRIO_PCT")) prio_pct = atoi(e);
   bool stop_flag = true;                              // end a launch when its first slot runs out of work
   if (const char* e = getenv("LWFB_STOP_FLAG")) stop_flag = atoi(e) != 0;
-  const bool quanta = use_lanes(h) && h->placement >= 1 && quantum > 0 && many_waves(h);
+  int min_waves = 1;                                  // launches that do not fill the device once are not cut into quanta
+  if (const char* e = getenv("LWFB_MIN_WAVES")) min_waves = atoi(e);
+  bool spread = true;                                 // a device that is not full gets its members spread thinly over all slots
+  if (const char* e = getenv("LWFB_SPREAD")) spread = atoi(e) != 0;
+  int n_sm = 148;
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->o.device);
+  const int64_t R = (int64_t)n_sm * LWFB_LANES_MINBLOCKS;                       // resident blocks
+  const int64_t mpw = 32 / (h->o.n_layers > 0 && h->o.n_layers <= 32 ? h->o.n_layers : 32);   // members per warp
+  const int64_t wpb = LWFB_LANES_BLOCK / 32;
+  const int64_t mpb = wpb * mpw;                                                 // members per block
+  const bool enough = h->placement == 2 || (h->M + mpb - 1) / mpb >= (int64_t)min_waves * R;
+  const bool quanta = use_lanes(h) && h->placement >= 1 && quantum > 0 && enough;
   if (!quanta) {
     int rc = lwfb_run_async(h, cuda_stream);
     if (rc) return rc;
     return lwfb_sync(h);
   }
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  int n_sm = 148;
-  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->o.device);
-  const int64_t R = (int64_t)n_sm * LWFB_LANES_MINBLOCKS;                       // resident blocks
-  const int64_t mpb = (int64_t)(LWFB_LANES_BLOCK / 32) * (32 / h->o.n_layers);   // members per block
   // first launch: sorted by the cost of the previous run of the handle if there was one, else as given
   if (h->cost_valid) {
     int rc = sort_members_by_cost(h, st);
@@ -514,6 +531,18 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
       // every block has a slot: longer quanta the emptier the device (regrouping only thins the blocks out)
       int64_t f = R / nb;
       d.iter_budget = q * (f > 16 ? 16 : f);
+      // ... and thinner blocks: the members are dealt to all resident slots, w warps per block instead of all eight,
+      // so that a pass runs at the latency of few warps per SM (what is left at the end of a run is its critical path)
+      const int64_t w = (n_left + R * mpw - 1) / (R * mpw);
+      if (spread && h->perm_valid && w < wpb) {
+        const int64_t per_block = w * mpw, nbt = (n_left + per_block - 1) / per_block;
+        if (!h->d_perm_thin) CK(cudaMalloc(&h->d_perm_thin, (size_t)(R * mpb) * sizeof(int32_t)));
+        CK(cudaMemsetAsync(h->d_perm_thin, 0xff, (size_t)(nbt * mpb) * sizeof(int32_t), st));
+        spread_placement<<<(unsigned)((n_left + 255) / 256), 256, 0, st>>>(h->d_perm, n_left, (int)per_block, (int)mpb, h->d_perm_thin);
+        CK(cudaGetLastError());
+        d.perm = h->d_perm_thin;
+        d.n_slots = nbt * mpb;
+      }
     } else if (ramp) {
       d.iter_budget = q;
     } else {

@@ -120,9 +120,10 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
   const int base = g * N;
   const int64_t m_raw = warp_g * mpw + g;            // slot of the group
   const int64_t n_slots = d.n_slots > 0 ? d.n_slots : M;
-  const bool live = lane_valid && m_raw < n_slots;
   const int64_t slot = (m_raw < n_slots) ? m_raw : n_slots - 1;
-  const int64_t m = d.perm ? (int64_t)__ldg(d.perm + slot) : slot;   // member placed in this slot
+  const int64_t placed = d.perm ? (int64_t)__ldg(d.perm + slot) : slot;   // member placed in this slot; < 0: the slot is empty
+  const bool live = lane_valid && m_raw < n_slots && placed >= 0;
+  const int64_t m = placed >= 0 ? placed : 0;        // (lanes that are not live read some member's data and never write)
   const bool top = (i == 0), bot = (i == N - 1);
   const bool nodn = bot || !lane_valid, noup = top || !lane_valid;   // lanes without a real neighbour below / above
   const int L = d.L;

@@ -43,7 +43,7 @@ def lib():
         _lib.lwfb_emul_run.restype = C.c_int
         _lib.lwfb_emul_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int64, _ip,
                                        _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int,
-                                       _dp, _ip, _lp, _ip, C.c_int, C.c_int]
+                                       _dp, _ip, _lp, _ip, C.c_int, C.c_int, C.c_int64]
     return _lib
 
 
@@ -74,7 +74,7 @@ def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, 
                              _p(scal), _p(lay), _p(u0), reltol, abstol, dt_init, dtmax, maxiters, int(n_threads), _p(out),
                              _p(status, _ip), _p(counters, _lp),
                              None if perm is None else _p(np.ascontiguousarray(perm, dtype=np.int32), _ip),
-                             int(seg_len), int(bool(resort)))
+                             int(seg_len), int(bool(resort)), 0 if perm is None else int(len(perm)))
     if rc != 0:
         raise RuntimeError(f"lwfb_emul_run failed ({rc})")
     return out, status, counters

@@ -170,7 +170,8 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
                              const double* forcing, int64_t M, const int32_t* site_of_member, const double* scal,
                              const double* lay, const double* u0, double reltol, double abstol, double dt_init,
                              double dtmax, int64_t maxiters, int n_threads, double* out_daily, int32_t* status,
-                             int64_t* counters, const int32_t* perm, int seg_len, int resort) {
+                             int64_t* counters, const int32_t* perm, int seg_len, int resort,
+                             int64_t perm_len /* slots described by perm (may exceed M: empty slots = -1); 0: M */) {
   (void)n_sites;
   const int L = LWFB_STATE_LEN(N, iso);
   if (kernel == 0 && (N < 3 || N > 32)) return -1;
@@ -197,7 +198,7 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   const bool quanta = kernel == 0 && seg_len > 0;
   d.ck = quanta ? ck.data() : nullptr;
   d.iter_budget = quanta ? seg_len : 0;
-  d.n_slots = 0;
+  d.n_slots = (perm && perm_len > 0) ? perm_len : 0;
   d.resume = 0;
   static int never_stop[2] = {0, 0};                 // the stop flag is raised by the __global__ wrapper only (GPU tests)
   d.stop = never_stop; d.resident = 0; d.cb_wait = 0;

@@ -213,6 +213,8 @@ def test_work_quanta_with_regrouping_are_result_neutral(dav_full, monkeypatch, q
     status and counters must equal the oracle's single pass, for a cold handle and for a warm one (first launch
     cost-sorted)."""
     monkeypatch.setenv("LWFB_QUANTUM", str(quantum))
+    if quantum == 9:
+        monkeypatch.setenv("LWFB_SPREAD", "1")   # thin placement: one warp of members per block, the other slots empty
     ens = en.make_ensemble(dav_full, 200)
     nd = 60
     h = capi.Handle(ens.N, ens.iso, ens.t0_day, nd)

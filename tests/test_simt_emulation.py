@@ -101,6 +101,12 @@ def test_lane_kernel_placement_does_not_change_results(dav_full):
     got, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, 6, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, perm=perm)
     assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
     assert np.array_equal(got, ref, equal_nan=True)
+    # empty slots (placement entry -1): members spread thinly over more warps than they need
+    holes = np.full(3 * e.M, -1, dtype=np.int32)
+    holes[np.sort(np.random.default_rng(4).choice(3 * e.M, e.M, replace=False))] = perm
+    got, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, 6, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, perm=holes)
+    assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
+    assert np.array_equal(got, ref, equal_nan=True)
 
 
 def test_lane_kernel_work_quanta_with_regrouping(dav_full, isobea):
