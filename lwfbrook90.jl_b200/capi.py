@@ -240,7 +240,8 @@ class Handle:
         self._ck(self._L.lwfb_debug_force_legacy(self._h, int(on)))
 
     def set_placement(self, mode: int):
-        """0: members run in the given order; 1 (default): cost-sorted from the previous run of this handle."""
+        """0: one launch, members in the given order; 1 (default): work quanta with regrouping by progress (see
+        lwfb_set_placement in include/lwfb90.h); 2: the same also for ensembles that do not fill the device."""
         self._L.lwfb_set_placement.argtypes = [C.c_void_p, C.c_int32]
         self._ck(self._L.lwfb_set_placement(self._h, int(mode)))
 

@@ -1,13 +1,16 @@
 // lwfb90.cu — kernels and C ABI of liblwfb90 (see include/lwfb90.h).
 //
 // Kernels:
-//   integrate_kernel<NT>   persistent per-member integration: Tsit5 stages + RHS + error norm + PI
-//                          controller + per-step isotope transport + daily callbacks, one member per
-//                          thread, whole record in one launch.
+//   integrate_lanes<NMAX,EQ> (lwfb90_lanes.cuh)  production integrator: one lane per soil layer, 32/N members per warp,
+//                          Tsit5 stages + RHS + error norm + PI controller + per-step isotope transport + daily callbacks;
+//                          launched in work quanta by lwfb_run (checkpoint anywhere, regrouping by progress).
+//   integrate_kernel<NT> (lwfb90_member.cu)  thread-per-member fallback for N < 3 or N > 32, and rhs_kernel (one RHS
+//                          evaluation per member, unit parity tests).
+//   placement_keys / spread_placement  sort keys and thin slot assignment of the regrouping (with cub's radix sort).
 //   aos_to_soa / soa_to_aos layout transposes between the ABI's member-major blocks and the device's
 //                          [field][member] layout.
 //   score_kernel           per-member RMSE / KGE against observations, reading the daily record.
-//   rhs_kernel             one RHS evaluation per member (unit parity tests).
+//   water_partitioning_kernel, soil_state_kernel (lwfb90_post.cuh)  post-processing of the resident daily record.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
