@@ -10,6 +10,8 @@ Member 0 is always the unmodified site definition.
 """
 from __future__ import annotations
 
+import os
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -59,7 +61,21 @@ def uniforms(member_idx: np.ndarray, n_per_member: int, seed: int = 1234) -> np.
 
 # ----------------------------------------------------------------------------- batched setup
 def _bisect_wetf_vec(Kfc, KSAT, l, n):
-    """Vectorised twin of kpt._bisect_wetf (same midpoint sequence)."""
+    """Vectorised twin of kpt._bisect_wetf (same midpoint sequence).  Large batches are split along the member axis
+    and bisected on a thread pool (numpy releases the GIL inside the ufuncs; every operation is elementwise, so the
+    result does not depend on the split)."""
+    M = KSAT.shape[0]
+    nthr = min(os.cpu_count() or 1, 16)
+    if KSAT.ndim < 1 or M < 4096 or nthr < 2:
+        return _bisect_wetf_chunk(Kfc, KSAT, l, n)
+    bounds = np.linspace(0, M, 4 * nthr + 1).astype(int)
+    with ThreadPoolExecutor(nthr) as pool:
+        parts = list(pool.map(lambda k: _bisect_wetf_chunk(Kfc, KSAT[bounds[k]:bounds[k + 1]], l[bounds[k]:bounds[k + 1]],
+                                                           n[bounds[k]:bounds[k + 1]]), range(4 * nthr)))
+    return np.concatenate(parts, axis=0)
+
+
+def _bisect_wetf_chunk(Kfc, KSAT, l, n):
     a = np.zeros_like(KSAT)
     b = np.ones_like(KSAT)
     f = lambda x: -Kfc + FK_MvG(x, KSAT, l, n)
