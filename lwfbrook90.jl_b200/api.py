@@ -344,7 +344,12 @@ def get_daily_soilFluxes(sim: DiscretizedSPAC):
     sol = _sol(sim)
     t_out = np.arange(sol.t.min(), sol.t.max() + 0.5, 1.0)
     recs = np.stack([sol.record_at(float(t)) for t in t_out])
-    names = [n for n in lo.ACCUM_NAMES if n != "cum_d_pslvp"]
+    # column order of the reference's function (test/03-regression-tests.jl:231-273), not the state order
+    names = ["cum_d_prec", "cum_d_rfal", "cum_d_sfal", "cum_d_rint", "cum_d_sint", "cum_d_rthr", "cum_d_sthr", "cum_d_rsno",
+             "cum_d_rnet", "cum_d_smlt", "cum_d_evap", "cum_d_tran", "cum_d_irvp", "cum_d_isvp", "cum_d_slvp", "cum_d_snvp",
+             "cum_d_pint", "cum_d_ptran", "flow", "seep", "srfl", "slfl", "byfl", "dsfl", "gwfl", "vrfln", "StorageSWAT",
+             "StorageWATER", "BALERD_SWAT", "BALERD_total"]
+    assert sorted(names) == sorted(n for n in lo.ACCUM_NAMES if n != "cum_d_pslvp")
     out = {"time": [sol.reference_date + _dt.timedelta(days=float(t)) for t in t_out]}
     for n in names:
         out[n] = recs[:, sol.ix.acc(n)]

@@ -3,7 +3,7 @@ unit-test known answers (test/01-unit-tests.jl)."""
 import numpy as np
 import pytest
 
-from conftest import inputs
+from conftest import inputs, outputs
 
 from lwfbrook90.jl_b200 import ensemble as en, layout as lo
 from lwfbrook90.jl_b200.discretize import Rootden_beta_
@@ -164,3 +164,38 @@ def test_shard_range():
             assert r[0][0] == 0 and r[-1][1] == M and all(r[k][1] == r[k + 1][0] for k in range(W - 1))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_golden_csv_writers_match_reference_layout(lw, tmp_path):
+    """the tables of the reference's regression tests (test/03-regression-tests.jl:35-62, :231-273)
+    written in the goldens' CSV layout.  The solution comes from the CPU oracle here (the same ODESolution object that
+    simulate_ builds from the GPU record): headers must equal the reference's golden files column for column, values
+    agree at the oracle's pinned tolerances, and a write -> read round trip is exact."""
+    import oracle as orc
+    from lwfbrook90.jl_b200 import api, golden_io as gio
+    sim = lw.setup(lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True), requested_tspan=(0, 300))
+    orc.use("libm")
+    out, st, cnt, _ = orc.run_member(sim.N, sim.iso, sim.t0_day, sim.n_days, sim.forcing, sim.scal, sim.lay, sim.u0)
+    sim.solution = api.ODESolution(sim, sim.t0_day + np.arange(sim.n_days + 1, dtype=float), out, st, cnt)
+    paths = gio.write_regression_goldens(sim, str(tmp_path), "DAV2020-full")
+    for mine, ref, tol in ((paths[0], "DAV2020-full_u_sol_referenceu_mm.csv", 1e-12), (paths[1], "DAV2020-full_u_sol_referenceu_δ.csv", 1e-6),
+                           (paths[2], "DAV2020-full_u_sol_referenceu_belowground.csv", 1e-6)):
+        a, b = gio.read_table(mine), gio.read_table(outputs(ref))
+        assert list(a) == list(b), f"columns of {ref}"
+        for k in b:
+            assert np.array_equal(np.isnan(a[k]), np.isnan(b[k])), k
+            scale = np.maximum(1.0, np.abs(b[k]))
+            assert np.nanmax(np.abs(a[k] - b[k]) / scale, initial=0.0) < tol, k
+    # flux table: header of the reference's flux goldens, ISO time stamps, exact round trip
+    flux = gio.read_table(paths[3])
+    ref_hdr = list(gio.read_table(outputs("INFEXP1_fluxes_referencedf.csv")))
+    assert list(flux) == ref_hdr and len(flux["time"]) == 301
+    assert flux["time"][0] == sim.parametrizedSPAC.reference_date and (flux["time"][1] - flux["time"][0]).days == 1
+    direct = api.get_daily_soilFluxes(sim)
+    assert all(np.array_equal(flux[k], np.asarray(direct[k], float), equal_nan=True) for k in ref_hdr[1:])
+    # number formatting: shortest round-trip repr, NaN, signed zero, infinities
+    t = {"time": np.array([0.0, 30.0, 60.0, 90.0]), "x": np.array([0.1, np.nan, -0.0, 1e-310]), "y": np.array([np.inf, -np.inf, 1 / 3, 5e22])}
+    gio.write_table(str(tmp_path / "t.csv"), t)
+    back = gio.read_table(str(tmp_path / "t.csv"))
+    assert all(np.array_equal(back[k], t[k], equal_nan=True) for k in t) and np.signbit(back["x"][2])
+    assert open(tmp_path / "t.csv").read().splitlines()[2] == "30.0,NaN,-Inf"
