@@ -71,6 +71,11 @@ def test_lane_kernel_saturation_bypass_groundwater(lw):
     W = ref[:, :, ix.SWATI_mm] / e.lay[:, None, lo.L.SWATMAX, :]
     assert (W >= 1.0).any(), "the window must contain saturated layers"
     assert (cnt[:, 1] > 20).all(), "the window must contain rejected steps"
+    # the same window in work quanta of 11 passes with regrouping: checkpoints fall between rejected steps and their
+    # retries, inside the infiltration pulse, with groundwater feedback (GWAT partial sums) and 21 lanes per member
+    got, st, cnt_q = emul.run(emul.LANES, e.N, e.iso, e.t0_day, e.n_days, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
+                              seg_len=11, resort=True)
+    assert (st == 0).all() and np.array_equal(cnt_q, cnt) and np.array_equal(got, ref, equal_nan=True)
 
 
 @pytest.mark.parametrize("N", [3, 4, 8, 16, 32])
