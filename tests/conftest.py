@@ -69,3 +69,11 @@ def read_table(path):
         except ValueError:
             return np.nan
     return hdr, np.array([[num(x) for x in r] for r in rows[1:]])
+
+
+def aligned_grid(N):
+    """N layer thicknesses (m) for DAV2020-full whose boundaries fall on the horizon interfaces (0.03 m, 0.40 m), so that
+    the discretisation keeps exactly N layers (a grid that cuts through a horizon gets extra layers at the interfaces)."""
+    a = max(1, round((N - 1) * 0.35))
+    b = N - 1 - a
+    return [0.03] + [0.37 / a] * a + [0.7 / b] * b

@@ -12,7 +12,7 @@ Two comparisons:
 import numpy as np
 import pytest
 
-from conftest import inputs, outputs, read_table
+from conftest import aligned_grid, inputs, outputs, read_table
 
 import oracle as orc
 from lwfbrook90.jl_b200 import api, capi, ensemble as en, layout as lo
@@ -177,12 +177,11 @@ def test_thread_per_member_kernel_agrees_with_lane_per_layer_kernel(dav_full, be
 @pytest.mark.parametrize("N", [3, 4, 6, 8, 9, 16, 22, 32])
 def test_lane_kernel_all_group_sizes(lw, N):
     """Every lanes-per-member geometry (32/N members per warp, idle lanes, 1..3 extra components per lane)."""
-    m = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=[1.1 / N] * N,
+    m = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=aligned_grid(N),
                     root_distribution=dict(beta=0.97, z_rootMax_m=None),
                     IC_soil=dict(PSIM_init_kPa=-6.0, delta18O_init_permil=-12.0, delta2H_init_permil=-90.0))
     s = lw.setup(m, ε=0.001 if N > 16 else 0.01, requested_tspan=(100, 130))
-    if s.N > 32:
-        pytest.skip("refinement pushed N above 32")
+    assert s.N == N
     e = en.make_ensemble(s, 11)
     h, sub, nd = gpu_run(e)
     assert_bit_identical(h, sub, nd)

@@ -12,7 +12,7 @@ import sys
 import numpy as np
 import pytest
 
-from conftest import inputs
+from conftest import aligned_grid, inputs
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
 import emul  # noqa: E402
@@ -81,13 +81,17 @@ def test_lane_kernel_saturation_bypass_groundwater(lw):
 @pytest.mark.parametrize("N", [3, 4, 8, 16, 32])
 def test_lane_kernel_group_geometries(lw, N):
     """32/N members per warp, 1..3 accumulator slots per lane, N = 32 fills the warp."""
-    m = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=[1.1 / N] * N,
+    m = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=aligned_grid(N),
                     root_distribution=dict(beta=0.97, z_rootMax_m=None),
                     IC_soil=dict(PSIM_init_kPa=-6.0, delta18O_init_permil=-12.0, delta2H_init_permil=-90.0))
     s = lw.setup(m, ε=0.001 if N > 16 else 0.01, requested_tspan=(100, 104))
-    if s.N > 32:
-        pytest.skip("refinement pushed N above 32")
-    check(en.make_ensemble(s, 5), 4, emul.LANES)
+    assert s.N == N
+    e = en.make_ensemble(s, 5)
+    ref, cnt = check(e, 4, emul.LANES)
+    # and in work quanta (the checkpoint holds 1..3 accumulator derivatives per lane, depending on the geometry)
+    got, st, cnt_q = emul.run(emul.LANES, e.N, e.iso, e.t0_day, 4, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
+                              seg_len=7, resort=True)
+    assert (st == 0).all() and np.array_equal(cnt_q, cnt) and np.array_equal(got, ref, equal_nan=True)
 
 
 def test_member_kernel_generic_layer_count(lw, dav_full):
