@@ -82,6 +82,16 @@ __global__ void spread_placement(const int32_t* __restrict__ sorted, int64_t n, 
   if (j < n) out[(j / per_block) * slots_per_block + (j % per_block)] = sorted[j];
 }
 
+// thin FRONT blocks of a full device (experimental, LWFB_THIN_FRONT): the first n_front blocks get per_front members
+// each (the rest of their slots stays empty), the other members are packed behind them
+__global__ void spread_front(const int32_t* __restrict__ sorted, int64_t n, int64_t n_front, int per_front,
+                             int slots_per_block, int32_t* __restrict__ out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int64_t thin = n_front * per_front;
+  out[j < thin ? (j / per_front) * slots_per_block + (j % per_front) : n_front * slots_per_block + (j - thin)] = sorted[j];
+}
+
 // per-member goodness of fit against observed theta / delta18O (RMSE, KGE)
 __global__ void score_kernel(DevData d, int n_obs_days, const int32_t* __restrict__ obs_day, int n_obs_layers,
                              const int32_t* __restrict__ obs_layer, const double* __restrict__ obs_theta,
@@ -197,7 +207,8 @@ struct lwfb_handle {
   void* d_sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   int* d_nleft = nullptr;
-  int32_t* d_perm_thin = nullptr;   // placement with empty slots (spread_placement), [resident blocks x slots per block]
+  int32_t* d_perm_thin = nullptr;   // placement with empty slots (spread_placement / spread_front)
+  size_t perm_thin_len = 0;
   bool perm_valid = false;     // d_perm holds a permutation for the current member count
   bool cost_valid = false;     // d_counters holds the RHS-evaluation counts of a completed lane-kernel run
   std::string err;
@@ -248,7 +259,7 @@ static void free_members(lwfb_handle* h) {
   cudaFree(h->d_scal); cudaFree(h->d_lay); cudaFree(h->d_u0); cudaFree(h->d_rec); cudaFree(h->d_fin);
   cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm); cudaFree(h->d_ck); cudaFree(h->d_stop);
   cudaFree(h->d_key); cudaFree(h->d_key2); cudaFree(h->d_idx); cudaFree(h->d_sort_tmp); cudaFree(h->d_nleft);
-  cudaFree(h->d_perm_thin); h->d_perm_thin = nullptr;
+  cudaFree(h->d_perm_thin); h->d_perm_thin = nullptr; h->perm_thin_len = 0;
   h->d_key = h->d_key2 = nullptr; h->d_idx = nullptr; h->d_sort_tmp = nullptr; h->d_nleft = nullptr; h->sort_tmp_bytes = 0;
   h->d_perm = nullptr; h->d_ck = nullptr; h->d_stop = nullptr; h->perm_valid = false; h->cost_valid = false;
   h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
@@ -496,6 +507,8 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   if (const char* e = getenv("LWFB_MIN_WAVES")) min_waves = atoi(e);
   bool spread = true;                                 // a device that is not full gets its members spread thinly over all slots
   if (const char* e = getenv("LWFB_SPREAD")) spread = atoi(e) != 0;
+  int thin_front = 0;                                 // experimental: warps with members per FRONT block of a full device (0: all)
+  if (const char* e = getenv("LWFB_THIN_FRONT")) thin_front = atoi(e);
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->o.device);
   const int64_t R = (int64_t)n_sm * LWFB_LANES_MINBLOCKS;                       // resident blocks
@@ -539,7 +552,11 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
       const int64_t w = (n_left + R * mpw - 1) / (R * mpw);
       if (spread && h->perm_valid && w < wpb) {
         const int64_t per_block = w * mpw, nbt = (n_left + per_block - 1) / per_block;
-        if (!h->d_perm_thin) CK(cudaMalloc(&h->d_perm_thin, (size_t)(R * mpb) * sizeof(int32_t)));
+        if (h->perm_thin_len < (size_t)(R * mpb)) {
+          cudaFree(h->d_perm_thin); h->d_perm_thin = nullptr; h->perm_thin_len = 0;
+          CK(cudaMalloc(&h->d_perm_thin, (size_t)(R * mpb) * sizeof(int32_t)));
+          h->perm_thin_len = (size_t)(R * mpb);
+        }
         CK(cudaMemsetAsync(h->d_perm_thin, 0xff, (size_t)(nbt * mpb) * sizeof(int32_t), st));
         spread_placement<<<(unsigned)((n_left + 255) / 256), 256, 0, st>>>(h->d_perm, n_left, (int)per_block, (int)mpb, h->d_perm_thin);
         CK(cudaGetLastError());
@@ -560,6 +577,21 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
       d.iter_budget = quantum;
       d.prio_blocks = K;
       d.prio_budget = stop_flag ? (1LL << 60) : quantum * ((nb - K + (R - K) - 1) / (R - K));
+      if (thin_front > 0 && thin_front < wpb && h->perm_valid && K > 0 && n_left > K * thin_front * mpw) {
+        // the front blocks carry thin_front warps of members each: their passes run at the latency of few warps
+        const int64_t per_front = thin_front * mpw;
+        const size_t need = (size_t)(K * mpb + n_left);
+        if (h->perm_thin_len < need) {
+          cudaFree(h->d_perm_thin); h->d_perm_thin = nullptr; h->perm_thin_len = 0;
+          CK(cudaMalloc(&h->d_perm_thin, (size_t)(R * mpb + h->M) * sizeof(int32_t)));
+          h->perm_thin_len = (size_t)(R * mpb + h->M);
+        }
+        CK(cudaMemsetAsync(h->d_perm_thin, 0xff, (size_t)(K * mpb) * sizeof(int32_t), st));
+        spread_front<<<(unsigned)((n_left + 255) / 256), 256, 0, st>>>(h->d_perm, n_left, K, (int)per_front, (int)mpb, h->d_perm_thin);
+        CK(cudaGetLastError());
+        d.perm = h->d_perm_thin;
+        d.n_slots = K * mpb + (n_left - K * per_front);
+      }
     }
     if (stop_flag) {
       // the launch ends when the first slot runs out of work (see DevData::stop)
