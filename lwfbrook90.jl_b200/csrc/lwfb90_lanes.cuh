@@ -72,9 +72,15 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
 // lines at the same time: fetch stalls drop to 0.2-0.6 cycles per instruction and IPC doubles.  The price is that a
 // block waits for its slowest member at every step (a few % more executed instructions).  Results do not depend on
 // the grouping: a member that waits does not change state.  -DLWFB_LANES_FREE_RUNNING restores warp-level votes.
-#if !defined(LWFB_LANES_FREE_RUNNING) && defined(__CUDACC__)
+#if !defined(LWFB_LANES_FREE_RUNNING) && (defined(__CUDACC__) || defined(LWFB_SIMT_EMUL))
 #define LWFB_VOTE_ANY(p) (__syncthreads_or((p) ? 1 : 0) != 0)
+#ifdef LWFB_SIMT_EMUL
+// the stage barrier is reached from two places (stage loop / warps that idle through a pass): the hardware matches
+// barriers by number, the emulator by this id
+#define LWFB_STAGE_SYNC() ((void)simt::block_or(false, 1000000))
+#else
 #define LWFB_STAGE_SYNC() __syncthreads()
+#endif
 #else
 #define LWFB_VOTE_ANY(p) __any_sync(LFULL, (p))
 #define LWFB_STAGE_SYNC() ((void)0)
@@ -102,7 +108,7 @@ enum {
 };
 #define LC(k) (*(const volatile double*)(cst + (k) * LWFB_LANES_BLOCK))
 #ifdef LWFB_SIMT_EMUL
-#define LWFB_BLOCK_OF_WARP(w) (w)                    // the emulator runs every warp as its own block
+#define LWFB_BLOCK_OF_WARP(w) ((w) / simt::warps_per_block())   // the emulator's block size is a run-time choice
 #else
 #define LWFB_BLOCK_OF_WARP(w) ((w) / (LWFB_LANES_BLOCK / 32))
 #endif

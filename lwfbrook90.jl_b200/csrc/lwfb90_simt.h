@@ -27,6 +27,8 @@ namespace simt {
 uint64_t exchange(uint64_t v, int src_lane, int op_id);     // value of src_lane (own value if out of range)
 unsigned vote(bool p, int op_id);                           // ballot over the warp
 int lane_id();
+bool block_or(bool p, int op_id);                           // __syncthreads_or over the emulated thread block
+int warps_per_block();                                      // warps the emulator runs as one thread block
 }  // namespace simt
 
 template <typename T> static inline T __ldg(const T* p) { return *p; }
@@ -51,6 +53,8 @@ template <typename T> static inline T simt_shfl(T v, int src, int op) { return s
 #define __any_sync(mask, p) (simt::vote((p), LWFB_OP_ID) != 0u)
 #define __all_sync(mask, p) (simt::vote((p), LWFB_OP_ID) == 0xffffffffu)
 #define __syncwarp(mask) ((void)simt::vote(true, LWFB_OP_ID))
+#define __syncthreads_or(p) (simt::block_or((p) != 0, LWFB_OP_ID) ? 1 : 0)
+#define __syncthreads() ((void)simt::block_or(false, LWFB_OP_ID))
 // redux.sync min over the lanes named in `mask` (every lane passes the mask of its own group)
 static inline unsigned simt_reduce_min(unsigned mask, unsigned v, int op) {
   unsigned r = 0xffffffffu;

@@ -43,7 +43,7 @@ def lib():
         _lib.lwfb_emul_run.restype = C.c_int
         _lib.lwfb_emul_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int64, _ip,
                                        _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int,
-                                       _dp, _ip, _lp, _ip, C.c_int, C.c_int, C.c_int64]
+                                       _dp, _ip, _lp, _ip, C.c_int, C.c_int, C.c_int64, C.c_int]
     return _lib
 
 
@@ -52,10 +52,12 @@ def _p(a, t=_dp):
 
 
 def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, *, reltol=1e-5, abstol=1e-6,
-        dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000, n_threads=8, perm=None, seg_len=0, resort=False):
+        dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000, n_threads=8, perm=None, seg_len=0, resort=False,
+        warps_per_block=1):
     """Same shapes and return values as oracle.run.  perm: optional placement (slot -> member) of the lane kernel;
     seg_len > 0: work-quantum execution (a launch ends after seg_len passes of the warp loop), resort: regroup the
-    unfinished members by progress between the launches."""
+    unfinished members by progress between the launches.  warps_per_block: size of the emulated thread block (the
+    block-uniform votes and stage barriers of the kernel span it; 8 = what the GPU runs)."""
     forcing = np.ascontiguousarray(forcing, dtype=np.float64)
     if forcing.ndim == 2:
         forcing = forcing[None]
@@ -74,7 +76,8 @@ def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, 
                              _p(scal), _p(lay), _p(u0), reltol, abstol, dt_init, dtmax, maxiters, int(n_threads), _p(out),
                              _p(status, _ip), _p(counters, _lp),
                              None if perm is None else _p(np.ascontiguousarray(perm, dtype=np.int32), _ip),
-                             int(seg_len), int(bool(resort)), 0 if perm is None else int(len(perm)))
+                             int(seg_len), int(bool(resort)), 0 if perm is None else int(len(perm)),
+                             int(warps_per_block))
     if rc != 0:
         raise RuntimeError(f"lwfb_emul_run failed ({rc})")
     return out, status, counters

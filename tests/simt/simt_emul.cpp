@@ -1,10 +1,12 @@
 // simt_emul.cpp — lock-step warp emulator for the liblwfb90 kernels.  TEST INFRASTRUCTURE ONLY.
 //
 // Compiles the kernel headers of lwfbrook90.jl_b200/csrc with a host compiler (-DLWFB_SIMT_EMUL, see
-// csrc/lwfb90_simt.h) and runs them with the semantics the hardware gives warp-synchronous code: the
-// 32 lanes of a warp are coroutines (ucontext) that advance round-robin from one warp primitive to the
-// next; a primitive returns when all lanes have reached it.  Every primitive carries its source line;
-// lanes meeting at different lines abort the run (that would be undefined behaviour on the GPU).
+// csrc/lwfb90_simt.h) and runs them with the semantics the hardware gives warp-synchronous, block-synchronous code:
+// the threads of a thread block (1..8 warps of 32 lanes) are coroutines (ucontext) on one host thread that advance
+// round-robin from one primitive to the next; a warp primitive returns when all lanes of the warp have reached it, a
+// block barrier (__syncthreads, __syncthreads_or) when all threads of the block have.  Every primitive carries its
+// source line; lanes meeting at different lines, a thread leaving before a barrier, or warps making different numbers
+// of barrier calls abort the run (undefined behaviour or a hang on the GPU).
 //
 // Purpose: the container that builds this repository has no GPU.  The emulator lets the non-GPU test
 // suite check the kernels' arithmetic, shuffle choreography and control flow bit-for-bit against the
@@ -27,25 +29,45 @@
 
 namespace {
 constexpr int WARP = 32;
+constexpr int MAX_WARPS = LWFB_LANES_BLOCK / 32;     // warps of an emulated thread block (run-time choice 1..MAX_WARPS)
+constexpr int MAX_LANES = WARP * MAX_WARPS;
 constexpr size_t STACK_BYTES = 1u << 20;
 
-struct Warp {
-  ucontext_t main_ctx, ctx[WARP];
+// One emulated thread block: n_lanes = 32 * warps coroutines on one host thread.  A lane runs until it reaches a
+// primitive, deposits its operand and hands control on: at a WARP primitive to the next live lane of its warp, at a
+// BLOCK primitive (__syncthreads, __syncthreads_or) to the next live lane of the block.  When control comes back, every
+// lane of the scope must have deposited at the same source line - anything else is divergence (undefined behaviour or
+// a hang on the GPU) and aborts the run.
+struct Block {
+  ucontext_t main_ctx, ctx[MAX_LANES];
   char* stacks = nullptr;
-  bool done[WARP];
-  uint64_t slot[2][WARP];
-  int opid[2][WARP];
-  unsigned long counter[WARP];
+  int n_lanes = WARP;
+  bool done[MAX_LANES];
+  uint64_t slot[2][MAX_LANES];          // warp primitives, double-buffered by the parity of the lane's primitive count
+  int opid[2][MAX_LANES];
+  unsigned long counter[MAX_LANES];
+  uint64_t bslot[2][MAX_LANES];         // block primitives
+  int bopid[2][MAX_LANES];
+  unsigned long bcounter[MAX_LANES];
   int cur = 0;
   void (*body)(void* arg, int lane) = nullptr;
   void* arg = nullptr;
   long n_ops = 0;
 };
-thread_local Warp* W = nullptr;
+thread_local Block* W = nullptr;
+thread_local int g_warps_per_block = 1;
 
-int next_alive(int l) {
+int next_alive_in_warp(int l) {
+  const int base = l & ~(WARP - 1);
   for (int s = 1; s <= WARP; s++) {
-    int n = (l + s) % WARP;
+    int n = base + ((l - base + s) % WARP);
+    if (!W->done[n]) return n;
+  }
+  return -1;
+}
+int next_alive_in_block(int l) {
+  for (int s = 1; s <= W->n_lanes; s++) {
+    int n = (l + s) % W->n_lanes;
     if (!W->done[n]) return n;
   }
   return -1;
@@ -54,27 +76,29 @@ int next_alive(int l) {
 void trampoline(int lane) {
   W->body(W->arg, lane);
   W->done[lane] = true;
-  int n = next_alive(lane);
+  int n = next_alive_in_warp(lane);
+  if (n < 0) n = next_alive_in_block(lane);
   if (n < 0) setcontext(&W->main_ctx);
   W->cur = n;
   setcontext(&W->ctx[n]);
 }
 
-// deposit a value, let every other lane run up to the same primitive, return the parity of the slot
+// warp scope: deposit a value, let every other lane of the warp run up to the same primitive, return the slot parity
 int rendezvous(uint64_t v, int op_id) {
   const int l = W->cur;
+  const int base = l & ~(WARP - 1);
   const unsigned long my_op = W->counter[l]++;
   const int par = (int)(my_op & 1ul);
   W->slot[par][l] = v;
   W->opid[par][l] = op_id;
-  const int n = next_alive(l);
+  const int n = next_alive_in_warp(l);
   if (n >= 0 && n != l) {
     W->cur = n;
     swapcontext(&W->ctx[l], &W->ctx[n]);
   }
-  for (int i = 0; i < WARP; i++) {
+  for (int i = base; i < base + WARP; i++) {
     if (W->done[i] && W->counter[i] <= my_op) { fprintf(stderr, "simt_emul: lane %d exited before the warp primitive at line %d\n", i, op_id); abort(); }
-    if (W->opid[par][i] != op_id) {
+    if (W->opid[par][i] != op_id || W->counter[i] <= my_op) {
       fprintf(stderr, "simt_emul: divergent warp primitive: lane %d at line %d, lane %d at line %d\n", l, op_id, i, W->opid[par][i]);
       abort();
     }
@@ -83,23 +107,49 @@ int rendezvous(uint64_t v, int op_id) {
   return par;
 }
 
-void run_warp(void (*body)(void*, int), void* arg) {
-  Warp w;
-  w.stacks = (char*)malloc(STACK_BYTES * WARP);
-  w.body = body; w.arg = arg;
-  W = &w;
-  for (int l = 0; l < WARP; l++) {
-    w.done[l] = false; w.counter[l] = 0;
-    w.opid[0][l] = w.opid[1][l] = -1;
-    getcontext(&w.ctx[l]);
-    w.ctx[l].uc_stack.ss_sp = w.stacks + (size_t)l * STACK_BYTES;
-    w.ctx[l].uc_stack.ss_size = STACK_BYTES;
-    w.ctx[l].uc_link = nullptr;
-    makecontext(&w.ctx[l], (void (*)())trampoline, 1, l);
+// block scope
+int block_rendezvous(uint64_t v, int op_id) {
+  const int l = W->cur;
+  const unsigned long my_op = W->bcounter[l]++;
+  const int par = (int)(my_op & 1ul);
+  W->bslot[par][l] = v;
+  W->bopid[par][l] = op_id;
+  const int n = next_alive_in_block(l);
+  if (n >= 0 && n != l) {
+    W->cur = n;
+    swapcontext(&W->ctx[l], &W->ctx[n]);
   }
-  w.cur = 0;
-  swapcontext(&w.main_ctx, &w.ctx[0]);
-  free(w.stacks);
+  for (int i = 0; i < W->n_lanes; i++) {
+    if (W->done[i] && W->bcounter[i] <= my_op) { fprintf(stderr, "simt_emul: lane %d exited before the block barrier at line %d\n", i, op_id); abort(); }
+    if (W->bopid[par][i] != op_id || W->bcounter[i] <= my_op) {
+      fprintf(stderr, "simt_emul: block barrier mismatch: lane %d at line %d, lane %d at line %d\n", l, op_id, i, W->bopid[par][i]);
+      abort();
+    }
+  }
+  return par;
+}
+
+void run_block(void (*body)(void*, int), void* arg, int warps) {
+  Block* w = new Block;
+  w->n_lanes = WARP * warps;
+  w->stacks = (char*)malloc(STACK_BYTES * (size_t)w->n_lanes);
+  w->body = body; w->arg = arg;
+  W = w;
+  g_warps_per_block = warps;
+  for (int l = 0; l < w->n_lanes; l++) {
+    w->done[l] = false; w->counter[l] = 0; w->bcounter[l] = 0;
+    w->opid[0][l] = w->opid[1][l] = -1;
+    w->bopid[0][l] = w->bopid[1][l] = -1;
+    getcontext(&w->ctx[l]);
+    w->ctx[l].uc_stack.ss_sp = w->stacks + (size_t)l * STACK_BYTES;
+    w->ctx[l].uc_stack.ss_size = STACK_BYTES;
+    w->ctx[l].uc_link = nullptr;
+    makecontext(&w->ctx[l], (void (*)())trampoline, 1, l);
+  }
+  w->cur = 0;
+  swapcontext(&w->main_ctx, &w->ctx[0]);
+  free(w->stacks);
+  delete w;
   W = nullptr;
 }
 }  // namespace
@@ -107,16 +157,25 @@ void run_warp(void (*body)(void*, int), void* arg) {
 namespace simt {
 uint64_t exchange(uint64_t v, int src_lane, int op_id) {
   const int l = W->cur;
+  const int base = l & ~(WARP - 1);
   const int par = rendezvous(v, op_id);
-  return (src_lane >= 0 && src_lane < WARP) ? W->slot[par][src_lane] : W->slot[par][l];
+  return (src_lane >= 0 && src_lane < WARP) ? W->slot[par][base + src_lane] : W->slot[par][l];
 }
 unsigned vote(bool p, int op_id) {
+  const int base = W->cur & ~(WARP - 1);
   const int par = rendezvous(p ? 1u : 0u, op_id);
   unsigned m = 0;
-  for (int i = 0; i < WARP; i++) m |= (W->slot[par][i] ? 1u : 0u) << i;
+  for (int i = 0; i < WARP; i++) m |= (W->slot[par][base + i] ? 1u : 0u) << i;
   return m;
 }
-int lane_id() { return W->cur; }
+bool block_or(bool p, int op_id) {
+  const int par = block_rendezvous(p ? 1u : 0u, op_id);
+  bool any = false;
+  for (int i = 0; i < W->n_lanes; i++) any = any || W->bslot[par][i] != 0;
+  return any;
+}
+int lane_id() { return W->cur & (WARP - 1); }
+int warps_per_block() { return g_warps_per_block; }
 }  // namespace simt
 
 // ----------------------------------------------------------------------------------------------
@@ -127,20 +186,23 @@ struct Job {
   lwfb::DevData d;
   int kernel;                 // 0 lanes, 1 thread-per-member
   std::atomic<int64_t> next{0};
-  int64_t n_units = 0;        // warps (lanes kernel) or members
+  int64_t n_units = 0;        // thread blocks (lanes kernel) or members
+  int warps = 1;              // warps per emulated thread block (lanes kernel)
   std::atomic<long> ops{0};
 };
 
-struct WarpArg { const lwfb::DevData* d; int64_t warp_g; double* cst; };
+struct WarpArg { const lwfb::DevData* d; int64_t block; int warps; double* cst; };
 
-void lanes_entry(void* a, int lane) {
+void lanes_entry(void* a, int tid) {             // tid = thread index within the emulated block
   const WarpArg* wa = (const WarpArg*)a;
   const lwfb::DevData& d = *wa->d;
-  double* cst = wa->cst + lane;                  // this lane's column of the "shared memory" constant block
-  if (d.N == 3) lwfb::lanes_body<8, 3>(d, lane, wa->warp_g, cst, lwfb_log_tab_h);
-  else if (d.N < 8) lwfb::lanes_body<8, 2>(d, lane, wa->warp_g, cst, lwfb_log_tab_h);
-  else if (d.N == 8) lwfb::lanes_body<8, 1>(d, lane, wa->warp_g, cst, lwfb_log_tab_h);
-  else lwfb::lanes_body<32, 1>(d, lane, wa->warp_g, cst, lwfb_log_tab_h);
+  double* cst = wa->cst + tid;                   // this thread's column of the "shared memory" constant block
+  const int lane = tid & 31;
+  const int64_t warp_g = wa->block * wa->warps + (tid >> 5);
+  if (d.N == 3) lwfb::lanes_body<8, 3>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  else if (d.N < 8) lwfb::lanes_body<8, 2>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  else if (d.N == 8) lwfb::lanes_body<8, 1>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  else lwfb::lanes_body<32, 1>(d, lane, warp_g, cst, lwfb_log_tab_h);
 }
 
 void* worker(void* p) {
@@ -150,8 +212,8 @@ void* worker(void* p) {
     if (u >= j->n_units) break;
     if (j->kernel == 0) {
       std::vector<double> cst((size_t)lwfb::KC_COUNT * LWFB_LANES_BLOCK);
-      WarpArg wa{&j->d, u, cst.data()};
-      run_warp(lanes_entry, &wa);
+      WarpArg wa{&j->d, u, j->warps, cst.data()};
+      run_block(lanes_entry, &wa, j->warps);
     } else {
       lwfb::integrate_member<0>(j->d, u);
     }
@@ -171,7 +233,8 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
                              const double* lay, const double* u0, double reltol, double abstol, double dt_init,
                              double dtmax, int64_t maxiters, int n_threads, double* out_daily, int32_t* status,
                              int64_t* counters, const int32_t* perm, int seg_len, int resort,
-                             int64_t perm_len /* slots described by perm (may exceed M: empty slots = -1); 0: M */) {
+                             int64_t perm_len /* slots described by perm (may exceed M: empty slots = -1); 0: M */,
+                             int warps_per_block /* 1 .. LWFB_LANES_BLOCK / 32 */) {
   (void)n_sites;
   const int L = LWFB_STATE_LEN(N, iso);
   if (kernel == 0 && (N < 3 || N > 32)) return -1;
@@ -188,7 +251,9 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   d.rec = rec.data(); d.fin = fin.data(); d.status = status; d.counters = cnt.data();
   d.reltol = reltol; d.abstol = abstol; d.dt_init = dt_init; d.dtmax = dtmax; d.maxiters = maxiters;
   job.kernel = kernel;
-  if (kernel == 0) { const int mpw = 32 / N; job.n_units = (M + mpw - 1) / mpw; }
+  if (warps_per_block < 1 || warps_per_block > MAX_WARPS) return 4;
+  job.warps = warps_per_block;
+  if (kernel == 0) { const int mpw = 32 / N; job.n_units = ((M + mpw - 1) / mpw + job.warps - 1) / job.warps; }
   else job.n_units = M;
   if (n_threads < 1) n_threads = 1;
   // work-quantum execution as in lwfb_run: a launch ends after `seg_len` passes of the block loop (here: of the warp
@@ -202,13 +267,13 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   d.resume = 0;
   static int never_stop[2] = {0, 0};                 // the stop flag is raised by the __global__ wrapper only (GPU tests)
   d.stop = never_stop; d.resident = 0; d.cb_wait = 0;
-  d.prio_blocks = quanta && resort ? 1 : 0;          // the first warp runs three times as long as the others
+  d.prio_blocks = quanta && resort ? 1 : 0;          // the first block runs three times as long as the others
   d.prio_budget = 3 * (long long)seg_len;
   const double tend = (double)(t0_day + n_days);
   for (int launch = 0;; launch++) {
     if (launch > 100000) return 3;
     job.next = 0;
-    if (kernel == 0) { const int mpw = 32 / N; const int64_t ns = d.n_slots > 0 ? d.n_slots : M; job.n_units = (ns + mpw - 1) / mpw; }
+    if (kernel == 0) { const int mpw = 32 / N; const int64_t ns = d.n_slots > 0 ? d.n_slots : M; job.n_units = ((ns + mpw - 1) / mpw + job.warps - 1) / job.warps; }
     std::vector<pthread_t> th(n_threads);
     for (int i = 0; i < n_threads; i++) pthread_create(&th[i], nullptr, worker, &job);
     for (int i = 0; i < n_threads; i++) pthread_join(th[i], nullptr);

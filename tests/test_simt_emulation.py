@@ -1,8 +1,8 @@
 """Kernel text under the lock-step warp emulator (tests/simt) against the CPU oracle, bit for bit.
 
 These tests need no GPU: the CUDA kernel headers of lwfbrook90.jl_b200/csrc are compiled for the host with
--DLWFB_SIMT_EMUL and executed with SIMT semantics (32 lanes as coroutines that meet at every warp
-primitive; lanes meeting at different primitives abort).  They check the arithmetic, the shuffle
+-DLWFB_SIMT_EMUL and executed with SIMT semantics (the threads of a block as coroutines that meet at every warp
+primitive and block barrier; threads meeting at different primitives abort).  They check the arithmetic, the shuffle
 choreography and the control flow of the kernels — what the GPU parity tests (-m gpu) check on the
 device — on the machine that builds the repository.  The emulator is test infrastructure only.
 """
@@ -151,6 +151,22 @@ def test_lane_kernel_aborting_members(dav_full):
         assert np.array_equal(got, ref, equal_nan=True)
     got, st, cnt = emul.run(emul.MEMBER, e.N, e.iso, e.t0_day, 9, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, **kw)
     assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o) and np.array_equal(got, ref, equal_nan=True)
+
+
+def test_lane_kernel_full_thread_blocks(dav_full, bea):
+    """What the GPU runs: thread blocks of 8 warps (and 2, 4) in lock step — block-uniform votes (__syncthreads_or), a
+    barrier per Runge-Kutta stage, warps without a stepping member idling through the barriers of a pass, bounded
+    waiting at the day boundary across the warps of a block, the last block partly empty.  The emulator matches block
+    barriers as the hardware does and aborts on a mismatch (a hang on the GPU).  One launch and work quanta."""
+    for sim, M, nd, wpb, quantum, resort in ((dav_full, 40, 6, 8, 0, False), (dav_full, 70, 5, 8, 19, True),
+                                             (bea, 21, 6, 2, 5, True), (dav_full, 100, 4, 4, 1, True)):
+        e = en.make_ensemble(sim, M)
+        orc.use("elem")
+        ref, st_o, cnt_o = orc.run(e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, n_threads=8)
+        got, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
+                                seg_len=quantum, resort=resort, warps_per_block=wpb)
+        assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
+        assert np.array_equal(got, ref, equal_nan=True)
 
 
 def test_emulator_rejects_divergent_warp_primitives():
