@@ -56,7 +56,8 @@ def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, 
         warps_per_block=1):
     """Same shapes and return values as oracle.run.  perm: optional placement (slot -> member) of the lane kernel;
     seg_len > 0: work-quantum execution (a launch ends after seg_len passes of the warp loop), resort: regroup the
-    unfinished members by progress between the launches.  warps_per_block: size of the emulated thread block (the
+    unfinished members by progress between the launches (resort=2: additionally with the stop flag that ends a launch
+    when the first block has used up its quantum and no block is left to take its place).  warps_per_block: size of the emulated thread block (the
     block-uniform votes and stage barriers of the kernel span it; 8 = what the GPU runs)."""
     forcing = np.ascontiguousarray(forcing, dtype=np.float64)
     if forcing.ndim == 2:
@@ -76,7 +77,7 @@ def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, 
                              _p(scal), _p(lay), _p(u0), reltol, abstol, dt_init, dtmax, maxiters, int(n_threads), _p(out),
                              _p(status, _ip), _p(counters, _lp),
                              None if perm is None else _p(np.ascontiguousarray(perm, dtype=np.int32), _ip),
-                             int(seg_len), int(bool(resort)), 0 if perm is None else int(len(perm)),
+                             int(seg_len), int(resort), 0 if perm is None else int(len(perm)),
                              int(warps_per_block))
     if rc != 0:
         raise RuntimeError(f"lwfb_emul_run failed ({rc})")

@@ -189,20 +189,28 @@ struct Job {
   int64_t n_units = 0;        // thread blocks (lanes kernel) or members
   int warps = 1;              // warps per emulated thread block (lanes kernel)
   std::atomic<long> ops{0};
+  // stop flag of the work-quantum execution, as the __global__ wrapper of integrate_lanes drives it: the first block that
+  // uses up its budget when no block is left to take its slot ends the launch for every block
+  bool use_stop = false;
+  int stop[2] = {0, 0};
+  std::atomic<int64_t> exited{0};
+  int resident = 1;           // blocks "resident" at a time = worker threads
 };
 
-struct WarpArg { const lwfb::DevData* d; int64_t block; int warps; double* cst; };
+struct WarpArg { const lwfb::DevData* d; int64_t block; int warps; double* cst; bool by_budget; };
 
 void lanes_entry(void* a, int tid) {             // tid = thread index within the emulated block
-  const WarpArg* wa = (const WarpArg*)a;
+  WarpArg* wa = (WarpArg*)a;
   const lwfb::DevData& d = *wa->d;
   double* cst = wa->cst + tid;                   // this thread's column of the "shared memory" constant block
   const int lane = tid & 31;
   const int64_t warp_g = wa->block * wa->warps + (tid >> 5);
-  if (d.N == 3) lwfb::lanes_body<8, 3>(d, lane, warp_g, cst, lwfb_log_tab_h);
-  else if (d.N < 8) lwfb::lanes_body<8, 2>(d, lane, warp_g, cst, lwfb_log_tab_h);
-  else if (d.N == 8) lwfb::lanes_body<8, 1>(d, lane, warp_g, cst, lwfb_log_tab_h);
-  else lwfb::lanes_body<32, 1>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  bool b;
+  if (d.N == 3) b = lwfb::lanes_body<8, 3>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  else if (d.N < 8) b = lwfb::lanes_body<8, 2>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  else if (d.N == 8) b = lwfb::lanes_body<8, 1>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  else b = lwfb::lanes_body<32, 1>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  if (tid == 0) wa->by_budget = b;
 }
 
 void* worker(void* p) {
@@ -212,8 +220,12 @@ void* worker(void* p) {
     if (u >= j->n_units) break;
     if (j->kernel == 0) {
       std::vector<double> cst((size_t)lwfb::KC_COUNT * LWFB_LANES_BLOCK);
-      WarpArg wa{&j->d, u, j->warps, cst.data()};
+      WarpArg wa{&j->d, u, j->warps, cst.data(), false};
       run_block(lanes_entry, &wa, j->warps);
+      if (j->use_stop) {
+        const int64_t n_exited = j->exited.fetch_add(1) + 1;
+        if (wa.by_budget && n_exited + j->resident > j->n_units) ((volatile int*)j->stop)[1] = 1;
+      }
     } else {
       lwfb::integrate_member<0>(j->d, u);
     }
@@ -265,14 +277,16 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   d.iter_budget = quanta ? seg_len : 0;
   d.n_slots = (perm && perm_len > 0) ? perm_len : 0;
   d.resume = 0;
-  static int never_stop[2] = {0, 0};                 // the stop flag is raised by the __global__ wrapper only (GPU tests)
-  d.stop = never_stop; d.resident = 0; d.cb_wait = 0;
-  d.prio_blocks = quanta && resort ? 1 : 0;          // the first block runs three times as long as the others
-  d.prio_budget = 3 * (long long)seg_len;
+  job.use_stop = quanta && resort == 2;              // resort == 2: regrouping + stop flag (front block without a budget)
+  job.resident = n_threads;
+  d.stop = job.stop; d.resident = n_threads; d.cb_wait = 0;
+  d.prio_blocks = quanta && resort ? 1 : 0;          // the first block runs three times as long as the others ...
+  d.prio_budget = job.use_stop ? (1LL << 60) : 3 * (long long)seg_len;   // ... or until the stop flag is raised
   const double tend = (double)(t0_day + n_days);
   for (int launch = 0;; launch++) {
     if (launch > 100000) return 3;
     job.next = 0;
+    job.exited = 0; job.stop[0] = job.stop[1] = 0;
     if (kernel == 0) { const int mpw = 32 / N; const int64_t ns = d.n_slots > 0 ? d.n_slots : M; job.n_units = ((ns + mpw - 1) / mpw + job.warps - 1) / job.warps; }
     std::vector<pthread_t> th(n_threads);
     for (int i = 0; i < n_threads; i++) pthread_create(&th[i], nullptr, worker, &job);

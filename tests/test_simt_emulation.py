@@ -169,6 +169,21 @@ def test_lane_kernel_full_thread_blocks(dav_full, bea):
         assert np.array_equal(got, ref, equal_nan=True)
 
 
+def test_lane_kernel_stop_flag_ends_launches_early(dav_full):
+    """The launch protocol of lwfb_run as the __global__ wrapper drives it: blocks run concurrently (host threads), the
+    first block that uses up its quantum when no block is left to take its slot raises the stop flag, every block
+    checkpoints at its next pass (threads of a block may see the flag one pass apart - the block vote decides), the
+    front block has no budget of its own.  Where a launch is cut depends on thread timing; the records must not."""
+    for M, nd, wpb, quantum, threads in ((120, 5, 2, 9, 4), (200, 4, 1, 7, 3), (90, 4, 8, 13, 2)):
+        e = en.make_ensemble(dav_full, M)
+        orc.use("elem")
+        ref, st_o, cnt_o = orc.run(e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, n_threads=8)
+        got, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
+                                seg_len=quantum, resort=2, warps_per_block=wpb, n_threads=threads)
+        assert np.array_equal(st, st_o) and np.array_equal(cnt, cnt_o)
+        assert np.array_equal(got, ref, equal_nan=True)
+
+
 def test_emulator_rejects_divergent_warp_primitives():
     """The emulator aborts when lanes meet at different warp primitives; a well-formed run reports none.  (The
     abort path itself is exercised by the build of every kernel change: a divergent shuffle never gets here.)"""
