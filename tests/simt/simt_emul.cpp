@@ -168,7 +168,9 @@ unsigned vote(bool p, int op_id) {
   for (int i = 0; i < WARP; i++) m |= (W->slot[par][base + i] ? 1u : 0u) << i;
   return m;
 }
+std::atomic<long> g_stage_syncs{0};      // stage barriers executed by thread 0 of every block (profiling: passes of the blocks)
 bool block_or(bool p, int op_id) {
+  if (op_id == 1000000 && W->cur == 0) g_stage_syncs.fetch_add(1, std::memory_order_relaxed);
   const int par = block_rendezvous(p ? 1u : 0u, op_id);
   bool any = false;
   for (int i = 0; i < W->n_lanes; i++) any = any || W->bslot[par][i] != 0;
@@ -239,6 +241,9 @@ void to_soa(const T* src, T* dst, int64_t M, int64_t K) {   // [M][K] -> [K][M]
     for (int64_t k = 0; k < K; k++) dst[k * M + m] = src[m * K + k];
 }
 }  // namespace
+
+// profiling aid: stage barriers executed by thread 0 of all blocks since the last call (6 or 7 per step pass of a block)
+extern "C" long lwfb_emul_stage_syncs() { return simt::g_stage_syncs.exchange(0); }
 
 extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days, int n_sites, int n_rows,
                              const double* forcing, int64_t M, const int32_t* site_of_member, const double* scal,
