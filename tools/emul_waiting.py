@@ -1,6 +1,6 @@
 """Lock-step waiting of the production kernel measured in the block emulator (CPU, no GPU needed): passes of the
 blocks against the members' own attempted steps, for one launch and for work quanta with regrouping.
-usage: emul_waiting.py [members] [days] [quantum,...]   (members: multiple of 48 for DAV2020-full)"""
+usage: emul_waiting.py [members] [days] [quantum,...] [warps_per_block]   (members: multiple of 48 for DAV2020-full)"""
 import os, sys, time, warnings
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "simt")):
@@ -17,15 +17,16 @@ quanta = [int(q) for q in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 
 sim = lw.setup(lw.loadSPAC(os.path.join(ROOT, "tests", "golden", "inputs", "DAV2020-full"), "DAV2020-full", simulate_isotopes=True))
 ens = en.make_ensemble(sim, M)
 L = emul.lib(); L.lwfb_emul_stage_syncs.restype = C.c_long
-mpb = 8 * (32 // ens.N)
+wpb = int(sys.argv[4]) if len(sys.argv) > 4 else 8       # lock-step group: warps that vote and barrier together
+mpb = wpb * (32 // ens.N)
 for q in quanta:
     L.lwfb_emul_stage_syncs()
     t = time.time()
     _, st, cnt = emul.run(emul.LANES, ens.N, ens.iso, ens.t0_day, D, ens.forcing, ens.site_of_member, ens.scal, ens.lay, ens.u0,
-                          seg_len=q, resort=2 if q else 0, warps_per_block=8, n_threads=os.cpu_count())
+                          seg_len=q, resort=2 if q else 0, warps_per_block=wpb, n_threads=os.cpu_count())
     syncs = L.lwfb_emul_stage_syncs()
     steps = (cnt[:, 0] + cnt[:, 1]).sum()
     reeval = D * M                                  # one 7-barrier pass per member-day at most; blocks share it
     passes = syncs / 6.0
-    print(f"quantum {q:5d}: block passes x slots = {passes * mpb:.3e}, member steps = {steps:.3e}, "
+    print(f"{wpb} warps per block, quantum {q:5d}: block passes x slots = {passes * mpb:.3e}, member steps = {steps:.3e}, "
           f"executed / needed = {passes * mpb / steps:.3f}   ({time.time() - t:.0f} s)", flush=True)
