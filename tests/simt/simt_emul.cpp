@@ -169,8 +169,9 @@ unsigned vote(bool p, int op_id) {
   return m;
 }
 std::atomic<long> g_stage_syncs{0};      // stage barriers executed by thread 0 of every block (profiling: passes of the blocks)
+std::atomic<long> g_votes{0};            // block votes executed by thread 0 of every block (3 per callback pass, 4 per step pass)
 bool block_or(bool p, int op_id) {
-  if (op_id == 1000000 && W->cur == 0) g_stage_syncs.fetch_add(1, std::memory_order_relaxed);
+  if (W->cur == 0) (op_id == 1000000 ? g_stage_syncs : g_votes).fetch_add(1, std::memory_order_relaxed);
   const int par = block_rendezvous(p ? 1u : 0u, op_id);
   bool any = false;
   for (int i = 0; i < W->n_lanes; i++) any = any || W->bslot[par][i] != 0;
@@ -244,6 +245,7 @@ void to_soa(const T* src, T* dst, int64_t M, int64_t K) {   // [M][K] -> [K][M]
 
 // profiling aid: stage barriers executed by thread 0 of all blocks since the last call (6 or 7 per step pass of a block)
 extern "C" long lwfb_emul_stage_syncs() { return simt::g_stage_syncs.exchange(0); }
+extern "C" long lwfb_emul_votes() { return simt::g_votes.exchange(0); }
 
 extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days, int n_sites, int n_rows,
                              const double* forcing, int64_t M, const int32_t* site_of_member, const double* scal,
@@ -285,6 +287,7 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   job.use_stop = quanta && resort == 2;              // resort == 2: regrouping + stop flag (front block without a budget)
   job.resident = n_threads;
   d.stop = job.stop; d.resident = n_threads; d.cb_wait = 0;
+  if (const char* e = getenv("LWFB_CB_WAIT")) d.cb_wait = atoi(e);     // profiling knob, as in the library
   d.prio_blocks = quanta && resort ? 1 : 0;          // the first block runs three times as long as the others ...
   d.prio_budget = job.use_stop ? (1LL << 60) : 3 * (long long)seg_len;   // ... or until the stop flag is raised
   const double tend = (double)(t0_day + n_days);

@@ -16,17 +16,20 @@ D = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 quanta = [int(q) for q in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 128]
 sim = lw.setup(lw.loadSPAC(os.path.join(ROOT, "tests", "golden", "inputs", "DAV2020-full"), "DAV2020-full", simulate_isotopes=True))
 ens = en.make_ensemble(sim, M)
-L = emul.lib(); L.lwfb_emul_stage_syncs.restype = C.c_long
+L = emul.lib(); L.lwfb_emul_stage_syncs.restype = C.c_long; L.lwfb_emul_votes.restype = C.c_long
 wpb = int(sys.argv[4]) if len(sys.argv) > 4 else 8       # lock-step group: warps that vote and barrier together
 mpb = wpb * (32 // ens.N)
 for q in quanta:
-    L.lwfb_emul_stage_syncs()
+    L.lwfb_emul_stage_syncs(); L.lwfb_emul_votes()
     t = time.time()
     _, st, cnt = emul.run(emul.LANES, ens.N, ens.iso, ens.t0_day, D, ens.forcing, ens.site_of_member, ens.scal, ens.lay, ens.u0,
                           seg_len=q, resort=2 if q else 0, warps_per_block=wpb, n_threads=os.cpu_count())
-    syncs = L.lwfb_emul_stage_syncs()
+    syncs = L.lwfb_emul_stage_syncs(); votes = L.lwfb_emul_votes()
     steps = (cnt[:, 0] + cnt[:, 1]).sum()
-    reeval = D * M                                  # one 7-barrier pass per member-day at most; blocks share it
-    passes = syncs / 6.0
+    # a step pass makes 4 block votes and 6 stage barriers (7 right after a callback: FSAL re-evaluation), a callback
+    # phase 3 votes; with one re-evaluation pass per callback phase: syncs = 6 P_step + P_cb, votes = 4 P_step + 3 P_cb
+    cb_passes = (votes - 2.0 * syncs / 3.0) / (7.0 / 3.0)
+    passes = (syncs - cb_passes) / 6.0
     print(f"{wpb} warps per block, quantum {q:5d}: block passes x slots = {passes * mpb:.3e}, member steps = {steps:.3e}, "
-          f"executed / needed = {passes * mpb / steps:.3f}   ({time.time() - t:.0f} s)", flush=True)
+          f"executed / needed = {passes * mpb / steps:.3f}, callback phases per block and day = "
+          f"{cb_passes / (M / mpb) / D:.2f}   ({time.time() - t:.0f} s)", flush=True)
