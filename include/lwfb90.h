@@ -214,13 +214,24 @@ int lwfb_get_status(lwfb_handle* h, int32_t* status, int64_t* counters);
 
 /* per-member goodness of fit against observations (the only reference analogue is
  * RMS_differences, test/fct-helpers-for-integration-tests.jl:6-18):
- *   obs_theta [n_obs_days][n_obs_layers], obs_d18o likewise; NaN = missing
+ *   obs_theta [n_obs_days][n_obs_layers], obs_d18o likewise; NaN = missing; either may be NULL
  *   obs_day   [n_obs_days]     record index k (0..n_days)
  *   obs_layer [n_obs_layers]   0-based layer index
- *   scores    [n_members][LWFB_NSCORES] */
+ *   scores    [n_members][LWFB_NSCORES]
+ * Two ways, bit-identical results:
+ *   (a) from the resident daily record (record_daily = 1): pass the observations here, after the run;
+ *   (b) without a record (record_daily = 0, e.g. 1 M members on one GPU): register the observations BEFORE the run
+ *       with lwfb_set_observations - the integrator then accumulates the sums itself at the observation days -
+ *       and call lwfb_scores / lwfb_scores_device with n_obs_days = 0 and NULL tables afterwards. */
 int lwfb_scores(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_day,
                 int32_t n_obs_layers, const int32_t* obs_layer,
                 const double* obs_theta, const double* obs_d18o, double* scores);
+
+/* registers (n_obs_days > 0) or clears (n_obs_days = 0) the observations scored during the following runs;
+ * obs_day must be strictly increasing.  See lwfb_scores. */
+int lwfb_set_observations(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_day,
+                          int32_t n_obs_layers, const int32_t* obs_layer,
+                          const double* obs_theta, const double* obs_d18o);
 
 /* device-resident views for callers that stay on the GPU (bench, NCCL all-gather):
  * pointer to scores [n_members][LWFB_NSCORES] after lwfb_scores_device. */
@@ -263,7 +274,8 @@ int lwfb_elem_eval(int32_t device, int32_t fn, int64_t n, const double* x, const
  * driver-written MEASURED_PEAKS.json has HBM and bf16 tensor figures only) */
 int lwfb_fp64_peak(int32_t device, int32_t reps, double* tflops);
 
-/* testing aid: raw device-layout copy ([field][member]) of the member blocks; which = 0 scal, 1 lay, 2 u0 */
+/* testing aid: copy of the device-resident member blocks (member-major like the arguments of lwfb_set_members);
+ * which = 0 scal, 1 lay, 2 u0 */
 int lwfb_debug_get_block(lwfb_handle* h, int32_t which, double* out);
 
 /* testing aid: run the thread-per-member kernel (a second, independently written CUDA implementation that
@@ -280,7 +292,9 @@ int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on);
  * RHS evaluations of that run.  When the unfinished members no longer fill the device they are dealt thinly to all
  * resident slots (LWFB_SPREAD, default 1).  Ensembles that do not fill the device once (LWFB_MIN_WAVES, default 1) run
  * in one launch, and lwfb_run_async is always a single launch (cost-sorted if the handle has run before).
- * mode 0: one launch, members as given.  mode 2: like 1 but also for small launches (testing). */
+ * mode 0: one launch, members as given.  mode 2: like 1 but also for small launches (testing).
+ * Every call also forgets what earlier runs of the handle learned about the members' cost (the next run is "cold");
+ * lwfb_set_members does the same. */
 int lwfb_set_placement(lwfb_handle* h, int32_t mode);
 
 /* kernel launch statistics of the last lwfb_run: number of kernel launches, device ms */

@@ -38,7 +38,7 @@ SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error"
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
            "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
            "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy", "lwfb_set_placement",
-           "lwfb_water_partitioning", "lwfb_soil_state"]
+           "lwfb_water_partitioning", "lwfb_soil_state", "lwfb_set_observations"]
 
 
 def lib():
@@ -64,6 +64,7 @@ def lib():
         L.lwfb_scores.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp, _dp]; L.lwfb_scores.restype = C.c_int
         L.lwfb_scores_device.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp, C.POINTER(vp)]
         L.lwfb_scores_device.restype = C.c_int
+        L.lwfb_set_observations.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp]; L.lwfb_set_observations.restype = C.c_int
         L.lwfb_eval_rhs.argtypes = [vp, C.c_double, _dp, _dp, _dp, _dp, _dp]; L.lwfb_eval_rhs.restype = C.c_int
         L.lwfb_last_run_stats.argtypes = [vp, _ip, C.POINTER(C.c_float)]; L.lwfb_last_run_stats.restype = C.c_int
         L.lwfb_elem_eval.argtypes = [C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp]; L.lwfb_elem_eval.restype = C.c_int
@@ -168,8 +169,12 @@ class Handle:
 
     def get_daily(self, first=0, count=None, out=None):
         count = self.M - first if count is None else count
+        shape = (count, self.n_days + 1, self.L)
         if out is None:
-            out = np.empty((count, self.n_days + 1, self.L))
+            out = np.empty(shape)
+        elif not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.shape == shape
+                  and out.flags.c_contiguous and out.flags.writeable):
+            raise LwfbError(f"get_daily(out=...): need a writeable C-contiguous float64 array of shape {shape}")
         self._ck(self._L.lwfb_get_daily(self._h, first, count, _p(out)))
         return out
 
@@ -185,7 +190,24 @@ class Handle:
         self._ck(self._L.lwfb_get_status(self._h, _p(st, _ip), _p(cnt, _lp)))
         return st, cnt
 
-    def scores(self, obs_day, obs_layer, obs_theta=None, obs_d18o=None):
+    def set_observations(self, obs_day=None, obs_layer=None, obs_theta=None, obs_d18o=None):
+        """Register the observations that the following runs score on the fly (needed with record_daily=False);
+        afterwards scores() / scores_device() without arguments return the result.  No arguments: clear."""
+        if obs_day is None:
+            self._ck(self._L.lwfb_set_observations(self._h, 0, None, 0, None, None, None))
+            return
+        od = np.ascontiguousarray(obs_day, dtype=np.int32)
+        ol = np.ascontiguousarray(obs_layer, dtype=np.int32)
+        th = None if obs_theta is None else _f64(obs_theta).reshape(len(od), len(ol))
+        d18 = None if obs_d18o is None else _f64(obs_d18o).reshape(len(od), len(ol))
+        self._ck(self._L.lwfb_set_observations(self._h, len(od), _p(od, _ip), len(ol), _p(ol, _ip),
+                                               None if th is None else _p(th), None if d18 is None else _p(d18)))
+
+    def scores(self, obs_day=None, obs_layer=None, obs_theta=None, obs_d18o=None):
+        if obs_day is None:           # the sums accumulated during the run (set_observations)
+            out = np.empty((self.M, lo.NSCORES))
+            self._ck(self._L.lwfb_scores(self._h, 0, None, 0, None, None, None, _p(out)))
+            return out
         od = np.ascontiguousarray(obs_day, dtype=np.int32)
         ol = np.ascontiguousarray(obs_layer, dtype=np.int32)
         th = None if obs_theta is None else _f64(obs_theta).reshape(len(od), len(ol))
@@ -195,8 +217,12 @@ class Handle:
                                      None if th is None else _p(th), None if d18 is None else _p(d18), _p(out)))
         return out
 
-    def scores_device(self, obs_day, obs_layer, obs_theta=None, obs_d18o=None) -> int:
+    def scores_device(self, obs_day=None, obs_layer=None, obs_theta=None, obs_d18o=None) -> int:
         """Like scores() but leaves the [M][NSCORES] block on the GPU and returns its device address."""
+        if obs_day is None:
+            ptr = C.c_void_p()
+            self._ck(self._L.lwfb_scores_device(self._h, 0, None, 0, None, None, None, C.byref(ptr)))
+            return int(ptr.value)
         od = np.ascontiguousarray(obs_day, dtype=np.int32)
         ol = np.ascontiguousarray(obs_layer, dtype=np.int32)
         th = None if obs_theta is None else _f64(obs_theta).reshape(len(od), len(ol))

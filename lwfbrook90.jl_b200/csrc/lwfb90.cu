@@ -7,9 +7,9 @@
 //   integrate_kernel<NT> (lwfb90_member.cu)  thread-per-member fallback for N < 3 or N > 32, and rhs_kernel (one RHS
 //                          evaluation per member, unit parity tests).
 //   placement_keys / spread_placement  sort keys and thin slot assignment of the regrouping (with cub's radix sort).
-//   aos_to_soa / soa_to_aos layout transposes between the ABI's member-major blocks and the device's
-//                          [field][member] layout.
-//   score_kernel           per-member RMSE / KGE against observations, reading the daily record.
+//   score_sums_kernel / score_finalize_kernel  per-member RMSE / KGE against observations from the daily record or from
+//                          the sums the integrator accumulated itself (lwfb_set_observations).
+// All device blocks are member-major (the ABI's own layouts): no transposes at the boundary.
 //   water_partitioning_kernel, soil_state_kernel (lwfb90_post.cuh)  post-processing of the resident daily record.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -29,41 +29,22 @@
 
 using namespace lwfb;
 
-// [K][M] rows k in [0,K) of members [m_first, m_first+cnt) -> [cnt][K]
-__global__ void soa_to_aos(const double* __restrict__ src, double* __restrict__ dst, int64_t M, int64_t m_first,
-                           int64_t cnt, int K) {
-  __shared__ double tile[32][33];
-  int64_t m0 = (int64_t)blockIdx.x * 32;
-  int k0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int kk = k0 + r;
-    int64_t mm = m0 + threadIdx.x;
-    if (mm < cnt && kk < K) tile[r][threadIdx.x] = src[(int64_t)kk * M + m_first + mm];
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int64_t mm = m0 + r;
-    int kk = k0 + threadIdx.x;
-    if (mm < cnt && kk < K) dst[mm * K + kk] = tile[threadIdx.x][r];
-  }
-}
-
 // sort keys of the placement (ascending radix sort, stable: ties keep the member order)
 //   by_cost: RHS evaluations of the previous run, most first
 //   else   : progress of the unfinished members (simulation time reached, least first); finished members get the
 //            largest key and are counted out of *n_left
-__global__ void placement_keys(const double* __restrict__ t, const int32_t* __restrict__ status,
-                               const long long* __restrict__ nf, int64_t M, double t0, double tend, int by_cost,
+__global__ void placement_keys(const double* __restrict__ ck, int ck_rows, const int32_t* __restrict__ status,
+                               const long long* __restrict__ counters, int64_t M, double t0, double tend, int by_cost,
                                uint32_t* __restrict__ key, int32_t* __restrict__ idx, int* __restrict__ n_left) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool unfinished = false;
   if (i < M) {
     uint32_t k;
     if (by_cost) {
-      const long long c = nf[i];
+      const long long c = counters[i * LWFB_NCOUNTERS + LWFB_C_NF];
       k = 0xffffffffu - (uint32_t)(c < 0 ? 0 : (c > 0xfffffffeLL ? 0xfffffffeLL : c));
     } else {
-      const double ti = t[i];
+      const double ti = ck[i * ck_rows + LWFB_CK_T];
       unfinished = status[i] == LWFB_ST_OK && ti < tend;
       k = unfinished ? __float_as_uint((float)(ti - t0)) : 0xffffffffu;   // >= 0: the bit pattern orders like the value
     }
@@ -92,51 +73,42 @@ __global__ void spread_front(const int32_t* __restrict__ sorted, int64_t n, int6
   out[j < thin ? (j / per_front) * slots_per_block + (j % per_front) : n_front * slots_per_block + (j - thin)] = sorted[j];
 }
 
-// per-member goodness of fit against observed theta / delta18O (RMSE, KGE)
-__global__ void score_kernel(DevData d, int n_obs_days, const int32_t* __restrict__ obs_day, int n_obs_layers,
-                             const int32_t* __restrict__ obs_layer, const double* __restrict__ obs_theta,
-                             const double* __restrict__ obs_d18o, double* __restrict__ scores) {
+// per-member goodness-of-fit sums against observed theta / delta18O from the resident daily record: the same
+// expressions in the same order (days outer, observed layers inner) as the integrator's own accumulation (score_rec in
+// lwfb90_lanes.cuh), so that both ways give bit-identical scores.  One thread per member (a few hundred scattered reads).
+__global__ void score_sums_kernel(DevData d, int n_obs_days, const int32_t* __restrict__ obs_day, int n_obs_layers,
+                                  const int32_t* __restrict__ obs_layer, const double* __restrict__ obs_theta,
+                                  const double* __restrict__ obs_d18o, double* __restrict__ sacc) {
   const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= d.M) return;
-  const int64_t M = d.M;
   const int N = d.N, L = d.L;
-  double res[LWFB_NSCORES];
-  for (int v = 0; v < 2; v++) {
-    const double* obs = v == 0 ? obs_theta : obs_d18o;
-    double n = 0, se = 0, so = 0, ss = 0, soo = 0, sss = 0, sos = 0;
-    if (obs != nullptr && (v == 0 || d.iso)) {
-      for (int l = 0; l < n_obs_layers; l++) {
-        int i = obs_layer[l];
-        double ths = __ldg(d.lay + ((int64_t)LWFB_L_THSAT * N + i) * M + m);
-        double thr = __ldg(d.lay + ((int64_t)LWFB_L_THR * N + i) * M + m);
-        double smax = __ldg(d.lay + ((int64_t)LWFB_L_SWATMAX * N + i) * M + m);
-        for (int k = 0; k < n_obs_days; k++) {
-          double o = obs[(int64_t)k * n_obs_layers + l];
-          if (o != o) continue;
-          const double* r = d.rec + (int64_t)obs_day[k] * L * M;
-          double sim;
-          if (v == 0) {
-            double sw = r[(int64_t)i * M + m];
-            double w = jmin(1.0, (ths * sw / smax - thr) / (ths - thr));
-            sim = w * (ths - thr) + thr;
-          } else {
-            sim = r[(int64_t)(N + i) * M + m];
-          }
-          double e = sim - o;
-          n += 1; se += e * e; so += o; ss += sim; soo += o * o; sss += sim * sim; sos += o * sim;
-        }
+  double a[2 * LWFB_SA];
+  for (int k = 0; k < 2 * LWFB_SA; k++) a[k] = 0.0;
+  for (int k = 0; k < n_obs_days; k++) {
+    const double* r = d.rec + (m * (int64_t)(d.n_days + 1) + obs_day[k]) * L;
+    for (int l = 0; l < n_obs_layers; l++) {
+      const int i = obs_layer[l];
+      if (obs_theta) {
+        const double ths = __ldg(d.lay + (m * LWFB_PL + LWFB_L_THSAT) * N + i);
+        const double thr = __ldg(d.lay + (m * LWFB_PL + LWFB_L_THR) * N + i);
+        const double smax = __ldg(d.lay + (m * LWFB_PL + LWFB_L_SWATMAX) * N + i);
+        const double dth = ths - thr;
+        const double w = jminc((ths * r[i] / smax - thr) / dth, 1.0);
+        score_add(a, w * dth + thr, obs_theta[(int64_t)k * n_obs_layers + l]);
       }
+      if (obs_d18o && d.iso) score_add(a + LWFB_SA, r[N + i], obs_d18o[(int64_t)k * n_obs_layers + l]);
     }
-    double rmse = NAN, kge = NAN;
-    if (n > 0) {
-      rmse = sqrt(se / n);
-      double mo = so / n, ms = ss / n;
-      double vo = soo / n - mo * mo, vs = sss / n - ms * ms, cov = sos / n - mo * ms;
-      double r = cov / sqrt(vo * vs), al = sqrt(vs / vo), be = ms / mo;
-      kge = 1 - sqrt((r - 1) * (r - 1) + (al - 1) * (al - 1) + (be - 1) * (be - 1));
-    }
-    res[2 * v] = rmse; res[2 * v + 1] = kge;
   }
+  for (int k = 0; k < 2 * LWFB_SA; k++) sacc[m * (2 * LWFB_SA) + k] = a[k];
+}
+
+// sums -> RMSE / KGE of theta and delta18O
+__global__ void score_finalize_kernel(const double* __restrict__ sacc, int64_t M, double* __restrict__ scores) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  double res[LWFB_NSCORES];
+  score_finish(sacc + m * (2 * LWFB_SA), &res[LWFB_SC_RMSE_THETA], &res[LWFB_SC_KGE_THETA]);
+  score_finish(sacc + m * (2 * LWFB_SA) + LWFB_SA, &res[LWFB_SC_RMSE_D18O], &res[LWFB_SC_KGE_D18O]);
   for (int s = 0; s < LWFB_NSCORES; s++) scores[m * LWFB_NSCORES + s] = res[s];
 }
 
@@ -190,10 +162,20 @@ struct lwfb_handle {
   double* d_stage = nullptr;  // staging for layout transposes
   size_t stage_bytes = 0;
   double* d_scores = nullptr;
+  // observations registered for scoring during the run (lwfb_set_observations) and the running sums [M][2][LWFB_SA]
+  int n_obs_days = 0, n_obs_layers = 0;
+  int32_t *d_obs_of_rec = nullptr, *d_obs_layer = nullptr;
+  double *d_obs_theta = nullptr, *d_obs_d18o = nullptr;
+  double *d_sacc = nullptr, *d_sacc_rec = nullptr;   // sums of the run / scratch of the record-based scores
+  bool sums_valid = false;     // d_sacc holds the sums of a completed run
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_launches = 0;
   float last_ms = 0.f;
   bool ran = false;
+  bool pending = false;        // lwfb_run_async launched, not yet synchronised
+  void* pin[2] = {nullptr, nullptr};   // pinned bounce buffers of the downloads
+  cudaEvent_t pin_ev[2] = {nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;
   bool force_legacy = false;   // testing: run the thread-per-member kernel also for 3 <= N <= 32
   // placement of members in the lane kernel's slots (lwfb_set_placement)
   int placement = 1;           // 0 identity, 1 adaptive (cost-sorted from the previous run), 2 the same for any launch size
@@ -222,6 +204,9 @@ struct lwfb_handle {
       return LWFB_ERR_CUDA;                                                                   \
     }                                                                                         \
   } while (0)
+
+static int ensure_done(lwfb_handle* h);
+static int download(lwfb_handle* h, void* dst, const void* src, size_t bytes);
 
 static int ensure_stage(lwfb_handle* h, size_t bytes) {
   if (h->stage_bytes >= bytes) return LWFB_OK;
@@ -260,6 +245,7 @@ static void free_members(lwfb_handle* h) {
   cudaFree(h->d_site); cudaFree(h->d_status); cudaFree(h->d_counters); cudaFree(h->d_scores); cudaFree(h->d_perm); cudaFree(h->d_ck); cudaFree(h->d_stop);
   cudaFree(h->d_key); cudaFree(h->d_key2); cudaFree(h->d_idx); cudaFree(h->d_sort_tmp); cudaFree(h->d_nleft);
   cudaFree(h->d_perm_thin); h->d_perm_thin = nullptr; h->perm_thin_len = 0;
+  cudaFree(h->d_sacc); cudaFree(h->d_sacc_rec); h->d_sacc = h->d_sacc_rec = nullptr; h->sums_valid = false;
   h->d_key = h->d_key2 = nullptr; h->d_idx = nullptr; h->d_sort_tmp = nullptr; h->d_nleft = nullptr; h->sort_tmp_bytes = 0;
   h->d_perm = nullptr; h->d_ck = nullptr; h->d_stop = nullptr; h->perm_valid = false; h->cost_valid = false;
   h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
@@ -272,6 +258,9 @@ extern "C" void lwfb_destroy(lwfb_handle* h) {
   cudaSetDevice(h->o.device);
   free_members(h);
   cudaFree(h->d_forc); cudaFree(h->d_stage);
+  cudaFree(h->d_obs_of_rec); cudaFree(h->d_obs_layer); cudaFree(h->d_obs_theta); cudaFree(h->d_obs_d18o);
+  for (int k = 0; k < 2; k++) { if (h->pin[k]) cudaFreeHost(h->pin[k]); if (h->pin_ev[k]) cudaEventDestroy(h->pin_ev[k]); }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;
@@ -288,40 +277,6 @@ extern "C" int lwfb_set_sites(lwfb_handle* h, int32_t n_sites, int32_t n_rows, c
   CK(cudaMalloc(&h->d_forc, bytes));
   CK(cudaMemcpy(h->d_forc, forcing, bytes, cudaMemcpyHostToDevice));
   h->n_sites = n_sites; h->n_rows = n_rows;
-  return LWFB_OK;
-}
-
-// strided transpose: [cnt][K] -> dst[k*M + m0 + m]
-__global__ void aos_to_soa_strided(const double* __restrict__ src, double* __restrict__ dst, int64_t cnt, int K,
-                                   int64_t M, int64_t m0) {
-  __shared__ double tile[32][33];
-  int64_t mb = (int64_t)blockIdx.x * 32;
-  int k0 = blockIdx.y * 32;
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int64_t mm = mb + r;
-    int kk = k0 + threadIdx.x;
-    if (mm < cnt && kk < K) tile[r][threadIdx.x] = src[mm * K + kk];
-  }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
-    int kk = k0 + r;
-    int64_t mm = mb + threadIdx.x;
-    if (mm < cnt && kk < K) dst[(int64_t)kk * M + m0 + mm] = tile[threadIdx.x][r];
-  }
-}
-
-static int upload_soa(lwfb_handle* h, const double* src, double* dst, int64_t M, int K) {
-  const int64_t chunk = 1 << 16;
-  int rc = ensure_stage(h, (size_t)chunk * K * sizeof(double));
-  if (rc) return rc;
-  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
-    int64_t cnt = M - m0 < chunk ? M - m0 : chunk;
-    CK(cudaMemcpy(h->d_stage, src + m0 * K, (size_t)cnt * K * sizeof(double), cudaMemcpyHostToDevice));
-    dim3 blk(32, 8), grd((unsigned)((cnt + 31) / 32), (unsigned)((K + 31) / 32));
-    aos_to_soa_strided<<<grd, blk>>>(h->d_stage, dst, cnt, K, M, m0);
-    CK(cudaGetLastError());
-    CK(cudaDeviceSynchronize());
-  }
   return LWFB_OK;
 }
 
@@ -344,6 +299,7 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
     CK(cudaMalloc(&h->d_status, (size_t)M * sizeof(int32_t)));
     CK(cudaMalloc(&h->d_counters, (size_t)M * LWFB_NCOUNTERS * sizeof(long long)));
     CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
+    CK(cudaMalloc(&h->d_sacc, (size_t)M * 2 * LWFB_SA * sizeof(double)));
     CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
     CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + LWFB_CKL * N) * sizeof(double)));
     CK(cudaMalloc(&h->d_stop, 2 * sizeof(int)));
@@ -362,11 +318,12 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
     h->M = M;
   }
   CK(cudaMemcpy(h->d_site, site_of_member, (size_t)h->M * sizeof(int32_t), cudaMemcpyHostToDevice));
-  int rc;
-  if ((rc = upload_soa(h, scal, h->d_scal, h->M, LWFB_PS))) return rc;
-  if ((rc = upload_soa(h, lay, h->d_lay, h->M, LWFB_PL * N))) return rc;
-  if ((rc = upload_soa(h, u0, h->d_u0, h->M, L))) return rc;
-  h->ran = false;
+  // the device blocks are member-major like the ABI's: plain copies, no transposes
+  CK(cudaMemcpy(h->d_scal, scal, (size_t)h->M * LWFB_PS * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_lay, lay, (size_t)h->M * LWFB_PL * N * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_u0, u0, (size_t)h->M * L * sizeof(double), cudaMemcpyHostToDevice));
+  h->ran = false; h->sums_valid = false;
+  h->cost_valid = false; h->perm_valid = false;   // counters / placement of the previous members say nothing about these
   return LWFB_OK;
 }
 
@@ -381,6 +338,9 @@ static DevData make_dev(lwfb_handle* h) {
   d.maxiters = h->o.maxiters;
   d.iter_budget = 0; d.prio_blocks = 0; d.prio_budget = 0; d.n_slots = 0; d.resume = 0; d.ck = nullptr;
   d.stop = nullptr; d.resident = 0; d.cb_wait = 0;
+  d.n_obs_layers = h->n_obs_days > 0 ? h->n_obs_layers : 0;
+  d.obs_of_rec = h->d_obs_of_rec; d.obs_layer = h->d_obs_layer; d.obs_theta = h->d_obs_theta; d.obs_d18o = h->d_obs_d18o;
+  d.sacc = h->d_sacc;
   if (const char* e = getenv("LWFB_CB_WAIT")) d.cb_wait = atoi(e);
   return d;
 }
@@ -404,7 +364,7 @@ static int sort_placement(lwfb_handle* h, bool by_cost, cudaStream_t st, int64_t
   if (M > 0x7fffffffLL) { h->err = "more than 2^31 members per handle"; return LWFB_ERR_ARG; }
   CK(cudaMemsetAsync(h->d_nleft, 0, sizeof(int), st));
   placement_keys<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(
-      h->d_ck + (size_t)LWFB_CK_T * M, h->d_status, h->d_counters + (size_t)LWFB_C_NF * M, M, (double)h->o.t0_day,
+      h->d_ck, LWFB_CK + LWFB_CKL * h->o.n_layers, h->d_status, h->d_counters, M, (double)h->o.t0_day,
       (double)(h->o.t0_day + h->o.n_days), by_cost ? 1 : 0, h->d_key, h->d_idx, h->d_nleft);
   CK(cudaGetLastError());
   CK(cub::DeviceRadixSort::SortPairs(h->d_sort_tmp, h->sort_tmp_bytes, h->d_key, h->d_key2, h->d_idx, h->d_perm, (int)M, 0, 32, st));
@@ -466,10 +426,13 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
   DevData d = make_dev(h);
   h->n_launches = 0;
   CK(cudaEventRecord(h->ev0, st));
+  if (d.n_obs_layers > 0) CK(cudaMemsetAsync(h->d_sacc, 0, (size_t)h->M * 2 * LWFB_SA * sizeof(double), st));
+  h->sums_valid = d.n_obs_layers > 0;
   int rc = launch_integrator(h, d, st);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev1, st));
   h->ran = true;
+  h->pending = true;
   h->cost_valid = lanes;
   return LWFB_OK;
 }
@@ -479,6 +442,7 @@ extern "C" int lwfb_sync(lwfb_handle* h) {
   CK(cudaSetDevice(h->o.device));
   CK(cudaEventSynchronize(h->ev1));
   CK(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->pending = false;
   return LWFB_OK;
 }
 
@@ -530,6 +494,8 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   } else h->perm_valid = false;
   h->n_launches = 0;
   CK(cudaEventRecord(h->ev0, st));
+  if (h->n_obs_days > 0) CK(cudaMemsetAsync(h->d_sacc, 0, (size_t)h->M * 2 * LWFB_SA * sizeof(double), st));
+  h->sums_valid = h->n_obs_days > 0;
   int64_t n_left = h->M;
   const bool cold = !h->cost_valid;
   for (int launch = 0; n_left > 0; launch++) {
@@ -614,6 +580,7 @@ extern "C" int lwfb_water_partitioning(lwfb_handle* h, int32_t n_groups, const i
   if (!h || !out || !group_of_record || n_groups < 1 || !h->ran) return LWFB_ERR_ARG;
   if (!h->d_rec) { h->err = "handle was created with record_daily = 0"; return LWFB_ERR_ARG; }
   CK(cudaSetDevice(h->o.device));
+  { int rc = ensure_done(h); if (rc) return rc; }
   const int n_rec = h->o.n_days + 1;
   std::vector<int32_t> n_in((size_t)n_groups, 0);
   for (int r = 0; r < n_rec; r++)
@@ -624,10 +591,11 @@ extern "C" int lwfb_water_partitioning(lwfb_handle* h, int32_t n_groups, const i
   CK(cudaMalloc(&d_grp, (size_t)(n_rec + n_groups) * sizeof(int32_t)));
   cudaError_t e = cudaMalloc(&d_out, out_bytes);
   if (e != cudaSuccess) { cudaFree(d_grp); h->err = "cannot allocate the aggregate block"; return LWFB_ERR_NOMEM; }
-  cudaMemcpy(d_grp, group_of_record, (size_t)n_rec * sizeof(int32_t), cudaMemcpyHostToDevice);
-  cudaMemcpy(d_grp + n_rec, n_in.data(), (size_t)n_groups * sizeof(int32_t), cudaMemcpyHostToDevice);
+  e = cudaMemcpy(d_grp, group_of_record, (size_t)n_rec * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_grp + n_rec, n_in.data(), (size_t)n_groups * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d_grp); cudaFree(d_out); h->err = std::string("lwfb_water_partitioning: ") + cudaGetErrorString(e); return LWFB_ERR_CUDA; }
   const SIdx ix(h->o.n_layers, h->o.simulate_isotopes);
-  water_partitioning_kernel<<<(unsigned)((h->M + 127) / 128), 128>>>(h->d_rec, h->M, h->L, ix.ACC, n_rec, d_grp, n_groups, d_out);
+  water_partitioning_kernel<<<(unsigned)((h->M + 3) / 4), 128>>>(h->d_rec, h->M, h->L, ix.ACC, n_rec, d_grp, n_groups, d_out);
   const int64_t n_cells = h->M * (int64_t)n_groups;
   water_partitioning_mean<<<(unsigned)((n_cells + 255) / 256), 256>>>(d_out, h->M, n_groups, d_grp + n_rec);
   e = cudaGetLastError();
@@ -646,16 +614,18 @@ extern "C" int lwfb_soil_state(lwfb_handle* h, int32_t n_rec_sel, const int32_t*
   for (int q = 0; q < n_lay_sel; q++)
     if (layer_idx[q] < 0 || layer_idx[q] >= h->o.n_layers) { h->err = "layer index out of range"; return LWFB_ERR_ARG; }
   CK(cudaSetDevice(h->o.device));
+  { int rc = ensure_done(h); if (rc) return rc; }
   int32_t* d_idx = nullptr;
   double* d_out = nullptr;
   const size_t out_bytes = (size_t)h->M * n_rec_sel * n_lay_sel * LWFB_NSV * sizeof(double);
   CK(cudaMalloc(&d_idx, (size_t)(n_rec_sel + n_lay_sel) * sizeof(int32_t)));
   cudaError_t e = cudaMalloc(&d_out, out_bytes);
   if (e != cudaSuccess) { cudaFree(d_idx); h->err = "cannot allocate the soil-state block"; return LWFB_ERR_NOMEM; }
-  cudaMemcpy(d_idx, rec_idx, (size_t)n_rec_sel * sizeof(int32_t), cudaMemcpyHostToDevice);
-  cudaMemcpy(d_idx + n_rec_sel, layer_idx, (size_t)n_lay_sel * sizeof(int32_t), cudaMemcpyHostToDevice);
+  e = cudaMemcpy(d_idx, rec_idx, (size_t)n_rec_sel * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_idx + n_rec_sel, layer_idx, (size_t)n_lay_sel * sizeof(int32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d_idx); cudaFree(d_out); h->err = std::string("lwfb_soil_state: ") + cudaGetErrorString(e); return LWFB_ERR_CUDA; }
   soil_state_kernel<<<(unsigned)((h->M + 127) / 128), 128>>>(h->d_rec, h->d_lay, h->M, h->o.n_layers, h->L,
-                                                             h->o.simulate_isotopes, n_rec_sel, d_idx, n_lay_sel,
+                                                             h->o.simulate_isotopes, h->o.n_days + 1, n_rec_sel, d_idx, n_lay_sel,
                                                              d_idx + n_rec_sel, d_out);
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpy(out, d_out, out_bytes, cudaMemcpyDeviceToHost);
@@ -671,68 +641,140 @@ extern "C" int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* d
   return LWFB_OK;
 }
 
+// every getter first waits for an asynchronous run (lwfb_run_async) that has not been synchronised yet: the getters copy
+// on the legacy default stream, which does not order against a caller's non-blocking stream
+static int ensure_done(lwfb_handle* h) {
+  if (!h->pending) return LWFB_OK;
+  return lwfb_sync(h);
+}
+
+// D2H through a pinned bounce buffer in chunks, two chunks in flight (pageable destinations would serialise on the
+// driver's own staging); the device record is already in the layout the caller gets
+static int download(lwfb_handle* h, void* dst, const void* src, size_t bytes) {
+  const size_t chunk = (size_t)32 << 20;
+  cudaPointerAttributes pa;
+  const bool dst_pinned = cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+  cudaGetLastError();                                 // (an unregistered host pointer may leave an error state behind)
+  // page-locked destination: one DMA at link speed, nothing to stage
+  if (dst_pinned || bytes <= chunk / 4) { CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost)); return LWFB_OK; }
+  if (!h->pin[0]) {
+    for (int k = 0; k < 2; k++) {
+      CK(cudaMallocHost(&h->pin[k], chunk));
+      CK(cudaEventCreateWithFlags(&h->pin_ev[k], cudaEventDisableTiming));
+    }
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  }
+  CK(cudaDeviceSynchronize());
+  size_t off[2] = {0, 0}, len[2] = {0, 0};
+  int k = 0;
+  for (size_t o = 0; o < bytes || len[0] || len[1]; k ^= 1) {
+    if (len[k]) {                                     // the chunk that went out two rounds ago has arrived
+      CK(cudaEventSynchronize(h->pin_ev[k]));
+      memcpy((char*)dst + off[k], h->pin[k], len[k]);
+      len[k] = 0;
+    }
+    if (o < bytes) {
+      const size_t n = bytes - o < chunk ? bytes - o : chunk;
+      CK(cudaMemcpyAsync(h->pin[k], (const char*)src + o, n, cudaMemcpyDeviceToHost, h->copy_stream));
+      CK(cudaEventRecord(h->pin_ev[k], h->copy_stream));
+      off[k] = o; len[k] = n; o += n;
+    }
+  }
+  return LWFB_OK;
+}
+
 extern "C" int lwfb_get_daily(lwfb_handle* h, int64_t member_first, int64_t member_count, double* out) {
   if (!h || !out || !h->ran) return LWFB_ERR_ARG;
   if (!h->d_rec) { h->err = "handle was created with record_daily = 0"; return LWFB_ERR_ARG; }
   if (member_first < 0 || member_count < 1 || member_first + member_count > h->M) return LWFB_ERR_ARG;
   CK(cudaSetDevice(h->o.device));
-  const int K = (h->o.n_days + 1) * h->L;  // rows of the [K][M] device record
-  // chunk over members so that the staging buffer stays moderate
-  int64_t chunk = (int64_t)((256u << 20) / ((size_t)K * sizeof(double)));
-  if (chunk < 32) chunk = 32;
-  int rc = ensure_stage(h, (size_t)chunk * K * sizeof(double));
+  int rc = ensure_done(h);
   if (rc) return rc;
-  for (int64_t m0 = 0; m0 < member_count; m0 += chunk) {
-    int64_t cnt = member_count - m0 < chunk ? member_count - m0 : chunk;
-    dim3 blk(32, 8), grd((unsigned)((cnt + 31) / 32), (unsigned)((K + 31) / 32));
-    soa_to_aos<<<grd, blk>>>(h->d_rec, h->d_stage, h->M, member_first + m0, cnt, K);
-    CK(cudaGetLastError());
-    CK(cudaMemcpy(out + m0 * K, h->d_stage, (size_t)cnt * K * sizeof(double), cudaMemcpyDeviceToHost));
-  }
-  return LWFB_OK;
+  const size_t K = (size_t)(h->o.n_days + 1) * h->L;  // doubles per member: [n_days+1][L], contiguous on the device too
+  return download(h, out, h->d_rec + (size_t)member_first * K, (size_t)member_count * K * sizeof(double));
 }
 
 extern "C" int lwfb_get_final(lwfb_handle* h, int64_t member_first, int64_t member_count, double* out) {
   if (!h || !out || !h->ran) return LWFB_ERR_ARG;
   if (member_first < 0 || member_count < 1 || member_first + member_count > h->M) return LWFB_ERR_ARG;
   CK(cudaSetDevice(h->o.device));
-  const int K = h->L;
-  int rc = ensure_stage(h, (size_t)member_count * K * sizeof(double));
+  int rc = ensure_done(h);
   if (rc) return rc;
-  dim3 blk(32, 8), grd((unsigned)((member_count + 31) / 32), (unsigned)((K + 31) / 32));
-  soa_to_aos<<<grd, blk>>>(h->d_fin, h->d_stage, h->M, member_first, member_count, K);
-  CK(cudaGetLastError());
-  CK(cudaMemcpy(out, h->d_stage, (size_t)member_count * K * sizeof(double), cudaMemcpyDeviceToHost));
-  return LWFB_OK;
+  return download(h, out, h->d_fin + (size_t)member_first * h->L, (size_t)member_count * h->L * sizeof(double));
 }
 
 extern "C" int lwfb_get_status(lwfb_handle* h, int32_t* status, int64_t* counters) {
   if (!h || !h->ran) return LWFB_ERR_ARG;
   CK(cudaSetDevice(h->o.device));
+  int rc = ensure_done(h);
+  if (rc) return rc;
   if (status) CK(cudaMemcpy(status, h->d_status, (size_t)h->M * sizeof(int32_t), cudaMemcpyDeviceToHost));
-  if (counters) {
-    std::vector<long long> tmp((size_t)h->M * LWFB_NCOUNTERS);
-    CK(cudaMemcpy(tmp.data(), h->d_counters, tmp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    for (int64_t m = 0; m < h->M; m++)
-      for (int c = 0; c < LWFB_NCOUNTERS; c++) counters[m * LWFB_NCOUNTERS + c] = tmp[(size_t)c * h->M + m];
+  static_assert(sizeof(long long) == sizeof(int64_t), "counter width");
+  if (counters) CK(cudaMemcpy(counters, h->d_counters, (size_t)h->M * LWFB_NCOUNTERS * sizeof(int64_t), cudaMemcpyDeviceToHost));
+  return LWFB_OK;
+}
+
+extern "C" int lwfb_set_observations(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_day, int32_t n_obs_layers,
+                                     const int32_t* obs_layer, const double* obs_theta, const double* obs_d18o) {
+  if (!h || n_obs_days < 0) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  cudaFree(h->d_obs_of_rec); cudaFree(h->d_obs_layer); cudaFree(h->d_obs_theta); cudaFree(h->d_obs_d18o);
+  h->d_obs_of_rec = h->d_obs_layer = nullptr; h->d_obs_theta = h->d_obs_d18o = nullptr;
+  h->n_obs_days = h->n_obs_layers = 0; h->sums_valid = false;
+  if (n_obs_days == 0) return LWFB_OK;                 // observations cleared
+  if (n_obs_layers < 1 || !obs_day || !obs_layer || (!obs_theta && !obs_d18o)) return LWFB_ERR_ARG;
+  std::vector<int32_t> of_rec((size_t)h->o.n_days + 1, -1);
+  for (int k = 0; k < n_obs_days; k++) {
+    if (obs_day[k] < 0 || obs_day[k] > h->o.n_days) { h->err = "obs_day out of range"; return LWFB_ERR_ARG; }
+    if (k > 0 && obs_day[k] <= obs_day[k - 1]) { h->err = "obs_day must be strictly increasing"; return LWFB_ERR_ARG; }
+    of_rec[(size_t)obs_day[k]] = k;
   }
+  for (int l = 0; l < n_obs_layers; l++)
+    if (obs_layer[l] < 0 || obs_layer[l] >= h->o.n_layers) { h->err = "obs_layer out of range"; return LWFB_ERR_ARG; }
+  const size_t nobs = (size_t)n_obs_days * n_obs_layers;
+  CK(cudaMalloc(&h->d_obs_of_rec, of_rec.size() * sizeof(int32_t)));
+  CK(cudaMalloc(&h->d_obs_layer, (size_t)n_obs_layers * sizeof(int32_t)));
+  CK(cudaMemcpy(h->d_obs_of_rec, of_rec.data(), of_rec.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_obs_layer, obs_layer, (size_t)n_obs_layers * sizeof(int32_t), cudaMemcpyHostToDevice));
+  if (obs_theta) {
+    CK(cudaMalloc(&h->d_obs_theta, nobs * sizeof(double)));
+    CK(cudaMemcpy(h->d_obs_theta, obs_theta, nobs * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  if (obs_d18o) {
+    CK(cudaMalloc(&h->d_obs_d18o, nobs * sizeof(double)));
+    CK(cudaMemcpy(h->d_obs_d18o, obs_d18o, nobs * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  h->n_obs_days = n_obs_days; h->n_obs_layers = n_obs_layers;
   return LWFB_OK;
 }
 
 extern "C" int lwfb_scores_device(lwfb_handle* h, int32_t n_obs_days, const int32_t* obs_day, int32_t n_obs_layers,
                                   const int32_t* obs_layer, const double* obs_theta, const double* obs_d18o,
                                   double** d_scores) {
-  if (!h || !h->ran || n_obs_days < 1 || n_obs_layers < 1 || !obs_day || !obs_layer) return LWFB_ERR_ARG;
-  if (!h->d_rec) { h->err = "scores need the daily record (record_daily = 1)"; return LWFB_ERR_ARG; }
+  if (!h || !h->ran || n_obs_days < 0) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  { int rc = ensure_done(h); if (rc) return rc; }
+  const unsigned grid = (unsigned)((h->M + 255) / 256);
+  if (n_obs_days == 0) {
+    // scores of the observations registered BEFORE the run: the integrator accumulated the sums itself
+    if (!h->sums_valid) { h->err = "no observations were registered (lwfb_set_observations) before the run"; return LWFB_ERR_ARG; }
+    score_finalize_kernel<<<grid, 256>>>(h->d_sacc, h->M, h->d_scores);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    if (d_scores) *d_scores = h->d_scores;
+    return LWFB_OK;
+  }
+  if (n_obs_layers < 1 || !obs_day || !obs_layer) return LWFB_ERR_ARG;
+  if (!h->d_rec) { h->err = "without the daily record (record_daily = 0) register the observations before the run: lwfb_set_observations, then lwfb_scores with n_obs_days = 0"; return LWFB_ERR_ARG; }
   for (int k = 0; k < n_obs_days; k++)
     if (obs_day[k] < 0 || obs_day[k] > h->o.n_days) { h->err = "obs_day out of range"; return LWFB_ERR_ARG; }
   for (int l = 0; l < n_obs_layers; l++)
     if (obs_layer[l] < 0 || obs_layer[l] >= h->o.n_layers) { h->err = "obs_layer out of range"; return LWFB_ERR_ARG; }
-  CK(cudaSetDevice(h->o.device));
   size_t nobs = (size_t)n_obs_days * n_obs_layers;
   size_t bytes = sizeof(int32_t) * (n_obs_days + n_obs_layers) + 2 * nobs * sizeof(double) + 64;
   int rc = ensure_stage(h, bytes);
   if (rc) return rc;
+  if (!h->d_sacc_rec) CK(cudaMalloc(&h->d_sacc_rec, (size_t)h->M * 2 * LWFB_SA * sizeof(double)));
   char* p = (char*)h->d_stage;
   double* d_th = (double*)p; p += nobs * sizeof(double);
   double* d_18 = (double*)p; p += nobs * sizeof(double);
@@ -743,9 +785,9 @@ extern "C" int lwfb_scores_device(lwfb_handle* h, int32_t n_obs_days, const int3
   CK(cudaMemcpy(d_day, obs_day, n_obs_days * sizeof(int32_t), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_layer, obs_layer, n_obs_layers * sizeof(int32_t), cudaMemcpyHostToDevice));
   DevData d = make_dev(h);
-  unsigned grid = (unsigned)((h->M + 255) / 256);
-  score_kernel<<<grid, 256>>>(d, n_obs_days, d_day, n_obs_layers, d_layer, obs_theta ? d_th : nullptr,
-                              obs_d18o ? d_18 : nullptr, h->d_scores);
+  score_sums_kernel<<<grid, 256>>>(d, n_obs_days, d_day, n_obs_layers, d_layer, obs_theta ? d_th : nullptr,
+                                   obs_d18o ? d_18 : nullptr, h->d_sacc_rec);
+  score_finalize_kernel<<<grid, 256>>>(h->d_sacc_rec, h->M, h->d_scores);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
   if (d_scores) *d_scores = h->d_scores;
@@ -854,6 +896,6 @@ extern "C" int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on) {
 extern "C" int lwfb_set_placement(lwfb_handle* h, int32_t mode) {
   if (!h || mode < 0 || mode > 2) return LWFB_ERR_ARG;
   h->placement = mode;
-  if (mode == 0) h->perm_valid = false;
+  h->perm_valid = false; h->cost_valid = false;      // the next run starts cold
   return LWFB_OK;
 }

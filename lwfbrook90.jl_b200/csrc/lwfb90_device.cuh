@@ -51,16 +51,19 @@ __device__ __forceinline__ double div_z(double a, double b) {
 struct DevData {
   int64_t M;        // members
   int N, iso, t0_day, n_days, n_rows, L;
-  const double* __restrict__ scal;   // [LWFB_PS][M]
-  const double* __restrict__ lay;    // [LWFB_PL][N][M]
+  // Device layouts are MEMBER-MAJOR, i.e. the ABI's own layouts (no transposes at the boundary): everything that belongs
+  // to a member is contiguous, so a member's reads and writes fill whole 32-byte sectors wherever the placement
+  // permutation has put it (round 1 kept [field][member] arrays: one sector per 8-byte access once members are permuted).
+  const double* __restrict__ scal;   // [M][LWFB_PS]
+  const double* __restrict__ lay;    // [M][LWFB_PL][N]
   const double* __restrict__ forc;   // [n_sites][n_rows][LWFB_F]
   const int32_t* __restrict__ site;  // [M]
   const int32_t* __restrict__ perm;  // [M] placement: slot -> member (null: identity); see lwfb_set_placement
-  const double* __restrict__ u0;     // [L][M]
-  double* __restrict__ rec;          // [n_days+1][L][M]  (may be null: no daily record)
-  double* __restrict__ fin;          // [L][M] final state (always written)
+  const double* __restrict__ u0;     // [M][L]
+  double* __restrict__ rec;          // [M][n_days+1][L]  (may be null: no daily record) = the layout lwfb_get_daily returns
+  double* __restrict__ fin;          // [M][L] final state (always written)
   int32_t* __restrict__ status;      // [M]
-  long long* __restrict__ counters;  // [LWFB_NCOUNTERS][M]
+  long long* __restrict__ counters;  // [M][LWFB_NCOUNTERS]
   double reltol, abstol, dt_init, dtmax;
   long long maxiters;
   // work-quantum execution of the lane kernel (lwfb_run): a launch ends after `iter_budget` passes of the block loop,
@@ -77,8 +80,36 @@ struct DevData {
   int cb_wait;                       // bounded waiting at the day boundary, in passes (LWFB_CB_WAIT)
   long long n_slots;                 // slots in use: perm[0 .. n_slots) are the members of this launch (0: all M)
   int resume;                        // 1: continue from fin / ck
-  double* __restrict__ ck;           // [LWFB_CK + LWFB_CKL * N][M] checkpoint block (null: single launch, nothing saved)
+  double* __restrict__ ck;           // [M][LWFB_CK + LWFB_CKL * N] checkpoint block (null: single launch, nothing saved)
+  // goodness-of-fit sums accumulated by the integrator itself at the observation days (lwfb_set_observations): scores
+  // without a resident daily record.  n_obs_layers == 0: off.
+  int n_obs_layers;
+  const int32_t* __restrict__ obs_of_rec;   // [n_days+1] row of the observation tables for daily record r, -1: none
+  const int32_t* __restrict__ obs_layer;    // [n_obs_layers] 0-based layers
+  const double* __restrict__ obs_theta;     // [n_obs_days][n_obs_layers] (null: not scored), NaN = missing
+  const double* __restrict__ obs_d18o;      // likewise
+  double* __restrict__ sacc;                // [M][2][LWFB_SA] running sums, theta then delta18O
 };
+// running sums of one scored variable, in the order they are accumulated: days outer, observed layers inner
+enum { LWFB_SA_N = 0, LWFB_SA_SE, LWFB_SA_SO, LWFB_SA_SS, LWFB_SA_SOO, LWFB_SA_SSS, LWFB_SA_SOS, LWFB_SA };
+__host__ __device__ __forceinline__ void score_add(double* a, double sim, double o) {
+  if (o != o) return;
+  const double e = sim - o;
+  a[LWFB_SA_N] += 1; a[LWFB_SA_SE] += e * e; a[LWFB_SA_SO] += o; a[LWFB_SA_SS] += sim; a[LWFB_SA_SOO] += o * o;
+  a[LWFB_SA_SSS] += sim * sim; a[LWFB_SA_SOS] += o * sim;
+}
+// RMSE and Kling-Gupta efficiency from the sums
+__host__ __device__ __forceinline__ void score_finish(const double* a, double* rmse, double* kge) {
+  *rmse = NAN; *kge = NAN;
+  const double n = a[LWFB_SA_N];
+  if (n > 0) {
+    *rmse = sqrt(a[LWFB_SA_SE] / n);
+    const double mo = a[LWFB_SA_SO] / n, ms = a[LWFB_SA_SS] / n;
+    const double vo = a[LWFB_SA_SOO] / n - mo * mo, vs = a[LWFB_SA_SSS] / n - ms * ms, cov = a[LWFB_SA_SOS] / n - mo * ms;
+    const double r = cov / sqrt(vo * vs), al = sqrt(vs / vo), be = ms / mo;
+    *kge = 1 - sqrt((r - 1) * (r - 1) + (al - 1) * (al - 1) + (be - 1) * (be - 1));
+  }
+}
 // rows of the checkpoint block: member level, then LWFB_CKL rows per layer
 enum { LWFB_CK_DT = 0, LWFB_CK_QOLD, LWFB_CK_ITER, LWFB_CK_NACCEPT, LWFB_CK_NREJECT, LWFB_CK_NF, LWFB_CK_REC, LWFB_CK_T,
        LWFB_CK_TSTOP, LWFB_CK_FLAGS, LWFB_CK_RS, LWFB_CK_SLVP, LWFB_CK_SUMT, LWFB_CK_SUMT_V, LWFB_CK_D0_18O, LWFB_CK_D0_2H,
@@ -127,8 +158,8 @@ struct Member {
   long long nf;
   int status;
 
-  __device__ __forceinline__ double S(int k) const { return __ldg(scal + (int64_t)k * M + m); }
-  __device__ __forceinline__ double Lp(int k, int i) const { return __ldg(lay + ((int64_t)k * N + i) * M + m); }
+  __device__ __forceinline__ double S(int k) const { return __ldg(scal + m * LWFB_PS + k); }
+  __device__ __forceinline__ double Lp(int k, int i) const { return __ldg(lay + (m * LWFB_PL + k) * N + i); }
 
   __device__ void load(const DevData& d, int64_t mm) {
     m = mm; M = d.M; N = NT > 0 ? NT : d.N; scal = d.scal; lay = d.lay;
@@ -648,14 +679,14 @@ struct DayState {
 // MSBPREINT :382-507, PLNTRES src/module_EVP.jl:144-190, CANOPY_* src/module_PET.jl:193-258,
 // ROUGH :325-366, WEATHER :429-480, SNOVAP src/module_SNO.jl:166-183, SNOENRGY :223-234, FRSS
 // src/module_PET.jl:873-888.
-// read-only view of one member's parameter blocks ([field][member] layout)
+// read-only view of one member's parameter blocks (member-major layout)
 struct ParamView {
   int N;
   int64_t m, M;
   const double* __restrict__ scal;
   const double* __restrict__ lay;
-  __device__ __forceinline__ double S(int k) const { return __ldg(scal + (int64_t)k * M + m); }
-  __device__ __forceinline__ double Lp(int k, int i) const { return __ldg(lay + ((int64_t)k * N + i) * M + m); }
+  __device__ __forceinline__ double S(int k) const { return __ldg(scal + m * LWFB_PS + k); }
+  __device__ __forceinline__ double Lp(int k, int i) const { return __ldg(lay + (m * LWFB_PL + k) * N + i); }
 };
 
 // Core of the daily callback: everything after the soil state (psim of the top layer, psiti[], kk[]) is

@@ -138,8 +138,10 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
   const ParamView pv{N, m, M, d.scal, d.lay};
   const double* __restrict__ forc = d.forc + (int64_t)__ldg(d.site + m) * d.n_rows * LWFB_F;
   double* const fin = d.fin;
-  auto U0 = [&](int j) { return __ldg(d.u0 + (int64_t)j * M + m); };
-  auto FIN = [&](int j) -> double& { return fin[(int64_t)j * M + m]; };
+  // member-major blocks: the member's state vector / checkpoint rows are contiguous, lanes i, i+1, ... of a group touch
+  // neighbouring words
+  auto U0 = [&](int j) { return __ldg(d.u0 + m * L + j); };
+  auto FIN = [&](int j) -> double& { return fin[m * L + j]; };
   auto bcast = [&](double v, int layer) { return __shfl_sync(LFULL, v, base + layer); };
 
   // ---- per-lane constants -> shared-memory column
@@ -186,8 +188,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 
   // ---- live state: fin := u0 (then kept current at day boundaries); registers for what evolves per step
   const bool resume = d.resume != 0;                 // continue from the checkpoint of the previous launch
-  auto CKP = [&](int r) -> double& { return d.ck[(int64_t)r * M + m]; };
-  auto CKL = [&](int r) -> double& { return d.ck[(int64_t)(LWFB_CK + r * N + i) * M + m]; };   // per-layer rows
+  const int ck_rows = LWFB_CK + LWFB_CKL * N;
+  auto CKP = [&](int r) -> double& { return d.ck[m * ck_rows + r]; };
+  auto CKL = [&](int r) -> double& { return d.ck[m * ck_rows + LWFB_CK + r * N + i]; };   // per-layer rows
   if (live && !resume) for (int j = i; j < L; j += N) FIN(j) = U0(j);
   __syncwarp(LFULL);
   double y = FIN(ix.SWATI + i), G = FIN(ix.GWAT);
@@ -242,6 +245,27 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     dp[1] = __ldg(forc + (int64_t)r * LWFB_F + LWFB_F_D2H);
   };
 
+  // goodness-of-fit sums at the observation days (lwfb_set_observations), from what daily record r holds: theta of the
+  // observed layers from SWATI, delta18O.  Called by the whole warp; `mine`: the lane's member saves record r now.
+  // Same expressions and the same order (days outer, layers inner) as score_sums_kernel uses on a resident record.
+  auto score_rec = [&](int r, bool mine, double sw_i, double d18_i) {
+    if (d.n_obs_layers == 0) return;                 // (uniform)
+    const int ko = mine ? __ldg(d.obs_of_rec + r) : -1;
+    if (!__any_sync(LFULL, ko >= 0)) return;
+    const double DTH = LC(KC_DTH), THR = LC(KC_THR);
+    const double w_ = jminc((LC(KC_THSAT) * sw_i / LC(KC_SWATMAX) - THR) / DTH, 1.0);
+    const double th_ = w_ * DTH + THR;
+    double* a = d.sacc + m * (2 * LWFB_SA);
+    for (int l = 0; l < d.n_obs_layers; l++) {
+      const int il = __ldg(d.obs_layer + l);
+      const double s_th = bcast(th_, il), s_d = bcast(d18_i, il);
+      if (ko >= 0 && top && live) {
+        if (d.obs_theta) score_add(a, s_th, __ldg(d.obs_theta + (int64_t)ko * d.n_obs_layers + l));
+        if (d.obs_d18o && iso) score_add(a + LWFB_SA, s_d, __ldg(d.obs_d18o + (int64_t)ko * d.n_obs_layers + l));
+      }
+    }
+  };
+
   const double qmin = 0.2, qmax = 10.0, gamma = 0.9, beta1 = 0.14, beta2 = 0.08, qoldinit = 1e-4;
   const double t0 = (double)d.t0_day, tend = (double)(d.t0_day + d.n_days);
   double t = resume ? CKP(LWFB_CK_T) : t0, tstop = resume ? CKP(LWFB_CK_TSTOP) : t0;
@@ -270,8 +294,10 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
   unsigned dbg_day_iter0 = 0;
 #endif
 
-  if (d.rec && live && !resume) for (int j = i; j < L; j += N) d.rec[(int64_t)j * M + m] = U0(j);     // record 0 = raw u0
+  double* const rec_m = d.rec ? d.rec + m * (int64_t)(d.n_days + 1) * L : nullptr;   // the member's records [n_days+1][L]
+  if (d.rec && live && !resume) for (int j = i; j < L; j += N) rec_m[j] = U0(j);     // record 0 = raw u0
   __syncwarp(LFULL);
+  if (!resume) score_rec(0, true, U0(ix.SWATI + i), iso ? U0(ix.SWATI + N + i) : 0.0);
 
   for (;;) {
     const bool active = (status == LWFB_ST_OK) && (t < tend);
@@ -735,10 +761,12 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 #endif
       __syncwarp(LFULL);
       double bs = 0, bt = 0, Wt = 0;
+      score_rec(rec, at_stop, y, LC(KC_DS_18O));
       if (at_stop) {
         if (d.rec && live) {
-          double* __restrict__ dst = d.rec + (int64_t)rec * L * M;
-          for (int j = i; j < L; j += N) dst[(int64_t)j * M + m] = FIN(j);
+          // 8 L contiguous bytes per member-day; the lanes of the group write neighbouring words, L2 merges the sectors
+          double* __restrict__ dst = rec_m + (int64_t)rec * L;
+          for (int j = i; j < L; j += N) dst[j] = FIN(j);
         }
         rec++;
         if (t < tend) {
@@ -841,23 +869,35 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         CKP(LWFB_CK_D0_18O) = LC(KC_D0_18O); CKP(LWFB_CK_D0_2H) = LC(KC_D0_2H);
       }
     }
+    if (d.n_obs_layers > 0 && top && status != LWFB_ST_OK && status_in == LWFB_ST_OK) {
+      // ... and so are its simulated values at the observation days it did not reach
+      double* a = d.sacc + m * (2 * LWFB_SA);
+      for (int r = rec; r <= d.n_days; r++) {
+        const int ko = __ldg(d.obs_of_rec + r);
+        if (ko < 0) continue;
+        for (int l = 0; l < d.n_obs_layers; l++) {
+          if (d.obs_theta) score_add(a, NAN, __ldg(d.obs_theta + (int64_t)ko * d.n_obs_layers + l));
+          if (d.obs_d18o && iso) score_add(a + LWFB_SA, NAN, __ldg(d.obs_d18o + (int64_t)ko * d.n_obs_layers + l));
+        }
+      }
+    }
     if (d.rec && status != LWFB_ST_OK && status_in == LWFB_ST_OK) {
       // the member ended in this launch before the end of the record: the records it did not reach are NaN
       for (; rec <= d.n_days; rec++) {
-        double* dst = d.rec + (int64_t)rec * L * M;
-        for (int j = i; j < L; j += N) dst[(int64_t)j * M + m] = NAN;
+        double* dst = rec_m + (int64_t)rec * L;
+        for (int j = i; j < L; j += N) dst[j] = NAN;
       }
     }
     flush_state();
     if (top) {
       d.status[m] = status;
-      d.counters[(int64_t)LWFB_C_NACCEPT * M + m] = naccept;
+      d.counters[m * LWFB_NCOUNTERS + LWFB_C_NACCEPT] = naccept;
 #ifdef LWFB_DEBUG_ITERS
-      d.counters[(int64_t)LWFB_C_NREJECT * M + m] = dbg_iters;
+      d.counters[m * LWFB_NCOUNTERS + LWFB_C_NREJECT] = dbg_iters;
 #else
-      d.counters[(int64_t)LWFB_C_NREJECT * M + m] = nreject;
+      d.counters[m * LWFB_NCOUNTERS + LWFB_C_NREJECT] = nreject;
 #endif
-      d.counters[(int64_t)LWFB_C_NF * M + m] = nf;
+      d.counters[m * LWFB_NCOUNTERS + LWFB_C_NF] = nf;
     }
   }
   return by_budget;

@@ -38,14 +38,13 @@ template <int NT>
 __device__ void integrate_member(const DevData& d, const int64_t m) {
   constexpr int NMAX = Member<NT>::NMAX;
   constexpr int NEMAX = NMAX + 9;
-  const int64_t M = d.M;
   Member<NT> mb;
   mb.load(d, m);
   const int N = mb.N, NE = N + 9, L = d.L;
   const bool iso = d.iso != 0;
   const SIdx ix(N, d.iso);
   const double* __restrict__ forc = d.forc + (int64_t)__ldg(d.site + m) * d.n_rows * LWFB_F;
-  auto U0 = [&](int j) { return __ldg(d.u0 + (int64_t)j * M + m); };
+  auto U0 = [&](int j) { return __ldg(d.u0 + m * L + j); };
 
   // ---- evolving state y = (SWATI[N], GWAT, 8 integrated accumulators) and the rest of u
   double y[NEMAX], yprev[NEMAX], k[7][NEMAX];
@@ -69,7 +68,7 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
 
   // writes the full reference-order state record (src/func_DiffEq_definition_u0.jl:42-73)
   auto write_record = [&](double* __restrict__ dst) {
-    auto W = [&](int j, double v) { dst[(int64_t)j * M + m] = v; };
+    auto W = [&](int j, double v) { dst[j] = v; };
     for (int i = 0; i < N; i++) W(ix.SWATI + i, y[i]);
     W(ix.GWAT, y[N]); W(ix.INTS, ds.INTS); W(ix.INTR, ds.INTR); W(ix.SNOW, ds.SNOW);
     W(ix.RWU, RWUst); W(ix.XYLEM, XYmm); W(ix.CC, ds.CC); W(ix.SNOWLQ, ds.SNOWLQ);
@@ -87,6 +86,23 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
     for (int j = 0; j < 3 * N; j++) W(ix.AUX + j, U0(ix.AUX + j));  // aux is never written after init
     for (int a = 0; a < LWFB_NACCUM; a++) W(ix.ACC + a, ds.acc[a]);
     for (int q = 0; q < 8; q++) W(ix.ACC + kAccPos[q], y[N + 1 + q]);
+  };
+  // goodness-of-fit sums at the observation days (lwfb_set_observations), from what daily record r holds
+  auto score_rec = [&](int r, bool reached) {
+    if (d.n_obs_layers == 0) return;
+    const int ko = __ldg(d.obs_of_rec + r);
+    if (ko < 0) return;
+    double* a = d.sacc + m * (2 * LWFB_SA);
+    for (int l = 0; l < d.n_obs_layers; l++) {
+      const int il = __ldg(d.obs_layer + l);
+      const double sw = reached ? (r == 0 ? U0(ix.SWATI + il) : y[il]) : NAN;
+      const double dth = mb.THSAT[il] - mb.THR[il];
+      const double w = jminc((mb.THSAT[il] * sw / mb.SWATMAX[il] - mb.THR[il]) / dth, 1.0);
+      if (d.obs_theta) score_add(a, reached ? w * dth + mb.THR[il] : NAN, __ldg(d.obs_theta + (int64_t)ko * d.n_obs_layers + l));
+      if (d.obs_d18o && iso)
+        score_add(a + LWFB_SA, reached ? (r == 0 ? U0(ix.SWATI + N + il) : is.dS[0][il]) : NAN,
+                  __ldg(d.obs_d18o + (int64_t)ko * d.n_obs_layers + l));
+    }
   };
   // delta of precipitation at time t: the value of forcing row r holds for t in (r-0.5, r+0.5]
   auto prec_delta = [&](double t, double* dp) {
@@ -111,18 +127,14 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
   int status = LWFB_ST_OK;
 
   // ---- init: save u0, initial_affect of the daily callbacks, FSAL
-  if (d.rec) write_record(d.rec);
+  double* const rec_m = d.rec ? d.rec + m * (int64_t)(d.n_days + 1) * L : nullptr;   // [n_days+1][L] of this member
+  if (d.rec) write_record(rec_m);
+  score_rec(0, true);
   cb_amounts<NT>(mb, forc + (int64_t)d.t0_day * LWFB_F, t0, y, ds, TRANIst, RWUst);
   for (int q = 0; q < 8; q++) y[N + 1 + q] = 0.0;
   cb_deltas(t0);
   for (int j = 0; j < NE; j++) yprev[j] = y[j];
   mb.rhs(yprev, yprev[N], t, k[0]);
-#ifdef LWFB_DBG
-  if (m == 0) {
-    printf("DBG y %g %g %g %g %g gw %g | SWATMAX %g %g | TRANI %g %g SLVP %g RNET %g SMLT %g | k0 %g %g %g %g %g %g st %d\n", y[0], y[1], y[2], y[3], y[4], y[5],
-           mb.SWATMAX[0], mb.SWATMAX[1], mb.TRANI[0], mb.TRANI[1], mb.SLVP, mb.RNET, mb.SMLT, k[0][0], k[0][1], k[0][2], k[0][3], k[0][4], k[0][5], mb.status);
-  }
-#endif
   double tstop = fmin(t0 + 1.0, tend);
   int rec = 1;
   status = mb.status;   // a failing initial callback stops the member before its first step
@@ -178,9 +190,6 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
       ss += r * r;
     }
     double EEst = sqrt(ss / (double)(3 * N + 39));
-#ifdef LWFB_DBG
-    if (m == 0 && iter <= 3) printf("DBG iter %lld t %g dt %g EEst %g y %g %g %g yprev %g %g k6 %g %g\n", iter, t, dt, EEst, y[0], y[1], y[2], yprev[0], yprev[1], k[6][0], k[6][1]);
-#endif
     // loopfooter!: PI controller
     reeval = false;
     double ttmp = t + dt;
@@ -204,7 +213,8 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
       if (iso) prec_delta(t, dp);
       if (t == tstop) {
         // the record is saved before the callbacks of this instant (and before this step's ADE update)
-        if (d.rec) write_record(d.rec + (int64_t)rec * L * M);
+        if (d.rec) write_record(rec_m + (int64_t)rec * L);
+        score_rec(rec, true);
         rec++;
         if (t < tend) {
           // LWFBrook90R_check_balance_errors! src/func_DiffEq_definition_cb.jl:1255-1314
@@ -238,15 +248,16 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
     }
     if (mb.status != LWFB_ST_OK) { status = mb.status; break; }
   }
+  for (int r = rec; r <= d.n_days; r++) score_rec(r, false);
   if (d.rec) {
     for (; rec <= d.n_days; rec++)
-      for (int j = 0; j < L; j++) d.rec[((int64_t)rec * L + j) * M + m] = NAN;
+      for (int j = 0; j < L; j++) rec_m[(int64_t)rec * L + j] = NAN;
   }
-  write_record(d.fin);
+  write_record(d.fin + m * L);
   d.status[m] = status;
-  d.counters[(int64_t)LWFB_C_NACCEPT * M + m] = naccept;
-  d.counters[(int64_t)LWFB_C_NREJECT * M + m] = nreject;
-  d.counters[(int64_t)LWFB_C_NF * M + m] = mb.nf;
+  d.counters[m * LWFB_NCOUNTERS + LWFB_C_NACCEPT] = naccept;
+  d.counters[m * LWFB_NCOUNTERS + LWFB_C_NREJECT] = nreject;
+  d.counters[m * LWFB_NCOUNTERS + LWFB_C_NF] = mb.nf;
 }
 
 }  // namespace lwfb

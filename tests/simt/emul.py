@@ -51,6 +51,33 @@ def _p(a, t=_dp):
     return a.ctypes.data_as(t)
 
 
+def set_observations(n_days, obs_day=None, obs_layer=None, obs_theta=None, obs_d18o=None):
+    """The emulator's lwfb_set_observations: the following runs accumulate the score sums (score_sums())."""
+    L = lib()
+    L.lwfb_emul_set_obs.argtypes = [C.c_int, C.c_int, _ip, C.c_int, _ip, _dp, _dp]
+    L.lwfb_emul_set_obs.restype = None
+    if obs_day is None:
+        z = np.zeros(1, dtype=np.int32)
+        L.lwfb_emul_set_obs(int(n_days), 0, _p(z, _ip), 0, _p(z, _ip), None, None)
+        return
+    od = np.ascontiguousarray(obs_day, dtype=np.int32)
+    ol = np.ascontiguousarray(obs_layer, dtype=np.int32)
+    th = None if obs_theta is None else np.ascontiguousarray(obs_theta, dtype=np.float64)
+    d18 = None if obs_d18o is None else np.ascontiguousarray(obs_d18o, dtype=np.float64)
+    L.lwfb_emul_set_obs(int(n_days), len(od), _p(od, _ip), len(ol), _p(ol, _ip), None if th is None else _p(th),
+                        None if d18 is None else _p(d18))
+
+
+def score_sums(M):
+    """[M][2][7] running sums (n, se, so, ss, soo, sss, sos for theta and delta18O) of the last run."""
+    L = lib()
+    L.lwfb_emul_get_sums.argtypes = [_dp, C.c_int64]
+    L.lwfb_emul_get_sums.restype = None
+    out = np.zeros((M, 2, 7))
+    L.lwfb_emul_get_sums(_p(out), out.size)
+    return out
+
+
 def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, *, reltol=1e-5, abstol=1e-6,
         dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000, n_threads=8, perm=None, seg_len=0, resort=False,
         warps_per_block=1):

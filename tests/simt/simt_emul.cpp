@@ -236,16 +236,27 @@ void* worker(void* p) {
   return nullptr;
 }
 
-template <typename T>
-void to_soa(const T* src, T* dst, int64_t M, int64_t K) {   // [M][K] -> [K][M]
-  for (int64_t m = 0; m < M; m++)
-    for (int64_t k = 0; k < K; k++) dst[k * M + m] = src[m * K + k];
-}
 }  // namespace
 
 // profiling aid: stage barriers executed by thread 0 of all blocks since the last call (6 or 7 per step pass of a block)
 extern "C" long lwfb_emul_stage_syncs() { return simt::g_stage_syncs.exchange(0); }
 extern "C" long lwfb_emul_votes() { return simt::g_votes.exchange(0); }
+
+// observations scored during the following runs (the emulator's lwfb_set_observations) and the sums of the last run
+static std::vector<int32_t> g_obs_of_rec, g_obs_layer;
+static std::vector<double> g_obs_theta, g_obs_d18o, g_sacc;
+extern "C" void lwfb_emul_set_obs(int n_days, int n_obs_days, const int32_t* obs_day, int n_obs_layers, const int32_t* obs_layer,
+                                  const double* obs_theta, const double* obs_d18o) {
+  g_obs_of_rec.assign((size_t)n_days + 1, -1);
+  for (int k = 0; k < n_obs_days; k++) g_obs_of_rec[(size_t)obs_day[k]] = k;
+  g_obs_layer.assign(obs_layer, obs_layer + n_obs_layers);
+  const size_t n = (size_t)n_obs_days * n_obs_layers;
+  g_obs_theta.clear(); g_obs_d18o.clear();
+  if (n_obs_days > 0 && obs_theta) g_obs_theta.assign(obs_theta, obs_theta + n);
+  if (n_obs_days > 0 && obs_d18o) g_obs_d18o.assign(obs_d18o, obs_d18o + n);
+  if (n_obs_days == 0) g_obs_layer.clear();
+}
+extern "C" void lwfb_emul_get_sums(double* out, int64_t n) { for (int64_t k = 0; k < n && k < (int64_t)g_sacc.size(); k++) out[k] = g_sacc[(size_t)k]; }
 
 extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days, int n_sites, int n_rows,
                              const double* forcing, int64_t M, const int32_t* site_of_member, const double* scal,
@@ -257,18 +268,22 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   (void)n_sites;
   const int L = LWFB_STATE_LEN(N, iso);
   if (kernel == 0 && (N < 3 || N > 32)) return -1;
-  std::vector<double> s_scal((size_t)M * LWFB_PS), s_lay((size_t)M * LWFB_PL * N), s_u0((size_t)M * L);
-  std::vector<double> rec((size_t)M * L * (n_days + 1)), fin((size_t)M * L);
-  std::vector<long long> cnt((size_t)M * LWFB_NCOUNTERS);
-  to_soa(scal, s_scal.data(), M, (int64_t)LWFB_PS);
-  to_soa(lay, s_lay.data(), M, (int64_t)LWFB_PL * N);
-  to_soa(u0, s_u0.data(), M, (int64_t)L);
+  // the device layouts are member-major = the layouts of the arguments: the kernels read and write them in place
+  std::vector<double> fin((size_t)M * L);
+  static_assert(sizeof(long long) == sizeof(int64_t), "counter width");
   Job job;
   lwfb::DevData& d = job.d;
   d.M = M; d.N = N; d.iso = iso; d.t0_day = t0_day; d.n_days = n_days; d.n_rows = n_rows; d.L = L;
-  d.scal = s_scal.data(); d.lay = s_lay.data(); d.forc = forcing; d.site = site_of_member; d.perm = perm; d.u0 = s_u0.data();
-  d.rec = rec.data(); d.fin = fin.data(); d.status = status; d.counters = cnt.data();
+  d.scal = scal; d.lay = lay; d.forc = forcing; d.site = site_of_member; d.perm = perm; d.u0 = u0;
+  d.rec = out_daily; d.fin = fin.data(); d.status = status; d.counters = (long long*)counters;
   d.reltol = reltol; d.abstol = abstol; d.dt_init = dt_init; d.dtmax = dtmax; d.maxiters = maxiters;
+  g_sacc.assign((size_t)M * 2 * lwfb::LWFB_SA, 0.0);
+  const bool with_obs = !g_obs_layer.empty() && (int)g_obs_of_rec.size() == n_days + 1;
+  d.n_obs_layers = with_obs ? (int)g_obs_layer.size() : 0;
+  d.obs_of_rec = g_obs_of_rec.data(); d.obs_layer = g_obs_layer.data();
+  d.obs_theta = g_obs_theta.empty() ? nullptr : g_obs_theta.data();
+  d.obs_d18o = g_obs_d18o.empty() ? nullptr : g_obs_d18o.data();
+  d.sacc = g_sacc.data();
   job.kernel = kernel;
   if (warps_per_block < 1 || warps_per_block > MAX_WARPS) return 4;
   job.warps = warps_per_block;
@@ -277,7 +292,8 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   if (n_threads < 1) n_threads = 1;
   // work-quantum execution as in lwfb_run: a launch ends after `seg_len` passes of the block loop (here: of the warp
   // loop), the unfinished members are regrouped by progress (resort) and the next launch resumes them from fin + ck
-  std::vector<double> ck((size_t)(lwfb::LWFB_CK + lwfb::LWFB_CKL * N) * M);
+  const size_t ck_rows = (size_t)(lwfb::LWFB_CK + lwfb::LWFB_CKL * N);
+  std::vector<double> ck(ck_rows * M);
   std::vector<int32_t> perm2((size_t)M);
   const bool quanta = kernel == 0 && seg_len > 0;
   d.ck = quanta ? ck.data() : nullptr;
@@ -302,21 +318,15 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
     if (!quanta) break;
     int64_t left = 0;
     for (int64_t i = 0; i < M; i++)
-      if (status[i] == LWFB_ST_OK && ck[(size_t)lwfb::LWFB_CK_T * M + i] < tend) perm2[(size_t)left++] = (int32_t)i;
+      if (status[i] == LWFB_ST_OK && ck[(size_t)i * ck_rows + lwfb::LWFB_CK_T] < tend) perm2[(size_t)left++] = (int32_t)i;
     if (left == 0) break;
     d.resume = 1;
     if (resort) {
       std::stable_sort(perm2.begin(), perm2.begin() + left, [&](int32_t a, int32_t b) {
-        return ck[(size_t)lwfb::LWFB_CK_T * M + a] < ck[(size_t)lwfb::LWFB_CK_T * M + b]; });
+        return ck[(size_t)a * ck_rows + lwfb::LWFB_CK_T] < ck[(size_t)b * ck_rows + lwfb::LWFB_CK_T]; });
       d.perm = perm2.data();
       d.n_slots = left;
     }
   }
-  // [day][L][M] -> [M][day][L]
-  const int64_t K = (int64_t)(n_days + 1) * L;
-  for (int64_t m = 0; m < M; m++)
-    for (int64_t k = 0; k < K; k++) out_daily[m * K + k] = rec[(size_t)k * M + m];
-  for (int64_t m = 0; m < M; m++)
-    for (int c = 0; c < LWFB_NCOUNTERS; c++) counters[m * LWFB_NCOUNTERS + c] = cnt[(size_t)c * M + m];
   return 0;
 }

@@ -194,8 +194,9 @@ def test_adaptive_placement_is_result_neutral(dav_full):
     ens = en.make_ensemble(dav_full, 300)
     h, sub, nd = gpu_run(ens, 150)
     first = h.get_daily(); st1, cnt1 = h.get_status()
-    h.set_placement(2)                        # mode 1 sorts only launches of several waves; 2 sorts always
-    h.run()                                   # placement now sorted by the first run's RHS counts
+    h.set_placement(2)                        # mode 1 sorts only launches of several waves; 2 sorts always (and forgets
+    h.run()                                   # the first run: this one is cold, in work quanta) ...
+    h.run()                                   # ... and this one starts sorted by the previous run's RHS counts
     second = h.get_daily(); st2, cnt2 = h.get_status()
     assert np.array_equal(first, second, equal_nan=True) and np.array_equal(st1, st2) and np.array_equal(cnt1, cnt2)
     h.set_placement(0); h.run()
@@ -509,3 +510,73 @@ def test_soil_state_on_device(dav_full, bea):
         idx = api.get_soil_idx(sim, [100, 500], only_valid_idxs=True)
         assert np.array_equal(by_depth, res.soil_state(days, layers=[i - 1 for i in idx]), equal_nan=True)
         res.close()
+
+
+def test_scores_accumulated_by_the_integrator(isobea, monkeypatch):
+    """lwfb_set_observations: scores without the resident daily record (record_daily = 0) are bit-identical to the
+    scores formed from the record, in a single launch and in work quanta, with a member that aborts."""
+    ens = en.make_ensemble(isobea, 40)
+    ens.u0[7, 3] = np.nan                     # member 7: NaN in SWATI -> Unstable
+    nd = 60
+    obs_day = np.array([0, 3, 10, 11, 30, 59, 60], dtype=np.int32)
+    obs_layer = np.array([0, 3, 6], dtype=np.int32)
+    rng = np.random.default_rng(11)
+    th = 0.25 + 0.05 * rng.random((len(obs_day), 3)); d18 = -10 + rng.random((len(obs_day), 3))
+    th[2, 1] = np.nan; d18[5, 2] = np.nan
+    # (a) from the record
+    h, sub, _ = gpu_run(ens, nd)
+    want = h.scores(obs_day, obs_layer, th, d18)
+    st_a, _ = h.get_status()
+    h.close()
+    assert st_a[7] == lo.ST.UNSTABLE and np.isnan(want[7]).all() and np.isfinite(np.delete(want, 7, axis=0)).all()
+    # (b) accumulated during the run, no record; single launch and quanta of 5 passes with regrouping
+    for quantum in (0, 5):
+        monkeypatch.setenv("LWFB_QUANTUM", str(quantum))
+        h = capi.Handle(ens.N, ens.iso, ens.t0_day, nd, record_daily=False)
+        h.set_placement(2)
+        h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+        with pytest.raises(capi.LwfbError, match="lwfb_set_observations"):
+            h.run(); h.scores()
+        with pytest.raises(capi.LwfbError, match="record_daily"):
+            h.scores(obs_day, obs_layer, th, d18)
+        h.set_observations(obs_day, obs_layer, th, d18)
+        h.run()
+        got = h.scores()
+        assert np.array_equal(got, want, equal_nan=True), quantum
+        h.run()                               # a second run starts its sums afresh
+        assert np.array_equal(h.scores(), want, equal_nan=True)
+        h.close()
+    # the thread-per-member kernel accumulates the same sums
+    h = capi.Handle(ens.N, ens.iso, ens.t0_day, nd, record_daily=False)
+    h.force_legacy(True)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    h.set_observations(obs_day, obs_layer, th, d18)
+    h.run()
+    assert np.array_equal(h.scores(), want, equal_nan=True)
+    h.close()
+
+
+def test_getters_wait_for_an_asynchronous_run(dav_full):
+    """lwfb_run_async on a caller's non-blocking stream followed directly by a getter: the getter synchronises."""
+    import torch
+    ens = en.make_ensemble(dav_full, 600)
+    nd = 40
+    h, sub, _ = gpu_run(ens, nd)
+    want = h.get_daily(); st_w, cnt_w = h.get_status()
+    h.close()
+    h = capi.Handle(ens.N, ens.iso, ens.t0_day, nd)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    s = torch.cuda.Stream()
+    h.run_async(s.cuda_stream)
+    st, cnt = h.get_status()                  # no lwfb_sync in between
+    assert np.array_equal(st, st_w) and np.array_equal(cnt, cnt_w)
+    h.run_async(s.cuda_stream)
+    got = h.get_daily()
+    assert np.array_equal(got, want, equal_nan=True)
+    # a pinned destination takes the direct path, a large pageable one the staged path: same bytes
+    pinned = torch.empty(want.shape, dtype=torch.float64).pin_memory()
+    h.get_daily(out=pinned.numpy())
+    assert np.array_equal(pinned.numpy(), want, equal_nan=True)
+    with pytest.raises(capi.LwfbError, match="get_daily"):
+        h.get_daily(out=np.empty((3, 3)))
+    h.close()

@@ -188,3 +188,61 @@ def test_emulator_rejects_divergent_warp_primitives():
     """The emulator aborts when lanes meet at different warp primitives; a well-formed run reports none.  (The
     abort path itself is exercised by the build of every kernel change: a divergent shuffle never gets here.)"""
     assert os.path.exists(emul.build())
+
+
+def _score_sums_numpy(rec, lay, iso, N, obs_day, obs_layer, obs_theta, obs_d18o):
+    """Sequential restatement of score_add over (days outer, layers inner) on a daily record [M][n_days+1][L]."""
+    M = rec.shape[0]
+    out = np.zeros((M, 2, 7))
+    for m in range(M):
+        for k, dday in enumerate(obs_day):
+            for l, i in enumerate(obs_layer):
+                ths, thr, smax = lay[m, lo.L.THSAT, i], lay[m, lo.L.THR, i], lay[m, lo.L.SWATMAX, i]
+                dth = ths - thr
+                x = (ths * rec[m, dday, i] / smax - thr) / dth
+                w = x if not (x >= 1.0) else 1.0
+                sims = [(w * dth + thr, obs_theta[k, l])]
+                if iso:
+                    sims.append((rec[m, dday, N + i], obs_d18o[k, l]))
+                for v, (sim, o) in enumerate(sims):
+                    if o != o:
+                        continue
+                    e = sim - o
+                    a = out[m, v]
+                    a[0] += 1; a[1] += e * e; a[2] += o; a[3] += sim; a[4] += o * o; a[5] += sim * sim; a[6] += o * sim
+    return out
+
+
+@pytest.mark.parametrize("seg_len", [0, 7])
+def test_score_sums_accumulated_by_the_integrator(dav_full, seg_len):
+    """lwfb_set_observations: the sums the lane kernel accumulates at the observation days (no record needed) equal,
+    bit for bit, the sums formed from the daily record afterwards - in one launch and in work quanta, for members
+    that finish and for one that aborts (its unreached observation days count as NaN, like its NaN records)."""
+    ens = en.make_ensemble(dav_full, 9)
+    nd = 12
+    ens.u0[4, 2] = np.nan            # member 4: NaN in SWATI -> Unstable at its first step
+    obs_day = np.array([0, 3, 4, 9, 12], dtype=np.int32)
+    obs_layer = np.array([0, 2, 4], dtype=np.int32)
+    rng = np.random.default_rng(5)
+    th = 0.2 + 0.05 * rng.random((5, 3)); d18 = -11 + rng.random((5, 3))
+    th[1, 2] = np.nan; d18[3, 0] = np.nan
+    emul.set_observations(nd, obs_day, obs_layer, th, d18)
+    try:
+        rec, st, cnt = emul.run(emul.LANES, ens.N, ens.iso, ens.t0_day, nd, ens.forcing, ens.site_of_member, ens.scal,
+                                ens.lay, ens.u0, seg_len=seg_len, resort=2 if seg_len else False, warps_per_block=2)
+        got = emul.score_sums(ens.M)
+    finally:
+        emul.set_observations(nd)
+    assert st[4] != 0 and (np.delete(st, 4) == 0).all()
+    want = _score_sums_numpy(rec, ens.lay, ens.iso, ens.N, obs_day, obs_layer, th, d18)
+    assert np.array_equal(got, want, equal_nan=True)
+    assert np.isnan(got[4, :, 1]).all() and np.isfinite(np.delete(got, 4, axis=0)).all()
+    # the thread-per-member kernel accumulates the same sums
+    emul.set_observations(nd, obs_day, obs_layer, th, d18)
+    try:
+        rec2, _, _ = emul.run(emul.MEMBER, ens.N, ens.iso, ens.t0_day, nd, ens.forcing, ens.site_of_member, ens.scal,
+                              ens.lay, ens.u0)
+        got2 = emul.score_sums(ens.M)
+    finally:
+        emul.set_observations(nd)
+    assert np.array_equal(rec2, rec, equal_nan=True) and np.array_equal(got2, want, equal_nan=True)
