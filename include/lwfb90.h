@@ -193,6 +193,24 @@ int lwfb_set_sites(lwfb_handle* h, int32_t n_sites, int32_t n_rows, const double
 int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t* site_of_member,
                      const double* scal, const double* lay, const double* u0);
 
+/* replaces remakeSPAC -> setup of every member (src/LWFBrook90.jl:214-345, :365-587: define_LWFB90_p, the
+ * KPT_SOILPAR_Mvg1d constructor with its bisection, init_LWFB90_u0!) ON THE DEVICE: the member blocks are built in HBM
+ * from ONE base member (the blocks lwfb_set_members would take for the unmodified site definition) and a row of knob
+ * values per member, so only the knobs cross the bus.  Layouts and arithmetic: include/lwfb90_setup.h.
+ *   site_of_member [n_members] or NULL (all members on site 0)
+ *   knobs          [n_members][LWFB_K + n_over]   NaN = keep the base value
+ *   over_idx       [n_over]   LWFB_S_* indices of the scalar columns that follow the LWFB_K fixed columns
+ *   profiles       [n_profiles][2 N + 1]   root profiles (RELDEN[N], TINI[N], RELDEN_CONST) selected by LWFB_K_ROOTPROFILE
+ *   psim_base      [N]   initial matric potential of the soil discretisation (kPa)
+ *   ilayer         number of layers that receive infiltration (IDEPTH)
+ *   n_invalid      (optional) members for which no field-capacity wetness exists (the reference throws for those)
+ * Equivalent to lwfb_set_members with the blocks that lwfb_setup_member() produces on the host. */
+int lwfb_setup_members(lwfb_handle* h, int64_t n_members, const int32_t* site_of_member,
+                       const double* base_scal, const double* base_lay, const double* base_u0,
+                       const double* knobs, int32_t n_over, const int32_t* over_idx,
+                       int32_t n_profiles, const double* profiles, const double* psim_base, int32_t ilayer,
+                       int32_t* n_invalid);
+
 /* replaces solve(prob), src/LWFBrook90.jl:643.  Integrates every member over tspan with
  * Tsit5 + PI controller + daily / per-step callbacks (src/func_DiffEq_definition_cb.jl:11-57).
  * Synchronous; if cuda_stream != NULL it is the cudaStream_t to launch on (still synchronised

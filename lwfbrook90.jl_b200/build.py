@@ -15,8 +15,12 @@ _OBJ = os.path.join(_HERE, "_obj")
 # host replay (oracle mode B); the elementary functions use explicit fma().
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-Xcompiler", "-fPIC"]
-# translation units: (source, extra flags); two units so that they compile in parallel
-UNITS = [("lwfb90.cu", []), ("lwfb90_member.cu", [])]
+# translation units: (source, extra flags); two units so that they compile in parallel.
+# lwfb90_member.cu (thread-per-member fallback, not on the measured path) is built with NVVM -O1: at -O3 nvcc 12.9 has
+# produced wrong results in this kernel twice (round 1: a select between the addresses of two local arrays; round 2:
+# isoBEA2016 member 22 goes NaN in its first step while -O1, -O0, the host build of the same text and the lane kernel agree
+# with the oracle bit for bit, tools/legacy_diag.py).  Both builds are checked against the oracle by the GPU tests.
+UNITS = [("lwfb90.cu", []), ("lwfb90_member.cu", ["-Xcicc", "-O1"])]
 
 
 def _deps():

@@ -38,7 +38,7 @@ SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error"
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
            "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
            "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy", "lwfb_set_placement",
-           "lwfb_water_partitioning", "lwfb_soil_state", "lwfb_set_observations"]
+           "lwfb_water_partitioning", "lwfb_soil_state", "lwfb_set_observations", "lwfb_setup_members"]
 
 
 def lib():
@@ -65,6 +65,8 @@ def lib():
         L.lwfb_scores_device.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp, C.POINTER(vp)]
         L.lwfb_scores_device.restype = C.c_int
         L.lwfb_set_observations.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp]; L.lwfb_set_observations.restype = C.c_int
+        L.lwfb_setup_members.argtypes = [vp, C.c_int64, _ip, _dp, _dp, _dp, _dp, C.c_int32, _ip, C.c_int32, _dp, _dp, C.c_int32, _ip]
+        L.lwfb_setup_members.restype = C.c_int
         L.lwfb_eval_rhs.argtypes = [vp, C.c_double, _dp, _dp, _dp, _dp, _dp]; L.lwfb_eval_rhs.restype = C.c_int
         L.lwfb_last_run_stats.argtypes = [vp, _ip, C.POINTER(C.c_float)]; L.lwfb_last_run_stats.restype = C.c_int
         L.lwfb_elem_eval.argtypes = [C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp]; L.lwfb_elem_eval.restype = C.c_int
@@ -157,6 +159,33 @@ class Handle:
         som = np.ascontiguousarray(site_of_member, dtype=np.int32).reshape(M)
         self._ck(self._L.lwfb_set_members(self._h, M, _p(som, _ip), _p(scal), _p(lay), _p(u0)))
         self.M = M
+
+    def setup_members(self, kb, site_of_member=None):
+        """Batched setup ON THE DEVICE (lwfb_setup_members): kb is an ensemble.KnobBlock - the base member and one row of
+        knob values per member; the member blocks are built in HBM.  Returns the number of invalid members."""
+        knobs = _f64(kb.knobs)
+        M = knobs.shape[0]
+        bs, bl, bu = _f64(kb.base_scal), _f64(kb.base_lay), _f64(kb.base_u0)
+        assert bs.shape == (lo.NPS,) and bl.shape == (lo.NPL, self.N) and bu.shape == (self.L,)
+        oi = np.ascontiguousarray(kb.over_idx, dtype=np.int32)
+        assert knobs.shape[1] == 8 + len(oi)
+        pr = _f64(kb.profiles).reshape(-1, 2 * self.N + 1)
+        ps = _f64(kb.psim_base)
+        som = None if site_of_member is None else np.ascontiguousarray(site_of_member, dtype=np.int32).reshape(M)
+        n_inv = C.c_int32()
+        self._ck(self._L.lwfb_setup_members(self._h, M, None if som is None else _p(som, _ip), _p(bs), _p(bl), _p(bu), _p(knobs),
+                                            len(oi), _p(oi, _ip) if len(oi) else None, pr.shape[0],
+                                            _p(pr) if pr.size else None, _p(ps), int(kb.ilayer), C.byref(n_inv)))
+        self.M = M
+        return int(n_inv.value)
+
+    def get_block(self, which: int):
+        """Testing aid: copy of a device-resident member block (0 scal, 1 lay, 2 u0)."""
+        shape = {0: (self.M, lo.NPS), 1: (self.M, lo.NPL, self.N), 2: (self.M, self.L)}[which]
+        out = np.empty(shape)
+        self._L.lwfb_debug_get_block.argtypes = [C.c_void_p, C.c_int32, _dp]
+        self._ck(self._L.lwfb_debug_get_block(self._h, int(which), _p(out)))
+        return out
 
     def run(self, stream=None):
         self._ck(self._L.lwfb_run(self._h, C.c_void_p(stream) if stream else None))

@@ -26,6 +26,7 @@
 #include "lwfb90_lanes.cuh"
 #include "lwfb90_launch.h"
 #include "lwfb90_post.cuh"
+#include "lwfb90_setup.cuh"
 
 using namespace lwfb;
 
@@ -92,9 +93,7 @@ __global__ void score_sums_kernel(DevData d, int n_obs_days, const int32_t* __re
         const double ths = __ldg(d.lay + (m * LWFB_PL + LWFB_L_THSAT) * N + i);
         const double thr = __ldg(d.lay + (m * LWFB_PL + LWFB_L_THR) * N + i);
         const double smax = __ldg(d.lay + (m * LWFB_PL + LWFB_L_SWATMAX) * N + i);
-        const double dth = ths - thr;
-        const double w = jminc((ths * r[i] / smax - thr) / dth, 1.0);
-        score_add(a, w * dth + thr, obs_theta[(int64_t)k * n_obs_layers + l]);
+        score_add(a, score_theta(ths, thr, smax, r[i]), obs_theta[(int64_t)k * n_obs_layers + l]);
       }
       if (obs_d18o && d.iso) score_add(a + LWFB_SA, r[N + i], obs_d18o[(int64_t)k * n_obs_layers + l]);
     }
@@ -206,6 +205,7 @@ struct lwfb_handle {
   } while (0)
 
 static int ensure_done(lwfb_handle* h);
+static int alloc_members(lwfb_handle* h, int64_t n_members);
 static int download(lwfb_handle* h, void* dst, const void* src, size_t bytes);
 
 static int ensure_stage(lwfb_handle* h, size_t bytes) {
@@ -288,35 +288,7 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
     if (site_of_member[i] < 0 || site_of_member[i] >= h->n_sites) { h->err = "site index out of range"; return LWFB_ERR_ARG; }
   CK(cudaSetDevice(h->o.device));
   const int N = h->o.n_layers, L = h->L;
-  if (n_members != h->M) {
-    free_members(h);
-    int64_t M = n_members;
-    CK(cudaMalloc(&h->d_scal, (size_t)M * LWFB_PS * sizeof(double)));
-    CK(cudaMalloc(&h->d_lay, (size_t)M * LWFB_PL * N * sizeof(double)));
-    CK(cudaMalloc(&h->d_u0, (size_t)M * L * sizeof(double)));
-    CK(cudaMalloc(&h->d_fin, (size_t)M * L * sizeof(double)));
-    CK(cudaMalloc(&h->d_site, (size_t)M * sizeof(int32_t)));
-    CK(cudaMalloc(&h->d_status, (size_t)M * sizeof(int32_t)));
-    CK(cudaMalloc(&h->d_counters, (size_t)M * LWFB_NCOUNTERS * sizeof(long long)));
-    CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
-    CK(cudaMalloc(&h->d_sacc, (size_t)M * 2 * LWFB_SA * sizeof(double)));
-    CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
-    CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + LWFB_CKL * N) * sizeof(double)));
-    CK(cudaMalloc(&h->d_stop, 2 * sizeof(int)));
-    CK(cudaMalloc(&h->d_key, (size_t)M * sizeof(uint32_t)));
-    CK(cudaMalloc(&h->d_key2, (size_t)M * sizeof(uint32_t)));
-    CK(cudaMalloc(&h->d_idx, (size_t)M * sizeof(int32_t)));
-    CK(cudaMalloc(&h->d_nleft, sizeof(int)));
-    h->sort_tmp_bytes = 0;
-    CK(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_tmp_bytes, h->d_key, h->d_key2, h->d_idx, h->d_perm, (int)M));
-    CK(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes ? h->sort_tmp_bytes : 16));
-    if (h->o.record_daily) {
-      size_t bytes = (size_t)M * (h->o.n_days + 1) * L * sizeof(double);
-      cudaError_t e = cudaMalloc(&h->d_rec, bytes);
-      if (e != cudaSuccess) { h->err = "cannot allocate the daily record (" + std::to_string(bytes >> 20) + " MiB)"; free_members(h); return LWFB_ERR_NOMEM; }
-    }
-    h->M = M;
-  }
+  { int rc = alloc_members(h, n_members); if (rc) return rc; }
   CK(cudaMemcpy(h->d_site, site_of_member, (size_t)h->M * sizeof(int32_t), cudaMemcpyHostToDevice));
   // the device blocks are member-major like the ABI's: plain copies, no transposes
   CK(cudaMemcpy(h->d_scal, scal, (size_t)h->M * LWFB_PS * sizeof(double), cudaMemcpyHostToDevice));
@@ -324,6 +296,100 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
   CK(cudaMemcpy(h->d_u0, u0, (size_t)h->M * L * sizeof(double), cudaMemcpyHostToDevice));
   h->ran = false; h->sums_valid = false;
   h->cost_valid = false; h->perm_valid = false;   // counters / placement of the previous members say nothing about these
+  return LWFB_OK;
+}
+
+// device blocks of an ensemble of n_members members (re)allocated; h->M set
+static int alloc_members(lwfb_handle* h, int64_t n_members) {
+  const int N = h->o.n_layers, L = h->L;
+  if (n_members == h->M) return LWFB_OK;
+  free_members(h);
+  int64_t M = n_members;
+  CK(cudaMalloc(&h->d_scal, (size_t)M * LWFB_PS * sizeof(double)));
+  CK(cudaMalloc(&h->d_lay, (size_t)M * LWFB_PL * N * sizeof(double)));
+  CK(cudaMalloc(&h->d_u0, (size_t)M * L * sizeof(double)));
+  CK(cudaMalloc(&h->d_fin, (size_t)M * L * sizeof(double)));
+  CK(cudaMalloc(&h->d_site, (size_t)M * sizeof(int32_t)));
+  CK(cudaMalloc(&h->d_status, (size_t)M * sizeof(int32_t)));
+  CK(cudaMalloc(&h->d_counters, (size_t)M * LWFB_NCOUNTERS * sizeof(long long)));
+  CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
+  CK(cudaMalloc(&h->d_sacc, (size_t)M * 2 * LWFB_SA * sizeof(double)));
+  CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
+  CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + LWFB_CKL * N) * sizeof(double)));
+  CK(cudaMalloc(&h->d_stop, 2 * sizeof(int)));
+  CK(cudaMalloc(&h->d_key, (size_t)M * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->d_key2, (size_t)M * sizeof(uint32_t)));
+  CK(cudaMalloc(&h->d_idx, (size_t)M * sizeof(int32_t)));
+  CK(cudaMalloc(&h->d_nleft, sizeof(int)));
+  h->sort_tmp_bytes = 0;
+  CK(cub::DeviceRadixSort::SortPairs(nullptr, h->sort_tmp_bytes, h->d_key, h->d_key2, h->d_idx, h->d_perm, (int)M));
+  CK(cudaMalloc(&h->d_sort_tmp, h->sort_tmp_bytes ? h->sort_tmp_bytes : 16));
+  if (h->o.record_daily) {
+    size_t bytes = (size_t)M * (h->o.n_days + 1) * L * sizeof(double);
+    cudaError_t e = cudaMalloc(&h->d_rec, bytes);
+    if (e != cudaSuccess) { h->err = "cannot allocate the daily record (" + std::to_string(bytes >> 20) + " MiB)"; free_members(h); return LWFB_ERR_NOMEM; }
+  }
+  h->M = M;
+  return LWFB_OK;
+}
+
+// replaces remakeSPAC -> setup for every member (src/LWFBrook90.jl:214-345, :365-587): builds the member blocks ON THE
+// DEVICE from one base member and a knob row per member (include/lwfb90_setup.h); only the knobs cross the bus
+extern "C" int lwfb_setup_members(lwfb_handle* h, int64_t n_members, const int32_t* site_of_member, const double* base_scal,
+                                  const double* base_lay, const double* base_u0, const double* knobs, int32_t n_over,
+                                  const int32_t* over_idx, int32_t n_profiles, const double* profiles,
+                                  const double* psim_base, int32_t ilayer, int32_t* n_invalid) {
+  if (!h || n_members < 1 || !base_scal || !base_lay || !base_u0 || !knobs || n_over < 0 || (n_over > 0 && !over_idx) ||
+      n_profiles < 0 || (n_profiles > 0 && !profiles) || !psim_base)
+    return LWFB_ERR_ARG;
+  if (!h->d_forc) { h->err = "lwfb_set_sites must be called first"; return LWFB_ERR_ARG; }
+  if (site_of_member)
+    for (int64_t i = 0; i < n_members; i++)
+      if (site_of_member[i] < 0 || site_of_member[i] >= h->n_sites) { h->err = "site index out of range"; return LWFB_ERR_ARG; }
+  for (int j = 0; j < n_over; j++)
+    if (over_idx[j] < 0 || over_idx[j] >= LWFB_PS) { h->err = "scalar index out of range"; return LWFB_ERR_ARG; }
+  CK(cudaSetDevice(h->o.device));
+  const int N = h->o.n_layers, L = h->L;
+  int rc = alloc_members(h, n_members);
+  if (rc) return rc;
+  const int64_t M = h->M;
+  if (site_of_member) CK(cudaMemcpy(h->d_site, site_of_member, (size_t)M * sizeof(int32_t), cudaMemcpyHostToDevice));
+  else CK(cudaMemset(h->d_site, 0, (size_t)M * sizeof(int32_t)));
+  // small inputs in one staging block: base blocks, index list, root profiles, initial potentials; then the knob rows
+  const size_t n_small = (size_t)LWFB_PS + (size_t)LWFB_PL * N + L + (size_t)n_profiles * (2 * N + 1) + N;
+  const size_t knob_doubles = (size_t)M * (LWFB_K + n_over);
+  rc = ensure_stage(h, (n_small + knob_doubles) * sizeof(double) + (size_t)(n_over + 2) * sizeof(int32_t));
+  if (rc) return rc;
+  double* p = h->d_stage;
+  double* d_bs = p; p += LWFB_PS;
+  double* d_bl = p; p += (size_t)LWFB_PL * N;
+  double* d_bu = p; p += L;
+  double* d_pr = p; p += (size_t)n_profiles * (2 * N + 1);
+  double* d_ps = p; p += N;
+  double* d_kn = p; p += knob_doubles;
+  int32_t* d_oi = (int32_t*)p;
+  CK(cudaMemcpy(d_bs, base_scal, LWFB_PS * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_bl, base_lay, (size_t)LWFB_PL * N * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_bu, base_u0, (size_t)L * sizeof(double), cudaMemcpyHostToDevice));
+  if (n_profiles > 0) CK(cudaMemcpy(d_pr, profiles, (size_t)n_profiles * (2 * N + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_ps, psim_base, (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_kn, knobs, knob_doubles * sizeof(double), cudaMemcpyHostToDevice));
+  if (n_over > 0) CK(cudaMemcpy(d_oi, over_idx, (size_t)n_over * sizeof(int32_t), cudaMemcpyHostToDevice));
+  setup_members_kernel<<<(unsigned)((M + 127) / 128), 128>>>(M, N, h->o.simulate_isotopes, d_bs, d_bl, d_bu, d_kn, n_over, d_oi,
+                                                              n_profiles, d_pr, d_ps, ilayer, h->d_scal, h->d_lay, h->d_u0,
+                                                              h->d_status);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  if (n_invalid) {
+    // members without a field-capacity wetness (the reference throws "Computed invalid p_WETF" for those)
+    std::vector<int32_t> st((size_t)M);
+    CK(cudaMemcpy(st.data(), h->d_status, (size_t)M * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    int32_t n = 0;
+    for (int64_t i = 0; i < M; i++) n += st[(size_t)i] != LWFB_ST_OK;
+    *n_invalid = n;
+  }
+  h->ran = false; h->sums_valid = false;
+  h->cost_valid = false; h->perm_valid = false;
   return LWFB_OK;
 }
 

@@ -25,6 +25,26 @@ __device__ constexpr double p_WTOMJ = 0.0864, p_ETOM = 0.4085, p_CPRHO = 1240., 
                             p_RHOWG = 0.00981, p_SIGMA = 5.67E-08, p_SC = 1367., p_K = 0.4,
                             p_PI = 3.1416, p_DTIMIN = 1.e-9;
 
+// Divisions by run constants (layer thicknesses, SWATMAX, theta_s - theta_r, rho g, 1000, the isotope ratios ...): x / c
+// costs ~20 instructions on the FP64 pipe and ncu showed 15 % of all executed instructions to be divisions.
+//  * In the WATER path (right-hand side, soil state of the callback) the quotient is formed from the reciprocal
+//    rc = 1 / c, which the lane kernel computes once per launch, with one correction step (Markstein): q = x rc,
+//    r = x - c q (exact, fma), q + r rc.  That IS the correctly rounded x / c for finite operands (0 mismatches against
+//    the hardware division on 3e8 random and near-midpoint operand pairs; the sign of a zero quotient may differ), so the
+//    step-size decisions - the chaotic part of the algorithm - see the reference's values.  Infinite / NaN dividends
+//    (log K = -inf of a dry layer) take the plain product, which has the quotient's value.
+//  * In the ISOTOPE step, whose results feed nothing back into the water balance or the step-size control, the plain
+//    product x * rc is used (LWFB_RCP): at most one ulp from x / c.
+// The CPU oracle's device-arithmetic build (mode B, -DLWFB_ORACLE_ELEM) forms both the same way, bit for bit.
+#define LWFB_RCP(c) (1.0 / (c))
+__host__ __device__ __forceinline__ double div_c(double x, double c, double rc) {
+  const double q = x * rc;
+  const double r = fma(-c, q, x);
+  const double e = fma(r, rc, q);
+  return (fabs(x) < INFINITY) ? e : q;
+}
+__host__ __device__ __forceinline__ double div_c(double x, double c) { return div_c(x, c, LWFB_RCP(c)); }
+
 // Julia min/max propagate NaN (fmin/fmax do not)
 __device__ __forceinline__ double jmin(double a, double b) { return (a != a || b != b) ? NAN : (a < b ? a : b); }
 __device__ __forceinline__ double jmax(double a, double b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
@@ -97,6 +117,15 @@ __host__ __device__ __forceinline__ void score_add(double* a, double sim, double
   const double e = sim - o;
   a[LWFB_SA_N] += 1; a[LWFB_SA_SE] += e * e; a[LWFB_SA_SO] += o; a[LWFB_SA_SS] += sim; a[LWFB_SA_SOO] += o * o;
   a[LWFB_SA_SSS] += sim * sim; a[LWFB_SA_SOS] += o * sim;
+}
+// simulated theta of a layer from its SWATI as a daily record holds it (FTheta_MvG of the clamped wetness).  Out of line
+// on purpose: the integrators (which score during the run) and the kernel that scores a resident record must produce the
+// same bits, and one compiled body guarantees it whatever the optimiser does with the surrounding code (round 2: inlined
+// into the thread-per-member integrator, NVVM -O3 produced sums that differed in the last bit from the other two places).
+static __device__ __noinline__ double score_theta(double ths, double thr, double smax, double sw) {
+  const double dth = ths - thr;
+  const double w = jminc((ths * sw / smax - thr) / dth, 1.0);
+  return w * dth + thr;
 }
 // RMSE and Kling-Gupta efficiency from the sums
 __host__ __device__ __forceinline__ void score_finish(const double* a, double* rmse, double* kge) {
@@ -194,7 +223,7 @@ struct Member {
   // derive_auxiliary_SOILVAR! src/module_KPT.jl:445-464 (FPSIM_MvG! :596-605, FK_MvG! :502-509,
   // FTheta_MvG! :692-696) for one layer
   __device__ __forceinline__ void soilvar1(int i, double sw, double& W, double& psim, double& theta, double& kk) const {
-    double w = jmin(1.0, (THSAT[i] * sw / SWATMAX[i] - THR[i]) / (THSAT[i] - THR[i]));
+    double w = jmin(1.0, div_c(div_c(THSAT[i] * sw, SWATMAX[i]) - THR[i], THSAT[i] - THR[i]));
     W = w;
     double a = jmax(w, 1.e-6);
     double la = m_log(a);
@@ -260,10 +289,10 @@ struct Member {
       for (int i = 0; i < N - 1; i++) {
         if (fabs(psiti[i] - psiti[i + 1]) < DPSIMAX) V0[i] = 0;
         else {
-          double kkmean = m_exp((THICK[i + 1] * lk[i] + THICK[i] * lk[i + 1]) / (THICK[i] + THICK[i + 1]));
+          double kkmean = m_exp(div_c(THICK[i + 1] * lk[i] + THICK[i] * lk[i + 1], THICK[i] + THICK[i + 1]));
           kkmean = jmin(jmin(kkmean, KSAT[i]), KSAT[i + 1]);
-          double grad = (psiti[i] - psiti[i + 1]) / ((THICK[i] + THICK[i + 1]) / 2.0);
-          V0[i] = (grad * kkmean / p_RHOWG) * (1.0 - (STONEF[i] + STONEF[i + 1]) / 2.0);
+          double grad = div_c(psiti[i] - psiti[i + 1], (THICK[i] + THICK[i + 1]) / 2.0);
+          V0[i] = div_c(grad * kkmean, p_RHOWG) * (1.0 - (STONEF[i] + STONEF[i + 1]) / 2.0);
         }
       }
       V0[N - 1] = (DRAIN > 0.00001) ? DRAIN * kk[N - 1] * (1 - STONEF[N - 1]) : 0.0;
@@ -278,7 +307,7 @@ struct Member {
       DTINEW = jmin(DTINEW, 0.01 * DSWMAX * THICK[i] * THSAT[i] * (1 - STONEF[i]) / jmax(0.000001, fabs(NTFLI[i])));
       double avail = (THR[i] - theta[i]) * THICK[i];
       if (NTFLI[i] < 0) {
-        DTINEW = jmin(DTINEW, avail / NTFLI[i] / 1.30);
+        DTINEW = jmin(DTINEW, div_c(avail / NTFLI[i], 1.30));
         if (DTINEW < p_DTIMIN) DTINEW = p_DTIMIN;
       }
     }
@@ -932,10 +961,10 @@ __device__ __forceinline__ void cb_amounts(Member<NT>& mb, const double* __restr
 
 // src/module_ISO.jl:36-37, :53-55
 __device__ constexpr double R18 = 2005.2e-6, R2H = 155.76e-6;
-__device__ __forceinline__ double d_to_x(double d, double R) { return 1 / (1 + 1 / (R * (d / 1000 + 1))); }
+__device__ __forceinline__ double d_to_x(double d, double R) { return 1 / (1 + 1 / (R * (d * LWFB_RCP(1000.0) + 1))); }
 __device__ __forceinline__ double x_to_d(double x, double R) { return (1 / (R * (1 / x - 1)) - 1) * 1000; }
 __device__ __forceinline__ double dxdt_to_dddt(double dxdt, double x, double R) {
-  return div_z(div_z(dxdt * 1, R) * 1, ((x - 1) * (x - 1))) * 1000;    // dxdt * 1 / R * 1 / (x-1)^2 * 1000
+  return div_z(dxdt * 1 * LWFB_RCP(R) * 1, ((x - 1) * (x - 1))) * 1000;    // dxdt * 1 / R * 1 / (x-1)^2 * 1000
 }
 
 // isotope state carried between steps: delta of SWATI[N], GWAT, RWU, XYLEM for 18O and 2H
@@ -957,7 +986,7 @@ __device__ __forceinline__ void ade_step(const Member<NT>& mb, IsoState<NT>& is,
   double th1[NMAX];
 #pragma unroll(NT > 0 ? NT : 1)
   for (int i = 0; i < N; i++) {
-    double w = jmin(1.0, (mb.THSAT[i] * S1[i] / mb.SWATMAX[i] - mb.THR[i]) / (mb.THSAT[i] - mb.THR[i]));
+    double w = jmin(1.0, div_c(div_c(mb.THSAT[i] * S1[i], mb.SWATMAX[i]) - mb.THR[i], mb.THSAT[i] - mb.THR[i]));
     th1[i] = w * (mb.THSAT[i] - mb.THR[i]) + mb.THR[i];
   }
   double Tk = mb.TA + 273.15;
@@ -970,8 +999,8 @@ __device__ __forceinline__ void ade_step(const Member<NT>& mb, IsoState<NT>& is,
   double tauth[NMAX], aq[NMAX];
 #pragma unroll(NT > 0 ? NT : 1)
   for (int i = 0; i < N; i++) {
-    tauth[i] = m_pow(th1[i], 7.0 / 3) / (mb.THSAT[i] * mb.THSAT[i]);
-    aq[i] = Lam * fabs(mb.VRFLI[i] / 1000);
+    tauth[i] = m_pow(th1[i], 7.0 / 3) * LWFB_RCP(mb.THSAT[i] * mb.THSAT[i]);
+    aq[i] = Lam * fabs(mb.VRFLI[i] * LWFB_RCP(1000.0));
   }
 #pragma unroll
   for (int s = 0; s < 2; s++) {
@@ -991,8 +1020,8 @@ __device__ __forceinline__ void ade_step(const Member<NT>& mb, IsoState<NT>& is,
     const double dzpad = 1.0;
 #pragma unroll(NT > 0 ? NT : 1)
     for (int i = 0; i < N; i++) {
-      double diff_upp = (i == 0) ? 0.0 : ((Dd[i - 1] + Dd[i]) / 2) * ((C[i] - C[i - 1]) / mb.Lp(LWFB_L_DZ, i - 1));
-      double diff_low = (i == N - 1) ? 0.0 : ((Dd[i] + Dd[i + 1]) / 2) * ((C[i + 1] - C[i]) / mb.Lp(LWFB_L_DZ, i));
+      double diff_upp = (i == 0) ? 0.0 : ((Dd[i - 1] + Dd[i]) / 2) * ((C[i] - C[i - 1]) * LWFB_RCP(mb.Lp(LWFB_L_DZ, i - 1)));
+      double diff_low = (i == N - 1) ? 0.0 : ((Dd[i] + Dd[i + 1]) / 2) * ((C[i + 1] - C[i]) * LWFB_RCP(mb.Lp(LWFB_L_DZ, i)));
       double qC_upp = (i == 0) ? 0.0 : mb.VRFLI[i - 1] * C[i - 1];
       double qC_low = mb.VRFLI[i] * C[i];
       double slv = (i == 0) ? Cslvp : 0.0;
@@ -1002,7 +1031,7 @@ __device__ __forceinline__ void ade_step(const Member<NT>& mb, IsoState<NT>& is,
       inner = inner - mb.DSFLI[i] * C[i];
       inner = inner - mb.SLVP * slv;
       inner = inner - mb.TRANI[i] * Ctr[i];
-      double dC = -C[i] / S1[i] * mb.NTFLI[i] + 1 / S1[i] * inner;
+      double dC = -C[i] * (1 / S1[i]) * mb.NTFLI[i] + 1 / S1[i] * inner;
       dd[i] = dxdt_to_dddt(dC, C[i], R);
     }
     (void)dzpad;

@@ -96,9 +96,9 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
     for (int l = 0; l < d.n_obs_layers; l++) {
       const int il = __ldg(d.obs_layer + l);
       const double sw = reached ? (r == 0 ? U0(ix.SWATI + il) : y[il]) : NAN;
-      const double dth = mb.THSAT[il] - mb.THR[il];
-      const double w = jminc((mb.THSAT[il] * sw / mb.SWATMAX[il] - mb.THR[il]) / dth, 1.0);
-      if (d.obs_theta) score_add(a, reached ? w * dth + mb.THR[il] : NAN, __ldg(d.obs_theta + (int64_t)ko * d.n_obs_layers + l));
+      if (d.obs_theta)
+        score_add(a, reached ? score_theta(mb.THSAT[il], mb.THR[il], mb.SWATMAX[il], sw) : NAN,
+                  __ldg(d.obs_theta + (int64_t)ko * d.n_obs_layers + l));
       if (d.obs_d18o && iso)
         score_add(a + LWFB_SA, reached ? (r == 0 ? U0(ix.SWATI + N + il) : is.dS[0][il]) : NAN,
                   __ldg(d.obs_d18o + (int64_t)ko * d.n_obs_layers + l));

@@ -28,6 +28,8 @@ uint64_t exchange(uint64_t v, int src_lane, int op_id);     // value of src_lane
 unsigned vote(bool p, int op_id);                           // ballot over the warp
 int lane_id();
 bool block_or(bool p, int op_id);                           // __syncthreads_or over the emulated thread block
+int block_count(bool p, int op_id);                         // __syncthreads_count
+void named_sync(int n_threads, int op_id);                  // bar.sync 1, n_threads (counted named barrier)
 int warps_per_block();                                      // warps the emulator runs as one thread block
 }  // namespace simt
 
@@ -55,6 +57,7 @@ template <typename T> static inline T simt_shfl(T v, int src, int op) { return s
 #define __syncwarp(mask) ((void)simt::vote(true, LWFB_OP_ID))
 #define __syncthreads_or(p) (simt::block_or((p) != 0, LWFB_OP_ID) ? 1 : 0)
 #define __syncthreads() ((void)simt::block_or(false, LWFB_OP_ID))
+#define __syncthreads_count(p) simt::block_count((p) != 0, LWFB_OP_ID)
 // redux.sync min over the lanes named in `mask` (every lane passes the mask of its own group)
 static inline unsigned simt_reduce_min(unsigned mask, unsigned v, int op) {
   unsigned r = 0xffffffffu;

@@ -225,9 +225,10 @@ def batched_setup(base: DiscretizedSPAC, *, ths_f=None, ksat_f=None, alpha_f=Non
                     site_of_member=np.zeros(M, np.int32), scal=scal, lay=lay, u0=u0)
 
 
-def make_ensemble(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member: int = 0) -> Ensemble:
-    """Members first_member .. first_member+M-1 of the synthetic ensemble of SURVEY.md section 8(d).
-    Global member 0 is the unmodified site definition."""
+def draw_knobs(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member: int = 0) -> dict:
+    """The perturbations of members first_member .. first_member+M-1 of the synthetic ensemble of SURVEY.md section
+    8(d) as keyword arguments of batched_setup (Philox4x32-10, key = seed, counter = global member index).  Global
+    member 0 is the unmodified site definition (neutral knobs; `keep` marks it)."""
     idx = np.arange(first_member, first_member + M, dtype=np.uint64)
     U = uniforms(idx, 20, seed)
     u = lambda j, a, b: a + (b - a) * U[:, j]
@@ -264,11 +265,93 @@ def make_ensemble(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member:
     df = base.parametrizedSPAC.soil_discretization["df"]
     psim_uniform = np.all(df["uAux_PSIM_init_kPa"] == df["uAux_PSIM_init_kPa"][0])
     psim = fix(u(19, -12.0, -3.0), df["uAux_PSIM_init_kPa"][0]) if psim_uniform else None
-    ens = batched_setup(base,
-                        ths_f=fix(u(0, 0.85, 1.15), 1.0), ksat_f=fix(logu(1, 1 / 3, 3.0), 1.0),
-                        alpha_f=fix(logu(2, 0.5, 2.0), 1.0), nm1_f=fix(u(3, 0.8, 1.25), 1.0),
-                        gravel_f=fix(u(4, 0.8, 1.2), 1.0), params=params, beta=beta, psim_init=psim)
+    return dict(ths_f=fix(u(0, 0.85, 1.15), 1.0), ksat_f=fix(logu(1, 1 / 3, 3.0), 1.0),
+                alpha_f=fix(logu(2, 0.5, 2.0), 1.0), nm1_f=fix(u(3, 0.8, 1.25), 1.0),
+                gravel_f=fix(u(4, 0.8, 1.2), 1.0), params=params, beta=beta, psim_init=psim, keep=keep)
+
+
+def make_ensemble(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member: int = 0) -> Ensemble:
+    """Members first_member .. first_member+M-1 of the synthetic ensemble of SURVEY.md section 8(d), built on the host
+    (numpy).  Global member 0 is the unmodified site definition."""
+    kn = draw_knobs(base, M, seed, first_member)
+    keep = kn.pop("keep")
+    ens = batched_setup(base, **kn)
     if keep.any():   # member 0 must be bit-identical to the base definition
         j = int(np.nonzero(keep)[0][0])
         ens.scal[j], ens.lay[j], ens.u0[j] = base.scal, base.lay, base.u0
     return ens
+
+
+@dataclass
+class KnobBlock:
+    """What lwfb_setup_members (include/lwfb90_setup.h) takes instead of finished member blocks: the base member and
+    one row of knob values per member - the batched setup then runs on the GPU."""
+    N: int
+    iso: bool
+    t0_day: int
+    n_days: int
+    forcing: np.ndarray          # [n_sites, n_rows, F]
+    base_scal: np.ndarray        # [PS]
+    base_lay: np.ndarray         # [PL, N]
+    base_u0: np.ndarray          # [L]
+    knobs: np.ndarray            # [M, K + n_over], NaN = keep the base value
+    over_idx: np.ndarray         # [n_over] int32, LWFB_S_* indices
+    profiles: np.ndarray         # [n_profiles, 2N+1]
+    psim_base: np.ndarray        # [N]
+    ilayer: int
+
+    @property
+    def M(self) -> int:
+        return self.knobs.shape[0]
+
+
+K_THS_F, K_KSAT_F, K_ALPHA_F, K_NM1_F, K_GRAVEL_F, K_INFEXP, K_ROOTPROFILE, K_PSIM_INIT, K_FIXED = range(9)
+
+
+def knob_block(base: DiscretizedSPAC, *, ths_f=None, ksat_f=None, alpha_f=None, nm1_f=None, gravel_f=None,
+               params=None, beta=None, psim_init=None, keep=None) -> KnobBlock:
+    """Same keyword arguments as batched_setup; returns the inputs of the DEVICE-side setup.  Members flagged in `keep`
+    get an all-NaN row (= the base member, bit for bit)."""
+    S = lo.S
+    some = [x for x in (ths_f, ksat_f, alpha_f, nm1_f, gravel_f, beta, psim_init) if x is not None]
+    params = dict(params or {})
+    some += list(params.values())
+    M = len(some[0]) if some else 1
+    infexp = params.pop("INFEXP", None)
+    names = list(params)
+    kb = np.full((M, K_FIXED + len(names)), np.nan)
+    for col, v in ((K_THS_F, ths_f), (K_KSAT_F, ksat_f), (K_ALPHA_F, alpha_f), (K_NM1_F, nm1_f), (K_GRAVEL_F, gravel_f),
+                   (K_INFEXP, infexp), (K_PSIM_INIT, psim_init)):
+        if v is not None:
+            kb[:, col] = np.asarray(v, float)
+    for j, name in enumerate(names):
+        kb[:, K_FIXED + j] = np.asarray(params[name], float)
+    N = base.N
+    profiles = np.zeros((0, 2 * N + 1))
+    if beta is not None:
+        rd = base.parametrizedSPAC.pars["root_distribution"]
+        zmax = rd.get("z_rootMax_m", None) if isinstance(rd, dict) else None
+        dz = base.parametrizedSPAC.soil_discretization["dz"]
+        par = base.parametrizedSPAC.pars["params"]
+        THICK = base.lay[lo.L.THICK]
+        ub, inv = np.unique(np.asarray(beta, float), return_inverse=True)
+        profiles = np.zeros((len(ub), 2 * N + 1))
+        for j, b in enumerate(ub):
+            prof, t_ini = root_growth_tini(THICK, Rootden_beta_(float(b), dz_m=dz, z_rootMax_m=zmax),
+                                           par["INITRDEP"], par["RGRORATE"], par["RGROPER"])
+            finite = t_ini[t_ini < 1e19]
+            const = par["RGROPER"] <= 0 or len(finite) == 0 or par["AGE_baseline_yrs"] > finite.max() + par["RGROPER"]
+            profiles[j, :N], profiles[j, N:2 * N], profiles[j, 2 * N] = prof, t_ini, 1.0 if const else 0.0
+        kb[:, K_ROOTPROFILE] = inv
+    if keep is not None:
+        kb[np.asarray(keep, bool)] = np.nan
+    df = base.parametrizedSPAC.soil_discretization["df"]
+    return KnobBlock(N=N, iso=base.iso, t0_day=base.t0_day, n_days=base.n_days, forcing=base.forcing[None].copy(),
+                     base_scal=base.scal.copy(), base_lay=base.lay.copy(), base_u0=base.u0.copy(), knobs=kb,
+                     over_idx=np.array([getattr(S, n) for n in names], dtype=np.int32), profiles=profiles,
+                     psim_base=np.asarray(df["uAux_PSIM_init_kPa"], float).copy(), ilayer=int(base.ILAYER))
+
+
+def make_knob_block(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member: int = 0) -> KnobBlock:
+    """The synthetic ensemble of make_ensemble as a knob block for the device-side setup."""
+    return knob_block(base, **draw_knobs(base, M, seed, first_member))

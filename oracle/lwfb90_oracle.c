@@ -41,6 +41,25 @@
 #define acos lwfb_acos
 #endif
 
+/* Mode B also forms the quotients by run constants the way the kernels do (csrc/lwfb90_device.cuh, div_c / LWFB_RCP):
+ * DIVX in the water path = product with the IEEE reciprocal plus one exact correction step (the correctly rounded
+ * quotient for finite operands), DIVC in the isotope step = plain product with the reciprocal.  Mode A divides, like
+ * the reference. */
+#if defined(LWFB_ORACLE_ELEM) && !defined(LWFB_ORACLE_NORCP)
+static double divx_(double x, double c) {
+  const double rc = 1.0 / c;
+  const double q = x * rc;
+  const double r = fma(-c, q, x);
+  const double e = fma(r, rc, q);
+  return (fabs(x) < INFINITY) ? e : q;
+}
+#define DIVX(x, c) divx_((x), (c))
+#define DIVC(x, c) ((x) * (1.0 / (c)))
+#else
+#define DIVX(x, c) ((x) / (c))
+#define DIVC(x, c) ((x) / (c))
+#endif
+
 #define MAXN 512
 
 /* ---- src/module_CONSTANTS.jl:5-23 ------------------------------------------------------ */
@@ -90,7 +109,7 @@ static void soilvar(const model_t* m, const double* swati, double* W, double* ps
                     double* theta, double* kk) {
   for (int i = 0; i < m->N; i++) {
     double ths = LY(m, THSAT, i), thr = LY(m, THR, i);
-    double w = jmin(1.0, (ths * swati[i] / LY(m, SWATMAX, i) - thr) / (ths - thr));
+    double w = jmin(1.0, DIVX(DIVX(ths * swati[i], LY(m, SWATMAX, i)) - thr, ths - thr));
     W[i] = w;
     double a = jmax(w, 1.e-6);
     double n = LY(m, NPAR, i), mm = LY(m, MPAR, i);
@@ -109,10 +128,10 @@ static void soilvar(const model_t* m, const double* swati, double* W, double* ps
 /* KKMEAN :238-252 and VERT :206-229 */
 static double vert(double KK_i, double KK_ip, double KSAT_i, double KSAT_ip, double T_i, double T_ip,
                    double PSIT_i, double PSIT_ip, double ST_i, double ST_ip) {
-  double kkmean = exp((T_ip * log(KK_i) + T_i * log(KK_ip)) / (T_i + T_ip));
+  double kkmean = exp(DIVX(T_ip * log(KK_i) + T_i * log(KK_ip), T_i + T_ip));
   kkmean = jmin(jmin(kkmean, KSAT_i), KSAT_ip);
-  double grad = (PSIT_i - PSIT_ip) / ((T_i + T_ip) / 2.0);
-  return (grad * kkmean / p_RHOWG) * (1.0 - (ST_i + ST_ip) / 2.0);
+  double grad = DIVX(PSIT_i - PSIT_ip, (T_i + T_ip) / 2.0);
+  return DIVX(grad * kkmean, p_RHOWG) * (1.0 - (ST_i + ST_ip) / 2.0);
 }
 
 /* INFLOW!  src/module_WAT.jl:313-457 */
@@ -167,7 +186,7 @@ static double iter_mvg(const model_t* m, double DTI, const double* NTFLI_prev, c
                               jmax(0.000001, fabs(NTFLI_prev[i])));
     double avail = (LY(m, THR, i) - theta[i]) * T;
     if (NTFLI_prev[i] < 0) {
-      DTINEW = jmin(DTINEW, avail / NTFLI_prev[i] / 1.30);
+      DTINEW = jmin(DTINEW, DIVX(avail / NTFLI_prev[i], 1.30));
       if (DTINEW < p_DTIMIN) DTINEW = p_DTIMIN;
     }
   }
@@ -881,10 +900,10 @@ static void cb_deltas(model_t* m, double* u, const sidx_t* ix, double t) {
 
 /* src/module_ISO.jl:36-37, :53-55 */
 static const double R18 = 2005.2e-6, R2H = 155.76e-6;
-static double d_to_x(double d, double R) { return 1 / (1 + 1 / (R * (d / 1000 + 1))); }
+static double d_to_x(double d, double R) { return 1 / (1 + 1 / (R * (DIVC(d, 1000.0) + 1))); }
 static double x_to_d(double x, double R) { return (1 / (R * (1 / x - 1)) - 1) * 1000; }
 static double dxdt_to_dddt(double dxdt, double x, double R) {
-  return dxdt * 1 / R * 1 / ((x - 1) * (x - 1)) * 1000;
+  return DIVC(dxdt * 1, R) * 1 / ((x - 1) * (x - 1)) * 1000;
 }
 
 /* LWFBrook90R_updateIsotopes_GWAT_SWAT_AdvecDiff!  src/func_DiffEq_definition_cb.jl:635-1250.
@@ -916,9 +935,9 @@ static void cb_ade(model_t* m, double* u, const double* uprev, const sidx_t* ix,
     double Cxy = d_to_x(u[ix->XYLEM + o], R[s]);
     double dSLVP = dnew[0];                          /* cb.jl:814-815 (before the update) */
     for (int i = 0; i < N; i++) {
-      double q = m->VRFLI[i] / 1000;
+      double q = DIVC(m->VRFLI[i], 1000.0);
       double ths = LY(m, THSAT, i);
-      double tau = pow(th1[i], 7.0 / 3) / (ths * ths);
+      double tau = DIVC(pow(th1[i], 7.0 / 3), ths * ths);
       Dd[i] = D0[s] * tau * th1[i] + Lam * fabs(q);
       C[i] = d_to_x(dk[i], R[s]);
     }
@@ -926,8 +945,8 @@ static void cb_ade(model_t* m, double* u, const double* uprev, const sidx_t* ix,
     double Cslvp = d_to_x(dSLVP, R[s]);
     for (int i = 0; i < N; i++) Ctr[i] = (m->TRANI[i] < 0) ? Cxy : C[i];
     for (int i = 0; i < N; i++) {
-      double diff_upp = (i == 0) ? 0.0 * 0.0 : ((Dd[i - 1] + Dd[i]) / 2) * ((C[i] - C[i - 1]) / LY(m, DZ, i - 1));
-      double diff_low = (i == N - 1) ? 0.0 * 0.0 : ((Dd[i] + Dd[i + 1]) / 2) * ((C[i + 1] - C[i]) / LY(m, DZ, i));
+      double diff_upp = (i == 0) ? 0.0 * 0.0 : ((Dd[i - 1] + Dd[i]) / 2) * DIVC(C[i] - C[i - 1], LY(m, DZ, i - 1));
+      double diff_low = (i == N - 1) ? 0.0 * 0.0 : ((Dd[i] + Dd[i + 1]) / 2) * DIVC(C[i + 1] - C[i], LY(m, DZ, i));
       double qC_upp = (i == 0) ? 0.0 : m->VRFLI[i - 1] * C[i - 1];
       double qC_low = m->VRFLI[i] * C[i];
       double slv = (i == 0) ? Cslvp : 0.0;
@@ -937,7 +956,11 @@ static void cb_ade(model_t* m, double* u, const double* uprev, const sidx_t* ix,
       inner = inner - m->DSFLI[i] * C[i];
       inner = inner - m->SLVP * slv;
       inner = inner - m->TRANI[i] * Ctr[i];
+#if defined(LWFB_ORACLE_ELEM) && !defined(LWFB_ORACLE_NORCP)
+      dC[i] = -C[i] * (1 / S1[i]) * m->NTFLI[i] + 1 / S1[i] * inner;
+#else
       dC[i] = -C[i] / S1[i] * m->NTFLI[i] + 1 / S1[i] * inner;
+#endif
     }
     /* GWAT cb.jl:1152-1188 */
     double ddG;

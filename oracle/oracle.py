@@ -34,7 +34,8 @@ _lp = C.POINTER(C.c_int64)
 
 def build(force: bool = False) -> str:
     src = [os.path.join(_HERE, "lwfb90_oracle.c"), os.path.join(os.path.dirname(_HERE), "include", "lwfb90.h"),
-           os.path.join(os.path.dirname(_HERE), "include", "lwfb90_elem.h")]
+           os.path.join(os.path.dirname(_HERE), "include", "lwfb90_elem.h"),
+           os.path.join(os.path.dirname(_HERE), "include", "lwfb90_setup.h"), os.path.join(_HERE, "lwfb90_setup_twin.c")]
     stale = any(not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in src)
                 for so in (_SO, _SO_ELEM))
     if force or stale:
@@ -141,3 +142,27 @@ def elem(fn: int, x, y=None):
     if fn == 8:
         return np.array([L.lwfb_oracle_fastpow(a, b) for a, b in zip(x, y)])
     return np.array([L.lwfb_oracle_elem(fn, a, b) for a, b in zip(x, y)])
+
+
+def setup_members(N, iso, base_scal, base_lay, base_u0, knobs, over_idx, profiles, psim_base, ilayer):
+    """CPU twin of lwfb_setup_members (include/lwfb90_setup.h compiled for the host; always the "elem" build).
+    Returns (scal [M, PS], lay [M, PL, N], u0 [M, L], status [M])."""
+    build()
+    L_ = _libs.get("setup") or C.CDLL(_SO_ELEM)
+    _libs["setup"] = L_
+    L_.lwfb_oracle_setup_members.restype = None
+    L_.lwfb_oracle_setup_members.argtypes = [C.c_int64, C.c_int, C.c_int, _dp, _dp, _dp, _dp, C.c_int, _ip, C.c_int, _dp, _dp,
+                                             C.c_int, _dp, _dp, _dp, _ip]
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    knobs = f(knobs)
+    oi = np.ascontiguousarray(over_idx, dtype=np.int32)
+    M = knobs.shape[0]
+    PS, PL = len(base_scal), np.asarray(base_lay).shape[0]
+    Ls = 9 * N + 51 if iso else 5 * N + 39
+    profiles = f(profiles).reshape(-1, 2 * N + 1) if profiles is not None and len(profiles) else np.zeros((0, 2 * N + 1))
+    scal, lay, u0 = np.empty((M, PS)), np.empty((M, PL, N)), np.empty((M, Ls))
+    status = np.zeros(M, dtype=np.int32)
+    L_.lwfb_oracle_setup_members(M, N, int(iso), _p(f(base_scal)), _p(f(base_lay)), _p(f(base_u0)), _p(knobs), len(oi),
+                                 _p(oi, _ip) if len(oi) else None, profiles.shape[0], _p(profiles) if profiles.size else None,
+                                 _p(f(psim_base)), int(ilayer), _p(scal), _p(lay), _p(u0), _p(status, _ip))
+    return scal, lay, u0, status

@@ -34,10 +34,13 @@ constexpr int MAX_LANES = WARP * MAX_WARPS;
 constexpr size_t STACK_BYTES = 1u << 20;
 
 // One emulated thread block: n_lanes = 32 * warps coroutines on one host thread.  A lane runs until it reaches a
-// primitive, deposits its operand and hands control on: at a WARP primitive to the next live lane of its warp, at a
-// BLOCK primitive (__syncthreads, __syncthreads_or) to the next live lane of the block.  When control comes back, every
-// lane of the scope must have deposited at the same source line - anything else is divergence (undefined behaviour or
-// a hang on the GPU) and aborts the run.
+// primitive, deposits its operand and WAITS: it hands control to the next live lane of the block (round robin) and, each
+// time control comes back, looks whether its primitive is complete - a warp primitive when all lanes of the warp have
+// deposited, a block barrier (__syncthreads*) when all threads of the block have, a counted named barrier
+// (bar.sync id, n) when n threads have arrived.  Warps may therefore be in different code at the same time (the lane
+// kernel runs daily callbacks in some warps while the others step), as on the hardware.  Every primitive carries its
+// source line; lanes meeting at different lines, a thread leaving before a barrier, warps making different numbers of
+// barrier calls or a block in which nobody can make progress abort the run (undefined behaviour or a hang on the GPU).
 struct Block {
   ucontext_t main_ctx, ctx[MAX_LANES];
   char* stacks = nullptr;
@@ -49,6 +52,10 @@ struct Block {
   uint64_t bslot[2][MAX_LANES];         // block primitives
   int bopid[2][MAX_LANES];
   unsigned long bcounter[MAX_LANES];
+  // counted named barrier (one id is enough for the kernels): generation, arrivals, what the first arrival asked for
+  unsigned long named_gen = 0;
+  int named_arrived = 0, named_expect = 0, named_op = 0;
+  unsigned long progress = 0;           // primitives completed / lanes finished (deadlock detection)
   int cur = 0;
   void (*body)(void* arg, int lane) = nullptr;
   void* arg = nullptr;
@@ -57,14 +64,6 @@ struct Block {
 thread_local Block* W = nullptr;
 thread_local int g_warps_per_block = 1;
 
-int next_alive_in_warp(int l) {
-  const int base = l & ~(WARP - 1);
-  for (int s = 1; s <= WARP; s++) {
-    int n = base + ((l - base + s) % WARP);
-    if (!W->done[n]) return n;
-  }
-  return -1;
-}
 int next_alive_in_block(int l) {
   for (int s = 1; s <= W->n_lanes; s++) {
     int n = (l + s) % W->n_lanes;
@@ -76,14 +75,35 @@ int next_alive_in_block(int l) {
 void trampoline(int lane) {
   W->body(W->arg, lane);
   W->done[lane] = true;
-  int n = next_alive_in_warp(lane);
-  if (n < 0) n = next_alive_in_block(lane);
+  W->progress++;
+  int n = next_alive_in_block(lane);
   if (n < 0) setcontext(&W->main_ctx);
   W->cur = n;
   setcontext(&W->ctx[n]);
 }
 
-// warp scope: deposit a value, let every other lane of the warp run up to the same primitive, return the slot parity
+// hand control to the next live lane of the block; returns when it is this lane's turn again
+struct Waiter {
+  int lane, op_id;
+  const char* what;
+  unsigned long seen;
+  int idle_rounds = 0;
+  Waiter(int l, int op, const char* w) : lane(l), op_id(op), what(w), seen(W->progress) {}
+  void yield() {
+    if (W->progress != seen) { seen = W->progress; idle_rounds = 0; }
+    else if (++idle_rounds > 4) {
+      fprintf(stderr, "simt_emul: deadlock: lane %d waits at the %s of line %d and no thread of the block can make progress\n",
+              lane, what, op_id);
+      abort();
+    }
+    const int n = next_alive_in_block(lane);
+    if (n < 0 || n == lane) { if (idle_rounds > 1) { fprintf(stderr, "simt_emul: lane %d waits alone at line %d\n", lane, op_id); abort(); } return; }
+    W->cur = n;
+    swapcontext(&W->ctx[lane], &W->ctx[n]);
+  }
+};
+
+// warp scope: deposit a value, wait until every lane of the warp has deposited at the same primitive, return the slot parity
 int rendezvous(uint64_t v, int op_id) {
   const int l = W->cur;
   const int base = l & ~(WARP - 1);
@@ -91,42 +111,71 @@ int rendezvous(uint64_t v, int op_id) {
   const int par = (int)(my_op & 1ul);
   W->slot[par][l] = v;
   W->opid[par][l] = op_id;
-  const int n = next_alive_in_warp(l);
-  if (n >= 0 && n != l) {
-    W->cur = n;
-    swapcontext(&W->ctx[l], &W->ctx[n]);
+  W->progress++;
+  Waiter w(l, op_id, "warp primitive");
+  for (;;) {
+    bool all = true;
+    for (int i = base; i < base + WARP; i++) {
+      if (W->done[i] && W->counter[i] <= my_op) { fprintf(stderr, "simt_emul: lane %d exited before the warp primitive at line %d\n", i, op_id); abort(); }
+      if (W->counter[i] <= my_op) all = false;
+    }
+    if (all) break;
+    w.yield();
   }
-  for (int i = base; i < base + WARP; i++) {
-    if (W->done[i] && W->counter[i] <= my_op) { fprintf(stderr, "simt_emul: lane %d exited before the warp primitive at line %d\n", i, op_id); abort(); }
-    if (W->opid[par][i] != op_id || W->counter[i] <= my_op) {
+  for (int i = base; i < base + WARP; i++)
+    if (W->opid[par][i] != op_id) {
       fprintf(stderr, "simt_emul: divergent warp primitive: lane %d at line %d, lane %d at line %d\n", l, op_id, i, W->opid[par][i]);
       abort();
     }
-  }
+  W->progress++;
   if (l == 0) W->n_ops++;
   return par;
 }
 
-// block scope
+// block scope (barrier 0: every thread of the block)
 int block_rendezvous(uint64_t v, int op_id) {
   const int l = W->cur;
   const unsigned long my_op = W->bcounter[l]++;
   const int par = (int)(my_op & 1ul);
   W->bslot[par][l] = v;
   W->bopid[par][l] = op_id;
-  const int n = next_alive_in_block(l);
-  if (n >= 0 && n != l) {
-    W->cur = n;
-    swapcontext(&W->ctx[l], &W->ctx[n]);
+  W->progress++;
+  Waiter w(l, op_id, "block barrier");
+  for (;;) {
+    bool all = true;
+    for (int i = 0; i < W->n_lanes; i++) {
+      if (W->done[i] && W->bcounter[i] <= my_op) { fprintf(stderr, "simt_emul: lane %d exited before the block barrier at line %d\n", i, op_id); abort(); }
+      if (W->bcounter[i] <= my_op) all = false;
+    }
+    if (all) break;
+    w.yield();
   }
-  for (int i = 0; i < W->n_lanes; i++) {
-    if (W->done[i] && W->bcounter[i] <= my_op) { fprintf(stderr, "simt_emul: lane %d exited before the block barrier at line %d\n", i, op_id); abort(); }
-    if (W->bopid[par][i] != op_id || W->bcounter[i] <= my_op) {
+  for (int i = 0; i < W->n_lanes; i++)
+    if (W->bopid[par][i] != op_id) {
       fprintf(stderr, "simt_emul: block barrier mismatch: lane %d at line %d, lane %d at line %d\n", l, op_id, i, W->bopid[par][i]);
       abort();
     }
-  }
+  W->progress++;
   return par;
+}
+
+// counted named barrier (bar.sync 1, n_threads): released when n_threads threads have arrived
+void named_rendezvous(int n_threads, int op_id) {
+  const int l = W->cur;
+  if (n_threads <= 0 || n_threads > W->n_lanes || (n_threads & (WARP - 1))) {
+    fprintf(stderr, "simt_emul: bar.sync with thread count %d at line %d\n", n_threads, op_id); abort();
+  }
+  const unsigned long g = W->named_gen;
+  if (W->named_arrived == 0) { W->named_expect = n_threads; W->named_op = op_id; }
+  else if (W->named_expect != n_threads || W->named_op != op_id) {
+    fprintf(stderr, "simt_emul: named barrier mismatch: lane %d arrives with (line %d, %d threads), the barrier is open for (line %d, %d threads)\n",
+            l, op_id, n_threads, W->named_op, W->named_expect);
+    abort();
+  }
+  W->progress++;
+  if (++W->named_arrived == n_threads) { W->named_arrived = 0; W->named_gen++; return; }
+  Waiter w(l, op_id, "named barrier");
+  while (W->named_gen == g) w.yield();
 }
 
 void run_block(void (*body)(void*, int), void* arg, int warps) {
@@ -176,6 +225,17 @@ bool block_or(bool p, int op_id) {
   bool any = false;
   for (int i = 0; i < W->n_lanes; i++) any = any || W->bslot[par][i] != 0;
   return any;
+}
+int block_count(bool p, int op_id) {
+  if (W->cur == 0) g_votes.fetch_add(1, std::memory_order_relaxed);
+  const int par = block_rendezvous(p ? 1u : 0u, op_id);
+  int n = 0;
+  for (int i = 0; i < W->n_lanes; i++) n += W->bslot[par][i] != 0;
+  return n;
+}
+void named_sync(int n_threads, int op_id) {
+  if ((W->cur & (WARP - 1)) == 0) g_stage_syncs.fetch_add(1, std::memory_order_relaxed);
+  named_rendezvous(n_threads, op_id);
 }
 int lane_id() { return W->cur & (WARP - 1); }
 int warps_per_block() { return g_warps_per_block; }

@@ -162,10 +162,10 @@ def test_generic_layer_count_kernels_bit_identical(lw, infexp1):
     h.close()
 
 
-def test_thread_per_member_kernel_agrees_with_lane_per_layer_kernel(dav_full, bea):
+def test_thread_per_member_kernel_agrees_with_lane_per_layer_kernel(dav_full, bea, isobea):
     """The library holds two independently written CUDA implementations (lane-per-layer production kernel,
     thread-per-member kernel for N < 3 or N > 32); both must reproduce the oracle bit-for-bit."""
-    for sim, M in ((dav_full, 24), (bea, 12)):
+    for sim, M in ((dav_full, 24), (bea, 12), (isobea, 40)):     # (isoBEA2016 member 22: miscompiled by NVVM -O3, see build.py)
         ens = en.make_ensemble(sim, M)
         h = capi.Handle(ens.N, ens.iso, ens.t0_day, 120)
         h.force_legacy(True)
@@ -275,18 +275,24 @@ def test_nonzero_start_day_and_short_span(dav_full):
 
 
 # ------------------------------------------------------------------------------ against the libm oracle
-def test_tolerance_vs_libm_oracle_with_conditioning(dav_full):
-    """GPU vs the golden-pinned oracle build.  A member counts as reproducible if the oracle itself
-    stays within tolerance under a 1e-15 relative perturbation of KSAT; every reproducible member must
-    meet the north-star tolerance, and the GPU deviation may never exceed the oracle's own spread by
-    more than a small factor."""
+def test_tolerance_vs_libm_oracle_with_conditioning(dav_full, capsys):
+    """GPU vs the golden-pinned oracle build (host libm, the reference's divisions) over the full record.
+
+    The reference algorithm is chaotic for part of any ensemble: the north-star tolerance (1e-6 relative on storage and
+    theta, 1e-4 permil on delta) is TIGHTER than the accuracy the solver is asked for (reltol 1e-5), so two correct
+    implementations agree to it only while they take the same sequence of accepted and rejected steps, and a one-ulp
+    difference in one pow() can flip one such decision.  What the test establishes:
+      * the fraction of members whose whole record stays within the north-star tolerance is reported and must be >= 0.8
+        (measured: 0.83 for these 64 members; member 0, the unmodified site definition, is among them);
+      * a member is CONDITIONED if the libm oracle itself stays within a tenth of the tolerance under six 1e-15 relative
+        perturbations of its soil parameters; every conditioned member must be within tolerance;
+      * every member outside the tolerance is one on which the oracle's own perturbed runs spread by a comparable amount
+        (the GPU deviation is below 100 x that spread)."""
     ens = en.make_ensemble(dav_full, 64)
     h, sub, nd = gpu_run(ens)
     gpu = h.get_daily()
     h.close()
     ref = oracle_run(sub, nd, "libm")[0]
-    lay_p = sub.lay.copy(); lay_p[:, lo.L.KSAT] *= (1 + 1e-15)
-    ref_p = oracle_run(sub, nd, "libm", lay=lay_p)[0]
     ix = lo.StateIndex(sub.N, True)
 
     def errs(a, b):
@@ -296,14 +302,25 @@ def test_tolerance_vs_libm_oracle_with_conditioning(dav_full):
                        np.nan_to_num(np.abs(a[:, :, ix.SWATI_d2H] - b[:, :, ix.SWATI_d2H])))
         return np.maximum(sw.max(axis=(1, 2)), st.max(axis=1)), d.max(axis=(1, 2))
     e_sw, e_d = errs(gpu, ref)
-    s_sw, s_d = errs(ref_p, ref)
-    reproducible = (s_sw < TOL_STORAGE / 10) & (s_d < TOL_DELTA / 10)
-    assert reproducible[0], "the unmodified site definition must be well conditioned"
-    assert reproducible.mean() > 0.5
-    assert np.all(e_sw[reproducible] < TOL_STORAGE) and np.all(e_d[reproducible] < TOL_DELTA)
+    s_sw, s_d = np.zeros(sub.M), np.zeros(sub.M)
+    for field, eps in ((lo.L.KSAT, 1e-15), (lo.L.THSAT, 1e-15), (lo.L.ALPHA, 1e-15), (lo.L.KSAT, -1e-15), (lo.L.NPAR, 1e-15),
+                       (lo.L.THICK, 1e-15)):
+        lay_p = sub.lay.copy(); lay_p[:, field] *= (1 + eps)
+        a, b = errs(oracle_run(sub, nd, "libm", lay=lay_p)[0], ref)
+        s_sw, s_d = np.maximum(s_sw, a), np.maximum(s_d, b)
+    within = (e_sw < TOL_STORAGE) & (e_d < TOL_DELTA)
+    conditioned = (s_sw < TOL_STORAGE / 10) & (s_d < TOL_DELTA / 10)
+    with capsys.disabled():
+        print(f"\n[tolerance vs libm oracle] {sub.M} members x {nd} days: within the north-star tolerance {within.mean():.3f} "
+              f"(storage/theta alone {np.mean(e_sw < TOL_STORAGE):.3f}); conditioned under perturbation {conditioned.mean():.3f}; "
+              f"median deviation storage {np.median(e_sw):.1e}, delta {np.median(e_d):.1e} permil; "
+              f"members outside: {np.nonzero(~within)[0].tolist()}")
+    assert within[0] and conditioned[0], "the unmodified site definition must be well conditioned and within tolerance"
+    assert within.mean() >= 0.8
+    assert np.all(within[conditioned]), np.nonzero(conditioned & ~within)[0]
     assert np.median(e_sw) < 1e-9
-    # chaotic members: the GPU is no further from the oracle than the oracle is from its perturbed self (x100)
-    assert np.all(e_sw[~reproducible] < 100 * np.maximum(s_sw[~reproducible], TOL_STORAGE))
+    out = ~within
+    assert np.all(e_sw[out] < 100 * np.maximum(s_sw[out], TOL_STORAGE)) and np.all(e_d[out] < 100 * np.maximum(s_d[out], TOL_DELTA))
 
 
 # ------------------------------------------------------------------------------ size-independent properties
@@ -579,4 +596,37 @@ def test_getters_wait_for_an_asynchronous_run(dav_full):
     assert np.array_equal(pinned.numpy(), want, equal_nan=True)
     with pytest.raises(capi.LwfbError, match="get_daily"):
         h.get_daily(out=np.empty((3, 3)))
+    h.close()
+
+
+@pytest.mark.parametrize("which", ["dav_full", "bea"])
+def test_setup_members_on_device(which, request):
+    """SURVEY 8f N1 on the GPU: lwfb_setup_members builds the member blocks in HBM from the base member and a knob row per
+    member; they must be bit-identical to what the host compile of the same text (oracle twin) produces, for 10^5
+    members, and a run from them bit-identical to a run from the uploaded blocks."""
+    import time
+    sim = request.getfixturevalue(which)
+    M = 100_000
+    kb = en.make_knob_block(sim, M)
+    kb.knobs[77, en.K_KSAT_F] = 1e-9          # an impossible soil: reported, does not disturb the others
+    want = orc.setup_members(kb.N, kb.iso, kb.base_scal, kb.base_lay, kb.base_u0, kb.knobs, kb.over_idx, kb.profiles,
+                             kb.psim_base, kb.ilayer)
+    h = capi.Handle(kb.N, kb.iso, kb.t0_day, 5, record_daily=False)
+    h.set_sites(kb.forcing)
+    h.setup_members(kb)                       # warm-up (allocations)
+    t = time.perf_counter()
+    n_invalid = h.setup_members(kb)
+    dt = time.perf_counter() - t
+    assert n_invalid == int((want[3] != 0).sum()) == 1
+    for k in range(3):
+        assert np.array_equal(h.get_block(k), want[k], equal_nan=True), ("scal", "lay", "u0")[k]
+    print(f"\n[setup_members] {M} members in {dt * 1e3:.1f} ms (H2D of the knob rows included)")
+    assert dt < 0.25
+    # integrate a few days from the device-built blocks and from the same blocks uploaded by lwfb_set_members
+    sub = np.r_[0:64, 99_936:100_000]
+    kb2 = en.KnobBlock(**{**kb.__dict__, "knobs": kb.knobs[sub]})
+    h.setup_members(kb2); h.run()
+    fin_a = h.get_final(); st_a, cnt_a = h.get_status()
+    h.set_members(np.zeros(len(sub), np.int32), want[0][sub], want[1][sub], want[2][sub]); h.run()
+    assert np.array_equal(fin_a, h.get_final(), equal_nan=True) and np.array_equal(cnt_a, h.get_status()[1])
     h.close()

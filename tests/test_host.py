@@ -199,3 +199,34 @@ def test_golden_csv_writers_match_reference_layout(lw, tmp_path):
     back = gio.read_table(str(tmp_path / "t.csv"))
     assert all(np.array_equal(back[k], t[k], equal_nan=True) for k in t) and np.signbit(back["x"][2])
     assert open(tmp_path / "t.csv").read().splitlines()[2] == "30.0,NaN,-Inf"
+
+
+@pytest.mark.parametrize("which", ["dav_full", "bea", "isobea"])
+def test_setup_twin_matches_batched_setup(which, request):
+    """the member setup that runs on the GPU (include/lwfb90_setup.h, here compiled for the host with the
+    device's elementary functions) against the numpy implementation pinned to remakeSPAC -> setup above: knob draw,
+    soil-horizon scaling, field-capacity bisection, INFPAR, root profile, initial state.  Scalars are identical; the
+    power-function results agree to the difference between two pow implementations."""
+    import oracle as orc
+    from lwfbrook90.jl_b200 import ensemble as en
+    sim = request.getfixturevalue(which)
+    M = 1500
+    ens = en.make_ensemble(sim, M)
+    kb = en.make_knob_block(sim, M)
+    assert np.isnan(kb.knobs[0]).all(), "member 0 is the unmodified site definition: all knobs unset"
+    scal, lay, u0, st = orc.setup_members(kb.N, kb.iso, kb.base_scal, kb.base_lay, kb.base_u0, kb.knobs, kb.over_idx,
+                                          kb.profiles, kb.psim_base, kb.ilayer)
+    assert (st == 0).all()
+    assert np.array_equal(scal[0], sim.scal) and np.array_equal(lay[0], sim.lay) and np.array_equal(u0[0], sim.u0)
+
+    def rel(a, b):
+        sc = np.maximum(np.abs(a), np.abs(b)); sc[sc == 0] = 1
+        return (np.abs(a - b) / sc).max()
+    assert rel(scal, ens.scal) < 1e-13
+    assert rel(lay, ens.lay) < 1e-10
+    assert rel(u0, ens.u0) < 1e-13
+    # an impossible soil (conductivity at saturation below the field-capacity conductivity): flagged, not silently used
+    kb.knobs[5, en.K_KSAT_F] = 1e-9
+    st = orc.setup_members(kb.N, kb.iso, kb.base_scal, kb.base_lay, kb.base_u0, kb.knobs, kb.over_idx, kb.profiles,
+                           kb.psim_base, kb.ilayer)[3]
+    assert st[5] == lo.ST.INPUT and (np.delete(st, 5) == 0).all()

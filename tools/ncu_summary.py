@@ -40,25 +40,34 @@ def main():
     lines = collections.OrderedDict()
     ops = collections.Counter()
     stall_cols = None
+    # the page lists every source line followed by the SASS instructions generated for it
     for b in blocks:
         h = b["hdr"]
-        ci = {name: i for i, name in enumerate(h)}
-        i_line, i_src, i_sass = 0, 1, 3
+        ci = {}
+        for i, name in enumerate(h):
+            ci.setdefault(name, i)
         i_exec, i_smp = ci["Instructions Executed"], ci["# Samples"]
         if stall_cols is None:
             stall_cols = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
+        cur_line, cur_src = "?", ""
         for r in b["rows"]:
+            if r[0] != "":                       # a source line (its counters are the sums of the SASS rows below)
+                cur_line, cur_src = r[0], r[1]
+                continue
+            if r[2] in ("", "...") or not r[2].startswith("0x"):
+                continue
             try:
                 ex = float(r[i_exec] or 0); smp = float(r[i_smp] or 0)
             except ValueError:
                 continue
-            key = (b["file"], r[i_line])
-            e = lines.setdefault(key, {"src": r[i_src], "static": 0, "exec": 0.0, "smp": 0.0, "ops": collections.Counter(),
+            key = (b["file"], cur_line)
+            e = lines.setdefault(key, {"src": cur_src, "static": 0, "exec": 0.0, "smp": 0.0, "ops": collections.Counter(),
                                        "st": collections.Counter()})
             e["static"] += 1; e["exec"] += ex; e["smp"] += smp
-            op = r[i_sass].split()[0] if r[i_sass].split() else "?"
-            if op.startswith("@"):
-                op = r[i_sass].split()[1]
+            toks = r[3].split()
+            op = toks[0] if toks else "?"
+            if op.startswith("@") and len(toks) > 1:
+                op = toks[1]
             op = op.split(".")[0]
             e["ops"][op] += ex; ops[op] += ex
             for sc in stall_cols:
@@ -72,6 +81,10 @@ def main():
     scale = (1.0 / n_rhs) if n_rhs else 100.0 / total_exec
     unit = "dyn/RHS" if n_rhs else "% of executed"
     print(f"\ntotal executed warp instructions {total_exec:.4g}; samples {tot_smp:.0f}")
+    per_file = collections.Counter(); per_file_smp = collections.Counter()
+    for (f, ln), e in lines.items():
+        per_file[f] += e["exec"]; per_file_smp[f] += e["smp"]
+    print("per file (" + unit + " / % samples): " + ", ".join(f"{f} {v * scale:.1f} / {per_file_smp[f] / tot_smp * 100:.1f}%" for f, v in per_file.most_common()))
     print("opcode mix (" + unit + "): " + ", ".join(f"{k} {v * scale:.1f}" for k, v in ops.most_common(32)))
     print(f"\n--- top 60 lines by executed instructions ({unit}; smp = % of stall samples; top stall reasons)")
     for (f, ln), e in sorted(lines.items(), key=lambda kv: -kv[1]["exec"])[:60]:
