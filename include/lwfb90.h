@@ -296,8 +296,11 @@ int lwfb_fp64_peak(int32_t device, int32_t reps, double* tflops);
  * which = 0 scal, 1 lay, 2 u0 */
 int lwfb_debug_get_block(lwfb_handle* h, int32_t which, double* out);
 
-/* testing aid: run the thread-per-member kernel (a second, independently written CUDA implementation that
- * is otherwise used only for N < 3 or N > 32 layers) instead of the lane-per-layer production kernel */
+/* testing aid: on = 1 runs the thread-per-member kernel (a second, independently written CUDA implementation that
+ * is otherwise used only for N < 3 or N > 32 layers) instead of the lane-per-layer production kernel; on = 2 keeps the
+ * lane kernel but only its general instantiation (run-time layer count, every optional flow path compiled in) where
+ * the library would pick a lean one (ensembles without bypass / source-area / downslope flow and groundwater feedback,
+ * N = 5 or 7); 0 restores the defaults */
 int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on);
 
 /* Placement of the members in the kernel's execution slots (no reference analogue; results do not depend on it).

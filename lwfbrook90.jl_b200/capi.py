@@ -289,8 +289,9 @@ class Handle:
         self._ck(self._L.lwfb_eval_rhs(self._h, float(t), _p(sw), _p(gw), _p(fr), _p(nt), _p(du)))
         return du
 
-    def force_legacy(self, on: bool = True):
-        """Testing aid: use the thread-per-member kernel instead of the lane-per-layer kernel."""
+    def force_legacy(self, on=True):
+        """Testing aid: True / 1 = the thread-per-member kernel instead of the lane-per-layer kernel; 2 = the lane kernel's
+        general instantiation where a lean one would be picked; False / 0 = defaults."""
         self._L.lwfb_debug_force_legacy.argtypes = [C.c_void_p, C.c_int32]
         self._ck(self._L.lwfb_debug_force_legacy(self._h, int(on)))
 

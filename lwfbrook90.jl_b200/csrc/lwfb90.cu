@@ -30,6 +30,19 @@
 
 using namespace lwfb;
 
+// does any member use one of the optional flow paths of the right-hand side (bypass flow, source-area flow, downslope
+// flow, groundwater storage feedback)?  If none does, the lean instantiation of the lane kernel applies.
+__global__ void optional_paths_kernel(const double* __restrict__ scal, int64_t M, int* __restrict__ used) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool u = false;
+  if (m < M) {
+    const double* s = scal + m * LWFB_PS;
+    const bool slope = !(s[LWFB_S_LENGTH_SLOPE] == 0 || s[LWFB_S_DSLOPE] == 0);
+    u = !(s[LWFB_S_GSC] < 1.0e-8) || s[LWFB_S_BYPAR] == 1.0 || (int)s[LWFB_S_QLAYER] > 0 || slope;
+  }
+  if (__any_sync(0xffffffffu, u) && (threadIdx.x & 31) == 0) atomicOr(used, 1);
+}
+
 // sort keys of the placement (ascending radix sort, stable: ties keep the member order)
 //   by_cost: RHS evaluations of the previous run, most first
 //   else   : progress of the unfinished members (simulation time reached, least first); finished members get the
@@ -176,6 +189,8 @@ struct lwfb_handle {
   cudaEvent_t pin_ev[2] = {nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
   bool force_legacy = false;   // testing: run the thread-per-member kernel also for 3 <= N <= 32
+  bool lean = false;           // no member uses an optional flow path of the RHS (optional_paths_kernel): lean lane kernel
+  bool force_general = false;  // testing: never use the lean / fixed-N instantiations
   // placement of members in the lane kernel's slots (lwfb_set_placement)
   int placement = 1;           // 0 identity, 1 adaptive (cost-sorted from the previous run), 2 the same for any launch size
   int32_t* d_perm = nullptr;
@@ -206,6 +221,7 @@ struct lwfb_handle {
 
 static int ensure_done(lwfb_handle* h);
 static int alloc_members(lwfb_handle* h, int64_t n_members);
+static int classify_members(lwfb_handle* h);
 static int download(lwfb_handle* h, void* dst, const void* src, size_t bytes);
 
 static int ensure_stage(lwfb_handle* h, size_t bytes) {
@@ -294,6 +310,7 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
   CK(cudaMemcpy(h->d_scal, scal, (size_t)h->M * LWFB_PS * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_lay, lay, (size_t)h->M * LWFB_PL * N * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_u0, u0, (size_t)h->M * L * sizeof(double), cudaMemcpyHostToDevice));
+  { int rc = classify_members(h); if (rc) return rc; }
   h->ran = false; h->sums_valid = false;
   h->cost_valid = false; h->perm_valid = false;   // counters / placement of the previous members say nothing about these
   return LWFB_OK;
@@ -388,8 +405,21 @@ extern "C" int lwfb_setup_members(lwfb_handle* h, int64_t n_members, const int32
     for (int64_t i = 0; i < M; i++) n += st[(size_t)i] != LWFB_ST_OK;
     *n_invalid = n;
   }
+  { int rc2 = classify_members(h); if (rc2) return rc2; }
   h->ran = false; h->sums_valid = false;
   h->cost_valid = false; h->perm_valid = false;
+  return LWFB_OK;
+}
+
+// after the member blocks have changed: may the lean lane kernel be used?
+static int classify_members(lwfb_handle* h) {
+  int* d_used = h->d_nleft;                            // (scratch word)
+  CK(cudaMemset(d_used, 0, sizeof(int)));
+  optional_paths_kernel<<<(unsigned)((h->M + 255) / 256), 256>>>(h->d_scal, h->M, d_used);
+  CK(cudaGetLastError());
+  int used = 1;
+  CK(cudaMemcpy(&used, d_used, sizeof(int), cudaMemcpyDeviceToHost));
+  h->lean = used == 0;
   return LWFB_OK;
 }
 
@@ -456,18 +486,26 @@ static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) 
     const int64_t warps = ((d.n_slots > 0 ? d.n_slots : d.M) + mpw - 1) / mpw;
     const int wpb = LWFB_LANES_BLOCK / 32;
     const unsigned lgrid = (unsigned)((warps + wpb - 1) / wpb);
-    size_t smem = ((size_t)KC_COUNT * LWFB_LANES_BLOCK + 3 * LWFB_LOG_TAB_N) * sizeof(double);   // constant columns + log table
+    size_t smem = LWFB_SMEM_DOUBLES((size_t)wpb * mpw) * sizeof(double);   // columns + log table + member slots + forcing rows
     if (const char* pad = getenv("LWFB_LANES_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // profiling knob: fewer resident blocks
-    if (smem > 48 * 1024) {
-      cudaFuncSetAttribute(integrate_lanes<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(integrate_lanes<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(integrate_lanes<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      cudaFuncSetAttribute(integrate_lanes<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    }
-    if (d.N == 3) integrate_lanes<8, 3><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
-    else if (d.N < 8) integrate_lanes<8, 2><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
-    else if (d.N == 8) integrate_lanes<8, 1><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
-    else integrate_lanes<32, 1><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);
+    // instantiations: general (run-time N, every flow path) and, for ensembles without optional flow paths, lean ones
+    // with the layer count fixed at compile time for the layer counts of BASELINE.json's configurations
+    const bool lean = h->lean && !h->force_general;
+#define LWFB_LAUNCH(...)                                                                                        \
+    do {                                                                                                       \
+      if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_lanes<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      integrate_lanes<__VA_ARGS__><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);                                    \
+    } while (0)
+#ifndef LWFB_FIXED_N
+#define LWFB_FIXED_N 1           // experiment knob: 0 = lean instantiations with a run-time layer count
+#endif
+    if (lean && d.N == 5) LWFB_LAUNCH(8, 2, LWFB_FIXED_N ? 5 : 0, true);
+    else if (lean && d.N == 7) LWFB_LAUNCH(8, 2, LWFB_FIXED_N ? 7 : 0, true);
+    else if (d.N == 3) LWFB_LAUNCH(8, 3);
+    else if (d.N < 8) LWFB_LAUNCH(8, 2);
+    else if (d.N == 8) LWFB_LAUNCH(8, 1);
+    else LWFB_LAUNCH(32, 1);
+#undef LWFB_LAUNCH
   } else {
     launch_member_integrate(d, st);   // thread-per-member, runtime layer count (N < 3 or N > 32)
   }
@@ -954,7 +992,8 @@ extern "C" int lwfb_fp64_peak(int32_t device, int32_t reps, double* tflops) {
 // testing aid: select the thread-per-member kernel (the second, independent CUDA implementation)
 extern "C" int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on) {
   if (!h) return LWFB_ERR_ARG;
-  h->force_legacy = on != 0;
+  h->force_legacy = on == 1;        // 1: thread-per-member kernel
+  h->force_general = on == 2;       // 2: lane kernel, but never its lean / fixed-N instantiations
   return LWFB_OK;
 }
 

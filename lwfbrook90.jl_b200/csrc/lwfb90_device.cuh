@@ -731,13 +731,13 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
                                         double* TRANI_state, double& RWU_state, int& status) {
   const int N = pv.N;
   double u_INTS = ds.INTS, u_INTR = ds.INTR, u_SNOW = ds.SNOW, u_CC = ds.CC, u_SNOWLQ = ds.SNOWLQ;
-  double TMAX = __ldg(frow + LWFB_F_TMAX), TMIN = __ldg(frow + LWFB_F_TMIN), EA = __ldg(frow + LWFB_F_VAPPRES),
-         UW = __ldg(frow + LWFB_F_WIND), SOLRAD = __ldg(frow + LWFB_F_GLOBRAD), PREC = __ldg(frow + LWFB_F_PREC),
-         DOY = __ldg(frow + LWFB_F_DOY);
-  double DENSEF = __ldg(frow + LWFB_F_DENSEF_REL) * pv.S(LWFB_S_DENSEF_BASELINE);
-  double HEIGHT = __ldg(frow + LWFB_F_HEIGHT_REL) * pv.S(LWFB_S_HEIGHT_BASELINE);
-  double LAI = __ldg(frow + LWFB_F_LAI_REL) * pv.S(LWFB_S_MAXLAI);
-  double SAI = __ldg(frow + LWFB_F_SAI_REL) * pv.S(LWFB_S_SAI_BASELINE);
+  double TMAX = frow[LWFB_F_TMAX], TMIN = frow[LWFB_F_TMIN], EA = frow[LWFB_F_VAPPRES],
+         UW = frow[LWFB_F_WIND], SOLRAD = frow[LWFB_F_GLOBRAD], PREC = frow[LWFB_F_PREC],
+         DOY = frow[LWFB_F_DOY];
+  double DENSEF = frow[LWFB_F_DENSEF_REL] * pv.S(LWFB_S_DENSEF_BASELINE);
+  double HEIGHT = frow[LWFB_F_HEIGHT_REL] * pv.S(LWFB_S_HEIGHT_BASELINE);
+  double LAI = frow[LWFB_F_LAI_REL] * pv.S(LWFB_S_MAXLAI);
+  double SAI = frow[LWFB_F_SAI_REL] * pv.S(LWFB_S_SAI_BASELINE);
   // relative root density of the day (HammelKennel_lateral_rootgrowth, src/func_DiffEq_definition_p.jl:606-628)
   double RELDEN[NMAX];
   if (pv.S(LWFB_S_RELDEN_CONST) != 0.0) {
@@ -888,7 +888,7 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
   // ---- MSBPREINT
   const double DTP = 1.0;
   double SFAL = SNOFRC * PREC, RFAL = PREC - SFAL;
-  int IHD = (int)__ldg(frow + LWFB_F_IHD);
+  int IHD = (int)frow[LWFB_F_IHD];
   double SINT, ISVP, RINT, IRVP;
   inter24(SFAL, (PINT < 0 && TA > 0) ? 0.0 : PINT, LAIeff, SAIeff, pv.S(LWFB_S_FSINTL), pv.S(LWFB_S_FSINTS),
           pv.S(LWFB_S_CINTSL), pv.S(LWFB_S_CINTSS), IHD, u_INTS, SINT, ISVP);

@@ -102,33 +102,64 @@ enum {
   KC_THSAT = 0, KC_THR, KC_DTH, KC_SWATMAX, KC_E1, KC_E2, KC_E3, KC_E4, KC_TORT, KC_CPSI, KC_KSAT, KC_PSIG,
   KC_THICK, KC_OMS, KC_INFRAC, KC_THICK_DN, KC_KSAT_DN, KC_TSUM, KC_THALF, KC_STFAC, KC_CITER, KC_WETF,
   KC_RDZ_UP, KC_RDZ_DN, KC_RTHS2, KC_ARATIO, KC_RSWATMAX, KC_RDTH, KC_RTSUM, KC_RTHALF,   // R...: reciprocals (div_c, LWFB_RCP)
-  // member-level
-  KC_DPSIMAX, KC_DTIMAX, KC_DRAIN, KC_GSC, KC_GSP, KC_IMPERV, KC_QFFC, KC_QFPAR, KC_SWATQF, KC_SWATQX,
-  KC_CS, KC_SNRHO, KC_LEN1000, KC_LAM, KC_VXYLEM,
-  // day constants written by the daily callback
-  KC_SUMT, KC_SUMT_V, KC_D0_18O, KC_D0_2H,
-  // isotope state of the lane (touched once per accepted step): delta18O / delta2H of SWATI[i], GWAT, XYLEM
-  KC_DS_18O, KC_DS_2H, KC_DG_18O, KC_DG_2H, KC_DXY_18O, KC_DXY_2H,
+  // isotope state of the lane (touched once per accepted step): delta18O / delta2H of SWATI[i]
+  KC_DS_18O, KC_DS_2H,
+  // frozen uptake of the layer (set by the daily callback, read twice per RHS evaluation)
+  KC_TRANI,
+  // exchange slot: a value of the lane that the other lanes of its group read (instead of N double shuffles)
+  KC_XCH,
   KC_COUNT
 };
+// per-MEMBER values (shared memory, one slot per member of the block: element k of the member is msm[k * mpb], mpb =
+// members per block; the lanes of a group read the same word - a broadcast - and the groups of a warp neighbouring words)
+enum {
+  KM_DPSIMAX = 0, KM_DTIMAX, KM_DRAIN, KM_GSC, KM_GSP, KM_IMPERV, KM_QFFC, KM_QFPAR, KM_SWATQF, KM_SWATQX,
+  KM_CS, KM_SNRHO, KM_LEN1000, KM_LAM, KM_VXYLEM,
+  // day constants written by the daily callback
+  KM_SUMT, KM_SUMT_V, KM_D0_18O, KM_D0_2H,
+  // isotope state of the member: delta18O / delta2H of GWAT, XYLEM
+  KM_DG_18O, KM_DG_2H, KM_DXY_18O, KM_DXY_2H,
+  // RNET + SMLT and SLVP of the day (set by the daily callback)
+  KM_RS, KM_SLVP,
+  // the rates of the 8 integrated accumulators of the last RHS evaluation (+ a zero for lanes that hold none): every
+  // lane picks its own by index instead of walking a chain of selects
+  KM_RATE0, KM_RATE_ZERO = KM_RATE0 + 8,
+  KM_COUNT
+};
 #define LC(k) (*(const volatile double*)(cst + (k) * LWFB_LANES_BLOCK))
+#define LM(k) (*(const volatile double*)(msm + (k) * mpb))
+#define SETM(k, v) (msm[(k) * mpb] = (v))
 #ifdef LWFB_SIMT_EMUL
-#define LWFB_BLOCK_OF_WARP(w) ((w) / simt::warps_per_block())   // the emulator's block size is a run-time choice
+#define LWFB_WARPS_PER_BLOCK (simt::warps_per_block())          // the emulator's block size is a run-time choice
 #else
-#define LWFB_BLOCK_OF_WARP(w) ((w) / (LWFB_LANES_BLOCK / 32))
+#define LWFB_WARPS_PER_BLOCK (LWFB_LANES_BLOCK / 32)
 #endif
+#define LWFB_BLOCK_OF_WARP(w) ((w) / LWFB_WARPS_PER_BLOCK)
+// shared memory of a block (doubles): per-thread columns, log table, per-member slots, forcing rows of two days per member
+#define LWFB_SMEM_DOUBLES(mpb) ((size_t)KC_COUNT * LWFB_LANES_BLOCK + 3 * LWFB_LOG_TAB_N + (size_t)(KM_COUNT + 2 * LWFB_F) * (mpb))
 
-template <int NMAX, int EQ>
+// NX > 0: the layer count is the compile-time constant NX (index arithmetic and the broadcast loops resolve at compile
+// time); 0: run-time N <= NMAX.  LEAN: the ensemble uses none of the optional flow paths - no bypass flow (BYPAR), no
+// source-area flow (QLAYER), no downslope flow, no groundwater storage feedback (GSC) - which is what DevData::lean
+// certifies (checked on the device when the members are set); their code, registers and constants disappear from the
+// stepping loop.  All of BASELINE.json's ensemble configurations are lean.  Same results as the general kernel.
+template <int NMAX, int EQ, int NX = 0, bool LEAN = false>
 __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, const int64_t warp_g, double* cst,
-                                           const double* ltab /* log table (shared-memory copy on the device) */) {
-  const int N = d.N;
+                                           const double* ltab /* log table (shared-memory copy on the device) */,
+                                           double* msm_block /* per-member slots + forcing rows of the block */) {
+  const int N = NX > 0 ? NX : d.N;
   const int mpw = 32 / N;                            // members per warp
+  const int mpb = LWFB_WARPS_PER_BLOCK * mpw;        // members per block
   const int64_t M = d.M;
   int g = lane / N;
   int i = lane - g * N;
   const bool lane_valid = g < mpw;
   if (!lane_valid) { g = 0; i = 0; }                 // surplus lanes shadow lane 0 and never commit
   const int base = g * N;
+  const int mib = (int)(warp_g % LWFB_WARPS_PER_BLOCK) * mpw + g;   // member within the block
+  double* const msm = msm_block + mib;               // the member's slots: msm[k * mpb]
+  const double* const xgrp = cst - (lane - base) + (size_t)KC_XCH * LWFB_LANES_BLOCK;   // exchange slots of the group: xgrp[j] = lane j's
+  double* const frow2 = msm_block + (size_t)KM_COUNT * mpb + (size_t)mib * 2 * LWFB_F;   // its two staged forcing rows
   const int64_t m_raw = warp_g * mpw + g;            // slot of the group
   const int64_t n_slots = d.n_slots > 0 ? d.n_slots : M;
   const int64_t slot = (m_raw < n_slots) ? m_raw : n_slots - 1;
@@ -175,23 +206,23 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     SETC(KC_WETF, BYPAR ? pv.Lp(LWFB_L_WETF, i) : 0.0);
     SETC(KC_RDZ_UP, top ? 1.0 : LWFB_RCP(pv.Lp(LWFB_L_DZ, i - 1))); SETC(KC_RDZ_DN, bot ? 1.0 : LWFB_RCP(pv.Lp(LWFB_L_DZ, i)));
     SETC(KC_RTHS2, LWFB_RCP(THSAT * THSAT));
-    SETC(KC_DPSIMAX, pv.S(LWFB_S_DPSIMAX)); SETC(KC_DTIMAX, pv.S(LWFB_S_DTIMAX)); SETC(KC_DRAIN, pv.S(LWFB_S_DRAIN));
-    SETC(KC_GSC, pv.S(LWFB_S_GSC)); SETC(KC_GSP, pv.S(LWFB_S_GSP)); SETC(KC_IMPERV, pv.S(LWFB_S_IMPERV));
-    SETC(KC_QFFC, pv.S(LWFB_S_QFFC)); SETC(KC_QFPAR, pv.S(LWFB_S_QFPAR));
-    SETC(KC_SWATQF, pv.S(LWFB_S_SWATQF)); SETC(KC_SWATQX, pv.S(LWFB_S_SWATQX));
+    SETM(KM_DPSIMAX, pv.S(LWFB_S_DPSIMAX)); SETM(KM_DTIMAX, pv.S(LWFB_S_DTIMAX)); SETM(KM_DRAIN, pv.S(LWFB_S_DRAIN));
+    SETM(KM_GSC, pv.S(LWFB_S_GSC)); SETM(KM_GSP, pv.S(LWFB_S_GSP)); SETM(KM_IMPERV, pv.S(LWFB_S_IMPERV));
+    SETM(KM_QFFC, pv.S(LWFB_S_QFFC)); SETM(KM_QFPAR, pv.S(LWFB_S_QFPAR));
+    SETM(KM_SWATQF, pv.S(LWFB_S_SWATQF)); SETM(KM_SWATQX, pv.S(LWFB_S_SWATQX));
     QLAYER = (int)pv.S(LWFB_S_QLAYER);
     const double DSLOPE = pv.S(LWFB_S_DSLOPE), LEN = pv.S(LWFB_S_LENGTH_SLOPE);
     SLOPE = !(LEN == 0 || DSLOPE == 0);
     const double cs = SLOPE ? lwfb_cos(DSLOPE) : 1.0, sn = SLOPE ? lwfb_sin(DSLOPE) : 0.0;   // DSLOPE used as radians (reference quirk)
-    SETC(KC_CS, cs); SETC(KC_SNRHO, sn * p_RHOWG); SETC(KC_LEN1000, 1000 * LEN);
+    SETM(KM_CS, cs); SETM(KM_SNRHO, sn * p_RHOWG); SETM(KM_LEN1000, 1000 * LEN);
     SETC(KC_ARATIO, SLOPE ? THICK * (1 - STONEF) * cs / (1000 * LEN) : 0.0);
-    SETC(KC_LAM, pv.S(LWFB_S_DISPERSIVITY)); SETC(KC_VXYLEM, pv.S(LWFB_S_VXYLEM));
+    SETM(KM_LAM, pv.S(LWFB_S_DISPERSIVITY)); SETM(KM_VXYLEM, pv.S(LWFB_S_VXYLEM));
   }
   const unsigned grpmask = (N == 32) ? LFULL : (((1u << N) - 1u) << base);
   // warp-uniform switches, voted once (inside the loops they would be re-derived from global memory at every use)
-  const bool any_bypar = __any_sync(LFULL, BYPAR), any_qlayer = __any_sync(LFULL, QLAYER > 0);
-  const bool any_slope = __any_sync(LFULL, SLOPE);
-  const bool gw_feedback = __any_sync(LFULL, !(pv.S(LWFB_S_GSC) < 1.0e-8));   // GWAT enters the RHS only through GSC >= 1e-8
+  const bool any_bypar = LEAN ? false : __any_sync(LFULL, BYPAR), any_qlayer = LEAN ? false : __any_sync(LFULL, QLAYER > 0);
+  const bool any_slope = LEAN ? false : __any_sync(LFULL, SLOPE);
+  const bool gw_feedback = LEAN ? false : __any_sync(LFULL, !(pv.S(LWFB_S_GSC) < 1.0e-8));   // GWAT enters the RHS only through GSC >= 1e-8
 
   // ---- live state: fin := u0 (then kept current at day boundaries); registers for what evolves per step
   const bool resume = d.resume != 0;                 // continue from the checkpoint of the previous launch
@@ -203,9 +234,12 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
   double y = FIN(ix.SWATI + i), G = FIN(ix.GWAT);
   double Q[EQ], kFQ[EQ];
   int qe[EQ];                                        // accumulator held in slot j (>= 8: none)
+  int qr[EQ];                                        // its rate slot (KM_RATE0 + qr; 8 = the zero)
+  SETM(KM_RATE_ZERO, 0.0);
 #pragma unroll
   for (int j = 0; j < EQ; j++) {
     qe[j] = i + j * N;
+    qr[j] = qe[j] < 8 ? qe[j] : 8;
     Q[j] = qe[j] < 8 ? FIN(ix.ACC + lAccPos[qe[j] & 7]) : 0.0;
     kFQ[j] = resume ? CKL(LWFB_CKL_KFQ + j) : 0.0;
   }
@@ -213,15 +247,18 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
   auto SETK = [&](int k, double v) { cst[k * LWFB_LANES_BLOCK] = v; };
   for (int s = 0; s < 2; s++) {
     SETK(KC_DS_18O + s, iso ? FIN(ix.SWATI + (s + 1) * N + i) : 0.0);
-    SETK(KC_DG_18O + s, iso ? FIN(ix.GWAT + 1 + s) : 0.0);
-    SETK(KC_DXY_18O + s, iso ? FIN(ix.XYLEM + 1 + s) : 0.0);
+    SETM(KM_DG_18O + s, iso ? FIN(ix.GWAT + 1 + s) : 0.0);
+    SETM(KM_DXY_18O + s, iso ? FIN(ix.XYLEM + 1 + s) : 0.0);
   }
-  double TRANI = resume ? CKL(LWFB_CKL_TRANI) : NAN; // frozen uptake of the layer
+  // (the frozen fluxes of the day live in shared memory: read once or twice per RHS evaluation, they were the first
+  // victims of the register allocator, and a spilled register costs an L2 round trip here - the L1 left beside
+  // 2 x 100 KB of shared memory is far smaller than the blocks' local memory)
+  SETK(KC_TRANI, resume ? CKL(LWFB_CKL_TRANI) : NAN);   // frozen uptake of the layer
   double ntfli = resume ? CKL(LWFB_CKL_NTFLI) : NAN; // du_NTFLI of the previous RHS call (NaN on a fresh problem)
-  double RS = resume ? CKP(LWFB_CK_RS) : NAN, SLVP = resume ? CKP(LWFB_CK_SLVP) : NAN;   // RNET + SMLT and SLVP of the day
+  SETM(KM_RS, resume ? CKP(LWFB_CK_RS) : NAN); SETM(KM_SLVP, resume ? CKP(LWFB_CK_SLVP) : NAN);   // RNET + SMLT and SLVP of the day
   if (resume) {                                      // day constants of the callback
-    SETK(KC_SUMT, CKP(LWFB_CK_SUMT)); SETK(KC_SUMT_V, CKP(LWFB_CK_SUMT_V));
-    SETK(KC_D0_18O, CKP(LWFB_CK_D0_18O)); SETK(KC_D0_2H, CKP(LWFB_CK_D0_2H));
+    SETM(KM_SUMT, CKP(LWFB_CK_SUMT)); SETM(KM_SUMT_V, CKP(LWFB_CK_SUMT_V));
+    SETM(KM_D0_18O, CKP(LWFB_CK_D0_18O)); SETM(KM_D0_2H, CKP(LWFB_CK_D0_2H));
   }
   double VV = 0, INFLI = 0, DSFLI = 0;               // flux caches of the last RHS (isotope step)
 
@@ -242,16 +279,28 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     for (int j = 0; j < EQ; j++) if (qe[j] < 8) FIN(ix.ACC + lAccPos[qe[j] & 7]) = Q[j];
     if (top) {
       FIN(ix.GWAT) = G;
-      if (iso) { FIN(ix.GWAT + 1) = LC(KC_DG_18O); FIN(ix.GWAT + 2) = LC(KC_DG_2H); FIN(ix.XYLEM + 1) = LC(KC_DXY_18O); FIN(ix.XYLEM + 2) = LC(KC_DXY_2H); }
+      if (iso) { FIN(ix.GWAT + 1) = LM(KM_DG_18O); FIN(ix.GWAT + 2) = LM(KM_DG_2H); FIN(ix.XYLEM + 1) = LM(KM_DXY_18O); FIN(ix.XYLEM + 2) = LM(KM_DXY_2H); }
     }
   };
+  // Forcing: the rows of the current and of the next day of the member's site are STAGED in shared memory (two slots per
+  // member, row r in slot r & 1).  The daily callback at day d reads row d, which was fetched a day of simulated time
+  // earlier, and starts the asynchronous copy (cp.async, 16 bytes per lane and instruction) of row d + 1 into the other
+  // slot; the per-step isotope update reads delta of precipitation from whichever of the two rows applies (the value of
+  // row r holds for t in (r - 0.5, r + 0.5]).  No load of forcing data is ever waited for inside the stepping loop.
+  auto stage_row = [&](int day) {
+    const int r = day < 0 ? 0 : (day > d.n_rows - 1 ? d.n_rows - 1 : day);
+    const double* src = forc + (int64_t)r * LWFB_F;
+    double* dst = frow2 + (day & 1) * LWFB_F;
+    for (int c = i; c < LWFB_F / 2; c += N) lwfb_cp_async16(dst + 2 * c, src + 2 * c);
+  };
+  auto staged_wait = [&]() { lwfb_cp_async_wait_all(); __syncwarp(LFULL); };   // own copies landed, then visible to the group
   auto prec_delta = [&](double t, double* dp) {
     int r = (int)ceil(t - 0.5);
     r = r < 0 ? 0 : (r > d.n_rows - 1 ? d.n_rows - 1 : r);
-    dp[0] = __ldg(forc + (int64_t)r * LWFB_F + LWFB_F_D18O);
-    dp[1] = __ldg(forc + (int64_t)r * LWFB_F + LWFB_F_D2H);
+    const volatile double* row = frow2 + (r & 1) * LWFB_F;
+    dp[0] = row[LWFB_F_D18O];
+    dp[1] = row[LWFB_F_D2H];
   };
-
   // goodness-of-fit sums at the observation days (lwfb_set_observations), from what daily record r holds: theta of the
   // observed layers from SWATI, delta18O.  Called by the whole warp; `mine`: the lane's member saves record r now.
   // Same expressions and the same order (days outer, layers inner) as score_sums_kernel uses on a resident record.
@@ -303,6 +352,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
   if (d.rec && live && !resume) for (int j = i; j < L; j += N) rec_m[j] = U0(j);     // record 0 = raw u0
   __syncwarp(LFULL);
   if (!resume) score_rec(0, true, U0(ix.SWATI + i), iso ? U0(ix.SWATI + N + i) : 0.0);
+  { const int d0 = (int)floor(t); stage_row(d0); stage_row(d0 + 1); staged_wait(); }
 
   for (;;) {
     const bool active = (status == LWFB_ST_OK) && (t < tend);
@@ -341,26 +391,27 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       int cbst = LWFB_ST_OK;
       DayState nds;
       nds.INTS = FIN(ix.INTS); nds.INTR = FIN(ix.INTR); nds.SNOW = FIN(ix.SNOW); nds.CC = FIN(ix.CC); nds.SNOWLQ = FIN(ix.SNOWLQ);
-      cb_core<NMAX>(pv, forc + (int64_t)day * LWFB_F, t, psim0, psiti_a, kk_a, nds, TRANI_a, nRNET, nSMLT, nSLVP, nTA,
+      staged_wait();                                // row `day` was requested at the previous callback (or at the start)
+      cb_core<NMAX>(pv, frow2 + (day & 1) * LWFB_F, t, psim0, psiti_a, kk_a, nds, TRANI_a, nRNET, nSMLT, nSLVP, nTA,
                     TRANIst_a, nRWU, cbst);
       __syncwarp(LFULL);                            // every lane has read the day-constant states before lane 0 overwrites them
       if (at_cb) {
         waited = 0;
         y = sw;
-        TRANI = TRANI_a[i];
+        SETK(KC_TRANI, TRANI_a[i]);
         {
           double sT = 0;                         // sum of the layer uptakes and its ratio to the xylem volume (isotope step)
           for (int j = 0; j < N; j++) sT += TRANI_a[j];
-          cst[KC_SUMT * LWFB_LANES_BLOCK] = sT;
-          cst[KC_SUMT_V * LWFB_LANES_BLOCK] = sT / LC(KC_VXYLEM);
+          SETM(KM_SUMT, sT);
+          SETM(KM_SUMT_V, sT / LM(KM_VXYLEM));
         }
-        RS = nRNET + nSMLT; SLVP = nSLVP;
+        SETM(KM_RS, nRNET + nSMLT); SETM(KM_SLVP, nSLVP);
         {
           // molecular diffusivities of the day (soil temperature = daily mean air temperature)
           const double Tk = nTA + 273.15;
           const double ee = lwfb_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
-          SETK(KC_D0_18O, 0.96691 * 1e-9 * ee * 3600 * 24);
-          SETK(KC_D0_2H, 0.98331 * 1e-9 * ee * 3600 * 24);
+          SETM(KM_D0_18O, 0.96691 * 1e-9 * ee * 3600 * 24);
+          SETM(KM_D0_2H, 0.98331 * 1e-9 * ee * 3600 * 24);
         }
         if (cbst != LWFB_ST_OK) status = cbst;
 #pragma unroll
@@ -382,6 +433,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         reeval = true;
         at_boundary = false;
         tstop = fmin(tstop + 1.0, tend);
+        stage_row(day + 1);                          // asynchronous: needed from t = day + 0.5 on (delta of precipitation)
       }
       __syncwarp(LFULL);
       continue;
@@ -482,8 +534,10 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       const double x1 = p1 - 1.0, x3 = 1.0 - p3;             // both are 0 at saturation (log -> -inf, power -> 0)
       double l1, l3;
       lwfb_log_main2_t(x1, x3, &l1, &l3, ltab);               // two interleaved chains, then the rare fix-ups
-      if (lwfb_log_isspecial(x1)) l1 = lwfb_log_cold(x1);
-      if (lwfb_log_isspecial(x3)) l3 = lwfb_log_cold(x3);
+      if (lwfb_log_isspecial(x1) | lwfb_log_isspecial(x3)) {                // one test for both (rare: saturation)
+        if (lwfb_log_isspecial(x1)) l1 = lwfb_log_cold(x1);
+        if (lwfb_log_isspecial(x3)) l3 = lwfb_log_cold(x3);
+      }
       double e1, e3;
       lwfb_exp2(E2 * l1, LC(KC_E4) * l3, &e1, &e3);
       const double psim = LC(KC_CPSI) * e1;
@@ -497,7 +551,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       double BYFRAC = 0;
       if (any_bypar) {
         const double WETF = LC(KC_WETF);
-        double bf = jminc(lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (w - WETF) / (1 - WETF)), 1.0);
+        double bf = jminc(lwfb_pow(LM(KM_QFFC), 1 - (1 / LM(KM_QFPAR)) * (w - WETF) / (1 - WETF)), 1.0);
         if (w > 0.99) bf = 1;
         BYFRAC = BYPAR ? bf : 0.0;
       }
@@ -506,15 +560,16 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         double sq = 0;
         for (int j = 0; j < N; j++) { const double v = bcast(sw, j); if (j < QLAYER) sq += v; }
         if (QLAYER > 0) {
-          const double SWATQF = LC(KC_SWATQF);
-          SAFRAC = jminc(lwfb_pow(LC(KC_QFFC), 1 - (1 / LC(KC_QFPAR)) * (sq - SWATQF) / (LC(KC_SWATQX) - SWATQF)), 1.0);
+          const double SWATQF = LM(KM_SWATQF);
+          SAFRAC = jminc(lwfb_pow(LM(KM_QFFC), 1 - (1 / LM(KM_QFPAR)) * (sq - SWATQF) / (LM(KM_SWATQX) - SWATQF)), 1.0);
         }
       }
-      const double SRFL = jminc(LC(KC_IMPERV) + SAFRAC, 1.) * RS;
+      const double RS = LM(KM_RS);
+      const double SRFL = jminc(LM(KM_IMPERV) + SAFRAC, 1.) * RS;
       const double SLFL = RS - SRFL;
       DSFLI = 0;
       if (any_slope) {
-        const double GRAD = LC(KC_CS) * (psim * 2 / LC(KC_LEN1000)) + LC(KC_SNRHO);
+        const double GRAD = LM(KM_CS) * (psim * 2 / LM(KM_LEN1000)) + LM(KM_SNRHO);
         const double dd = kkv * LC(KC_ARATIO) * GRAD / p_RHOWG;
         DSFLI = (SLOPE && !(dd < 0)) ? dd : 0.0;
       }
@@ -522,19 +577,19 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       const double psit_dn = __shfl_down_sync(LFULL, psit, 1), lk_dn = __shfl_down_sync(LFULL, lk, 1);
       double V0;
       {
-        const double THICK = LC(KC_THICK), DRAIN = LC(KC_DRAIN);
+        const double THICK = LC(KC_THICK), DRAIN = LM(KM_DRAIN);
         double kkmean = lwfb_exp(div_c(LC(KC_THICK_DN) * lk + THICK * lk_dn, LC(KC_TSUM), LC(KC_RTSUM)));
-        kkmean = jmin(jmin(kkmean, KSAT), LC(KC_KSAT_DN));
+        kkmean = jminc(jminc(kkmean, KSAT), LC(KC_KSAT_DN));   // (a NaN conductivity has made kkmean NaN already)
         const double dpsi = nodn ? 1.0 : (psit - psit_dn);     // no layer below: value unused, keep the divisions on their fast path
         const double grad = div_c(dpsi, LC(KC_THALF), LC(KC_RTHALF));
         const double vd = div_c(grad * kkmean, p_RHOWG, LWFB_RCP(p_RHOWG)) * LC(KC_STFAC);
         const double vb = (DRAIN > 0.00001) ? DRAIN * kkv * LC(KC_OMS) : 0.0;
-        V0 = bot ? vb : ((fabs(psit - psit_dn) < LC(KC_DPSIMAX)) ? 0.0 : vd);
+        V0 = bot ? vb : ((fabs(psit - psit_dn) < LM(KM_DPSIMAX)) ? 0.0 : vd);
       }
       const double V0_up = __shfl_up_sync(LFULL, V0, 1);        // prior flux from the layer above (unused at the top)
       // ITER: min-chain over the layers in index order (the clamp to DTIMIN makes the order matter)
       const double DTRI = 1.0 - (ts - floor(ts));                // = 1 - fmod(ts, 1) for ts >= 0
-      double DTI = jmin(DTRI, LC(KC_DTIMAX));
+      double DTI = jmin(DTRI, LM(KM_DTIMAX));
       {
         const double c1 = LC(KC_CITER) / jmaxc(fabs(nt), 0.000001);
         const double c2 = div_c(((THR - theta) * LC(KC_THICK)) / nt, 1.30, LWFB_RCP(1.30));
@@ -555,27 +610,29 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
           }
           if (DTINEW < DTI) DTI = DTINEW;
         } else {
+          // every lane posts its bound in its exchange slot and reads the N of its group (same comparison order as the
+          // broadcast loop of the slow path)
+          cst[KC_XCH * LWFB_LANES_BLOCK] = v;
+          __syncwarp(LFULL);
           double gm = v;
-          if (NMAX <= 8) {
-            double vj[NMAX];
+          if (NX > 0) {
 #pragma unroll
-            for (int j = 0; j < NMAX; j++) vj[j] = bcast(v, j < N ? j : 0);     // independent shuffles, issued back to back
-#pragma unroll
-            for (int j = 0; j < NMAX; j++) gm = vj[j] < gm ? vj[j] : gm;
+            for (int j = 0; j < NX; j++) { const double vj = *(const volatile double*)(xgrp + j); gm = vj < gm ? vj : gm; }
           } else {
-            for (int j = 0; j < N; j++) { const double vj = bcast(v, j); gm = vj < gm ? vj : gm; }
+            for (int j = 0; j < N; j++) { const double vj = *(const volatile double*)(xgrp + j); gm = vj < gm ? vj : gm; }
           }
           if (gm < DTI) DTI = gm;
         }
       }
       // INFLOW
       const double INFRAC = LC(KC_INFRAC);
-      double BYFLI = SLFL * INFRAC * BYFRAC;
-      INFLI = SLFL * INFRAC * (1.0 - BYFRAC);
+      double BYFLI = LEAN ? 0.0 : SLFL * INFRAC * BYFRAC;
+      INFLI = LEAN ? SLFL * INFRAC : SLFL * INFRAC * (1.0 - BYFRAC);
       VV = V0;
       {
         const double room = (SWATMAX - sw) / DTI;
         // no layer limits (the common case) <=> every layer passes its test with the unmodified fluxes
+        const double TRANI = LC(KC_TRANI), SLVP = LM(KM_SLVP);
         double MAXIN = room + V0 + DSFLI + TRANI;
         if (top) MAXIN = MAXIN + SLVP;
         const bool limited = top ? (INFLI > MAXIN) : (V0_up + INFLI > MAXIN);
@@ -615,13 +672,13 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       }
       const double VV_up = __shfl_up_sync(LFULL, VV, 1);
       double du0;
-      if (top) du0 = INFLI - VV - DSFLI - TRANI - SLVP;
-      else du0 = VV_up + INFLI - VV - DSFLI - TRANI;
+      if (top) du0 = INFLI - VV - DSFLI - LC(KC_TRANI) - LM(KM_SLVP);
+      else du0 = VV_up + INFLI - VV - DSFLI - LC(KC_TRANI);
       const double VN = bcast(VV, N - 1);
       double GWFL, SEEP;
       {
-        const double GSC = LC(KC_GSC), GSP = LC(KC_GSP);
-        if (GSC < 1.0e-8) { SEEP = GSP * VN; GWFL = VN - SEEP; }
+        const double GSC = LM(KM_GSC), GSP = LM(KM_GSP);
+        if (LEAN || GSC < 1.0e-8) { SEEP = GSP * VN; GWFL = VN - SEEP; }
         else {
           SEEP = xG * GSC * GSP;
           GWFL = xG * GSC * (1. - GSP);
@@ -632,20 +689,15 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       if (__any_sync(LFULL, BYFLI != 0.0)) for (int j = 0; j < N; j++) sby += bcast(BYFLI, j);
       if (any_slope) for (int j = 0; j < N; j++) sds += bcast(DSFLI, j);
       const double kny = du0, knG = VN - GWFL - SEEP;
+      // rates of the 8 integrated accumulators (member-level values, identical in the lanes of the group): posted in the
+      // member's slots, every lane then reads the (up to EQ) ones it integrates
+      SETM(KM_RATE0 + 0, SRFL + sby + sds + GWFL);      // flow
+      SETM(KM_RATE0 + 1, SEEP); SETM(KM_RATE0 + 2, SRFL); SETM(KM_RATE0 + 3, SLFL); SETM(KM_RATE0 + 4, sby);
+      SETM(KM_RATE0 + 5, sds); SETM(KM_RATE0 + 6, GWFL); SETM(KM_RATE0 + 7, VN);
+      __syncwarp(LFULL);
       double knQ[EQ];
 #pragma unroll
-      for (int j = 0; j < EQ; j++) {
-        const int e = qe[j];
-        double v = SRFL + sby + sds + GWFL;                // e == 0: flow
-        v = (e == 1) ? SEEP : v;
-        v = (e == 2) ? SRFL : v;
-        v = (e == 3) ? SLFL : v;
-        v = (e == 4) ? sby : v;
-        v = (e == 5) ? sds : v;
-        v = (e == 6) ? GWFL : v;
-        v = (e == 7) ? VN : v;
-        knQ[j] = (e < 8) ? v : 0.0;
-      }
+      for (int j = 0; j < EQ; j++) knQ[j] = LM(KM_RATE0 + qr[j]);
       if (!skip0) nt = du0;
       // ---- end of RHS
 
@@ -797,14 +849,16 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     const bool do_ade = accepted && iso && (t != tstop || t < tend);
     if (__any_sync(LFULL, do_ade)) {
       double dp[2];
+      staged_wait();
       prec_delta(t, dp);
       const double THR = LC(KC_THR), DTH = LC(KC_DTH);
       const double S1 = y;
       const double w1 = jminc(div_c(div_c(LC(KC_THSAT) * S1, LC(KC_SWATMAX), LC(KC_RSWATMAX)) - THR, DTH, LC(KC_RDTH)), 1.0);
       const double th1 = w1 * DTH + THR;
-      const double sumT = LC(KC_SUMT), sumT_V = LC(KC_SUMT_V);
+      const double sumT = LM(KM_SUMT), sumT_V = LM(KM_SUMT_V);
+      const double TRANI = LC(KC_TRANI), SLVP = LM(KM_SLVP);
       const double tauth = lwfb_pow(th1, 7.0 / 3) * LC(KC_RTHS2);
-      const double aq = LC(KC_LAM) * fabs(VV * LWFB_RCP(1000.0));
+      const double aq = LM(KM_LAM) * fabs(VV * LWFB_RCP(1000.0));
       const double VN = bcast(VV, N - 1);
       const double VV_up = __shfl_up_sync(LFULL, VV, 1);
       const double RDZ_up = LC(KC_RDZ_UP), RDZ_dn = LC(KC_RDZ_DN);
@@ -813,8 +867,8 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 #pragma unroll 1
       for (int s = 0; s < 2; s++) {
         const double R = s == 0 ? R18 : R2H;
-        const double D0 = LC(KC_D0_18O + s);
-        const double dSs = LC(KC_DS_18O + s), dGs = LC(KC_DG_18O + s), dXYs = LC(KC_DXY_18O + s);
+        const double D0 = LM(KM_D0_18O + s);
+        const double dSs = LC(KC_DS_18O + s), dGs = LM(KM_DG_18O + s), dXYs = LM(KM_DXY_18O + s);
         const double dps = s == 0 ? dp[0] : dp[1];
         // the three member-level mixing ratios (xylem, precipitation, groundwater) are converted by lanes 0, 1, 2 of the
         // group in ONE evaluation of d_to_x and broadcast
@@ -850,7 +904,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         const double dRW = nouptake ? NAN : dRWc;
         const double ddxy = (dRW != dRW) ? 0.0 : sumT_V * (dRW - dXYs);
         if (do_ade) {
-          SETK(KC_DG_18O + s, dGs + dtt * ddG); SETK(KC_DS_18O + s, dSs + dtt * dd); SETK(KC_DXY_18O + s, dXYs + dtt * ddxy);
+          SETM(KM_DG_18O + s, dGs + dtt * ddG); SETK(KC_DS_18O + s, dSs + dtt * dd); SETM(KM_DXY_18O + s, dXYs + dtt * ddxy);
           if (top && live) FIN(ix.RWU + 1 + s) = dRW;
         }
       }
@@ -860,7 +914,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     if (d.ck) {
       // checkpoint for the next launch: everything the loop keeps in registers / shared memory and flush_state does
       // not put into fin (controller, counters, clock, FSAL derivatives, day constants)
-      CKL(LWFB_CKL_NTFLI) = ntfli; CKL(LWFB_CKL_TRANI) = TRANI; CKL(LWFB_CKL_KFY) = kFy; CKL(LWFB_CKL_NAN) = cand_nan ? 1.0 : 0.0;
+      CKL(LWFB_CKL_NTFLI) = ntfli; CKL(LWFB_CKL_TRANI) = LC(KC_TRANI); CKL(LWFB_CKL_KFY) = kFy; CKL(LWFB_CKL_NAN) = cand_nan ? 1.0 : 0.0;
 #pragma unroll
       for (int j = 0; j < EQ; j++) CKL(LWFB_CKL_KFQ + j) = kFQ[j];
       if (top) {
@@ -868,9 +922,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         CKP(LWFB_CK_NACCEPT) = (double)naccept; CKP(LWFB_CK_NREJECT) = (double)nreject; CKP(LWFB_CK_NF) = (double)nf;
         CKP(LWFB_CK_REC) = (double)rec; CKP(LWFB_CK_T) = t; CKP(LWFB_CK_TSTOP) = tstop;
         CKP(LWFB_CK_FLAGS) = (double)((reeval ? 1 : 0) | (at_boundary ? 2 : 0));
-        CKP(LWFB_CK_RS) = RS; CKP(LWFB_CK_SLVP) = SLVP; CKP(LWFB_CK_KFG) = kFG;
-        CKP(LWFB_CK_SUMT) = LC(KC_SUMT); CKP(LWFB_CK_SUMT_V) = LC(KC_SUMT_V);
-        CKP(LWFB_CK_D0_18O) = LC(KC_D0_18O); CKP(LWFB_CK_D0_2H) = LC(KC_D0_2H);
+        CKP(LWFB_CK_RS) = LM(KM_RS); CKP(LWFB_CK_SLVP) = LM(KM_SLVP); CKP(LWFB_CK_KFG) = kFG;
+        CKP(LWFB_CK_SUMT) = LM(KM_SUMT); CKP(LWFB_CK_SUMT_V) = LM(KM_SUMT_V);
+        CKP(LWFB_CK_D0_18O) = LM(KM_D0_18O); CKP(LWFB_CK_D0_2H) = LM(KM_D0_2H);
       }
     }
     if (d.n_obs_layers > 0 && top && status != LWFB_ST_OK && status_in == LWFB_ST_OK) {
@@ -908,17 +962,19 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 }
 
 #ifdef __CUDACC__
-template <int NMAX, int EQ>
+template <int NMAX, int EQ, int NX = 0, bool LEAN = false>
 __global__ void __launch_bounds__(LWFB_LANES_BLOCK, LWFB_LANES_MINBLOCKS) integrate_lanes(DevData d) {
   extern __shared__ double lanes_smem[];
   double* ltab = lanes_smem + (size_t)KC_COUNT * LWFB_LANES_BLOCK;     // shared-memory copy of the log table
+  double* msm_block = ltab + 3 * LWFB_LOG_TAB_N;                       // per-member slots, then the staged forcing rows
   for (int k = threadIdx.x; k < 3 * LWFB_LOG_TAB_N; k += LWFB_LANES_BLOCK) ltab[k] = lwfb_log_tab_d[k];
   __syncthreads();
   unsigned tid = threadIdx.x;
   asm volatile("" : "+r"(tid));     // opaque copy of %tid: the column address stays in a register (it would be re-derived
                                     // from %tid at every use otherwise) and is still known to point to shared memory
   const bool by_budget =
-      lanes_body<NMAX, EQ>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + tid, ltab);
+      lanes_body<NMAX, EQ, NX, LEAN>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + tid, ltab,
+                                     msm_block);
   if (d.stop) {
     __syncthreads();
     if (threadIdx.x == 0) {

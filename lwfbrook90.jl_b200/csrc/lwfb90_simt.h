@@ -73,7 +73,17 @@ static inline int __double2loint(double x) { long long i; memcpy(&i, &x, 8); ret
 static inline double __hiloint2double(int hi, int lo) { long long i = ((long long)hi << 32) | (unsigned)lo; double x; memcpy(&x, &i, 8); return x; }
 // value barrier: the optimiser must treat x as unknown from here on
 #define LWFB_OPAQUE(x) asm volatile("" : "+x"(x))
+// asynchronous 16-byte copy global -> shared (cp.async) and the wait for the thread's outstanding copies
+static inline void lwfb_cp_async16(void* smem_dst, const void* gmem_src) { memcpy(smem_dst, gmem_src, 16); }
+static inline void lwfb_cp_async_wait_all() {}
 #else
 #include <cuda_runtime.h>
 #define LWFB_OPAQUE(x) asm volatile("" : "+d"(x))
+// asynchronous 16-byte copy global -> shared (LDGSTS: the data does not pass through registers and the thread does not
+// wait for it) and the wait for the thread's outstanding copies
+__device__ __forceinline__ void lwfb_cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void lwfb_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #endif

@@ -258,9 +258,10 @@ struct Job {
   int stop[2] = {0, 0};
   std::atomic<int64_t> exited{0};
   int resident = 1;           // blocks "resident" at a time = worker threads
+  bool lean = false;          // no member uses an optional flow path: the lean instantiations apply (as in the library)
 };
 
-struct WarpArg { const lwfb::DevData* d; int64_t block; int warps; double* cst; bool by_budget; };
+struct WarpArg { const lwfb::DevData* d; int64_t block; int warps; double* cst; bool by_budget; bool lean; double* msm; };
 
 void lanes_entry(void* a, int tid) {             // tid = thread index within the emulated block
   WarpArg* wa = (WarpArg*)a;
@@ -269,10 +270,12 @@ void lanes_entry(void* a, int tid) {             // tid = thread index within th
   const int lane = tid & 31;
   const int64_t warp_g = wa->block * wa->warps + (tid >> 5);
   bool b;
-  if (d.N == 3) b = lwfb::lanes_body<8, 3>(d, lane, warp_g, cst, lwfb_log_tab_h);
-  else if (d.N < 8) b = lwfb::lanes_body<8, 2>(d, lane, warp_g, cst, lwfb_log_tab_h);
-  else if (d.N == 8) b = lwfb::lanes_body<8, 1>(d, lane, warp_g, cst, lwfb_log_tab_h);
-  else b = lwfb::lanes_body<32, 1>(d, lane, warp_g, cst, lwfb_log_tab_h);
+  if (wa->lean && d.N == 5) b = lwfb::lanes_body<8, 2, 5, true>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
+  else if (wa->lean && d.N == 7) b = lwfb::lanes_body<8, 2, 7, true>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
+  else if (d.N == 3) b = lwfb::lanes_body<8, 3>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
+  else if (d.N < 8) b = lwfb::lanes_body<8, 2>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
+  else if (d.N == 8) b = lwfb::lanes_body<8, 1>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
+  else b = lwfb::lanes_body<32, 1>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
   if (tid == 0) wa->by_budget = b;
 }
 
@@ -283,7 +286,8 @@ void* worker(void* p) {
     if (u >= j->n_units) break;
     if (j->kernel == 0) {
       std::vector<double> cst((size_t)lwfb::KC_COUNT * LWFB_LANES_BLOCK);
-      WarpArg wa{&j->d, u, j->warps, cst.data(), false};
+      std::vector<double> msm((size_t)(lwfb::KM_COUNT + 2 * LWFB_F) * j->warps * (32 / j->d.N));
+      WarpArg wa{&j->d, u, j->warps, cst.data(), false, j->lean, msm.data()};
       run_block(lanes_entry, &wa, j->warps);
       if (j->use_stop) {
         const int64_t n_exited = j->exited.fetch_add(1) + 1;
@@ -344,6 +348,16 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   d.obs_theta = g_obs_theta.empty() ? nullptr : g_obs_theta.data();
   d.obs_d18o = g_obs_d18o.empty() ? nullptr : g_obs_d18o.data();
   d.sacc = g_sacc.data();
+  {   // the library's classification (optional_paths_kernel); LWFB_EMUL_GENERAL=1 keeps the general instantiation
+    bool used = false;
+    for (int64_t m = 0; m < M; m++) {
+      const double* sc = scal + m * LWFB_PS;
+      const bool slope = !(sc[LWFB_S_LENGTH_SLOPE] == 0 || sc[LWFB_S_DSLOPE] == 0);
+      used = used || !(sc[LWFB_S_GSC] < 1.0e-8) || sc[LWFB_S_BYPAR] == 1.0 || (int)sc[LWFB_S_QLAYER] > 0 || slope;
+    }
+    const char* g = getenv("LWFB_EMUL_GENERAL");
+    job.lean = !used && !(g && atoi(g) != 0);
+  }
   job.kernel = kernel;
   if (warps_per_block < 1 || warps_per_block > MAX_WARPS) return 4;
   job.warps = warps_per_block;
