@@ -275,12 +275,22 @@ enum { LWFB_SV_THETA = 0, LWFB_SV_PSI /* kPa */, LWFB_SV_W, LWFB_SV_SWATI /* mm 
 int lwfb_soil_state(lwfb_handle* h, int32_t n_rec_sel, const int32_t* rec_idx, int32_t n_lay_sel,
                     const int32_t* layer_idx, double* out);
 
+/* du_NTFLI across runs.  The reference keeps the net layer flows of the last RHS evaluation in `p` (du_NTFLI), and `p`
+ * survives simulate!: a second run on the same problem starts its first ITER from them instead of NaN (SURVEY A.5 #19;
+ * test/01-unit-tests.jl:875, :904 produce golden G5 that way).  lwfb_get_ntfli returns them after a run
+ * (out [n_members][N]); lwfb_set_ntfli0 hands them to the following runs (NULL = fresh problem; setting the members
+ * anew also clears them). */
+int lwfb_set_ntfli0(lwfb_handle* h, const double* ntfli0);
+int lwfb_get_ntfli(lwfb_handle* h, double* out);
+
 /* one evaluation of the right-hand side f(u,p,t) for every member, for unit parity tests
  * (replaces f_LWFBrook90!, src/func_DiffEq_definition_f.jl:7-243):
  *   swati [n_members][N], gwat [n_members], t scalar, daily-frozen fluxes as set by the
  *   daily callback are taken from `frozen` [n_members][N+3] = (RNET, SMLT, SLVP, TRANI[N]);
  *   ntfli_prev [n_members][N] is the stale du_NTFLI consumed by ITER (NaN on first call).
- *   du [n_members][N+9] = (dSWATI[N], dGWAT, flow, seep, srfl, slfl, byfl, dsfl, gwfl, vrfln) */
+ *   du [n_members][N+9] = (dSWATI[N], dGWAT, flow, seep, srfl, slfl, byfl, dsfl, gwfl, vrfln)
+ * Evaluated by the kernel that would integrate the members: for 3 <= N <= 32 the lane-per-layer production kernel
+ * (through its own stage code), else the thread-per-member kernel (lwfb_debug_force_legacy selects explicitly). */
 int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, const double* gwat,
                   const double* frozen, const double* ntfli_prev, double* du);
 

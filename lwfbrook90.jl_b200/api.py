@@ -130,19 +130,41 @@ def _successful(status: int) -> bool:
     return status == 0
 
 
+_SOLVE_KW = {"reltol": "reltol", "abstol": "abstol", "dt": "dt_init", "dtmax": "dtmax", "maxiters": "maxiters"}
+
+
 def simulate_(s: DiscretizedSPAC, *, assert_retcode: bool = True, saveat=None, save_everystep=None, tspan=None,
               device: int = 0, **kwargs) -> None:
     """simulate!(s): integrates the discretised SPAC on the GPU and stores the solution in
-    ``s.solution`` (``s.ODESolution``).  As in the reference only ``saveat``, ``save_everystep`` and
-    ``tspan`` may be overridden (SURVEY A.5 #21); the record is always daily (saveat = t0:1:t1)."""
+    ``s.solution`` (``s.ODESolution``).
+
+    The reference forwards its keyword arguments to solve() (src/LWFBrook90.jl:628-655).  Supported here:
+    ``tspan`` (whole days), ``reltol``, ``abstol``, ``dt``, ``dtmax``, ``maxiters`` (forwarded to the integrator),
+    ``saveat`` (whole days inside tspan: the library records the state at every day boundary).  NOT supported, and
+    refused rather than answered with something else: ``save_everystep=True`` (the reference's default; the record
+    of every accepted step is not kept on the GPU) is accepted only as the implicit default and means daily records
+    here; an explicit ``save_everystep=True``, a ``saveat`` between day boundaries (the reference interpolates between
+    its accepted steps, which would need them), and any other solve() keyword raise."""
+    solver = {}
+    for k in list(kwargs):
+        if k in _SOLVE_KW:
+            solver[_SOLVE_KW[k]] = kwargs.pop(k)
     if kwargs:
-        raise TypeError(f"simulate_: unsupported solve() keyword(s) {sorted(kwargs)}; tolerances and the "
-                        "algorithm are fixed by setup() as in the reference")
+        raise TypeError(f"simulate_: unsupported solve() keyword(s) {sorted(kwargs)} (supported: tspan, saveat on day "
+                        f"boundaries, {', '.join(sorted(_SOLVE_KW))})")
+    if save_everystep:
+        raise NotImplementedError("simulate_: save_everystep=True is not supported: the GPU integrator records the state "
+                                  "at day boundaries only (saveat = t0:1:t1)")
+    if saveat is not None:
+        sa_chk = np.asarray(list(saveat), float)
+        if np.any(sa_chk != np.floor(sa_chk)):
+            raise NotImplementedError("simulate_: saveat must lie on day boundaries; values in between would have to be "
+                                      "interpolated between the accepted steps of the solver, which are not recorded")
     t0, t1 = s.tspan if tspan is None else (float(tspan[0]), float(tspan[1]))
     if t0 != np.floor(t0) or t1 != np.floor(t1) or t1 <= t0:
         raise ValueError("tspan must have whole-day bounds")
     n_days = int(t1 - t0)
-    h = capi.Handle(s.N, s.iso, int(t0), n_days, device=device, record_daily=True)
+    h = capi.Handle(s.N, s.iso, int(t0), n_days, device=device, record_daily=True, **solver)
     try:
         h.set_sites(s.forcing)
         h.set_members([0], s.scal, s.lay, s.u0)

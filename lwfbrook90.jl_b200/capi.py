@@ -38,7 +38,8 @@ SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error"
            "lwfb_set_members", "lwfb_run", "lwfb_run_async", "lwfb_sync", "lwfb_get_daily", "lwfb_get_final",
            "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
            "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy", "lwfb_set_placement",
-           "lwfb_water_partitioning", "lwfb_soil_state", "lwfb_set_observations", "lwfb_setup_members"]
+           "lwfb_water_partitioning", "lwfb_soil_state", "lwfb_set_observations", "lwfb_setup_members",
+           "lwfb_set_ntfli0", "lwfb_get_ntfli"]
 
 
 def lib():
@@ -67,6 +68,8 @@ def lib():
         L.lwfb_set_observations.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp]; L.lwfb_set_observations.restype = C.c_int
         L.lwfb_setup_members.argtypes = [vp, C.c_int64, _ip, _dp, _dp, _dp, _dp, C.c_int32, _ip, C.c_int32, _dp, _dp, C.c_int32, _ip]
         L.lwfb_setup_members.restype = C.c_int
+        L.lwfb_set_ntfli0.argtypes = [vp, _dp]; L.lwfb_set_ntfli0.restype = C.c_int
+        L.lwfb_get_ntfli.argtypes = [vp, _dp]; L.lwfb_get_ntfli.restype = C.c_int
         L.lwfb_eval_rhs.argtypes = [vp, C.c_double, _dp, _dp, _dp, _dp, _dp]; L.lwfb_eval_rhs.restype = C.c_int
         L.lwfb_last_run_stats.argtypes = [vp, _ip, C.POINTER(C.c_float)]; L.lwfb_last_run_stats.restype = C.c_int
         L.lwfb_elem_eval.argtypes = [C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp]; L.lwfb_elem_eval.restype = C.c_int
@@ -185,6 +188,20 @@ class Handle:
         out = np.empty(shape)
         self._L.lwfb_debug_get_block.argtypes = [C.c_void_p, C.c_int32, _dp]
         self._ck(self._L.lwfb_debug_get_block(self._h, int(which), _p(out)))
+        return out
+
+    def set_ntfli0(self, ntfli0=None):
+        """du_NTFLI cache that the first ITER of the following runs sees ([M, N]); None = a fresh problem (NaN)."""
+        if ntfli0 is None:
+            self._ck(self._L.lwfb_set_ntfli0(self._h, None))
+            return
+        a = _f64(ntfli0).reshape(self.M, self.N)
+        self._ck(self._L.lwfb_set_ntfli0(self._h, _p(a)))
+
+    def get_ntfli(self):
+        """du_NTFLI as the last run left it ([M, N])."""
+        out = np.empty((self.M, self.N))
+        self._ck(self._L.lwfb_get_ntfli(self._h, _p(out)))
         return out
 
     def run(self, stream=None):

@@ -180,6 +180,7 @@ struct lwfb_handle {
   double *d_obs_theta = nullptr, *d_obs_d18o = nullptr;
   double *d_sacc = nullptr, *d_sacc_rec = nullptr;   // sums of the run / scratch of the record-based scores
   bool sums_valid = false;     // d_sacc holds the sums of a completed run
+  double *d_ntfli0 = nullptr, *d_ntfli_out = nullptr;   // du_NTFLI cache in (lwfb_set_ntfli0) / out (lwfb_get_ntfli), [M][N]
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int n_launches = 0;
   float last_ms = 0.f;
@@ -262,6 +263,7 @@ static void free_members(lwfb_handle* h) {
   cudaFree(h->d_key); cudaFree(h->d_key2); cudaFree(h->d_idx); cudaFree(h->d_sort_tmp); cudaFree(h->d_nleft);
   cudaFree(h->d_perm_thin); h->d_perm_thin = nullptr; h->perm_thin_len = 0;
   cudaFree(h->d_sacc); cudaFree(h->d_sacc_rec); h->d_sacc = h->d_sacc_rec = nullptr; h->sums_valid = false;
+  cudaFree(h->d_ntfli0); cudaFree(h->d_ntfli_out); h->d_ntfli0 = h->d_ntfli_out = nullptr;
   h->d_key = h->d_key2 = nullptr; h->d_idx = nullptr; h->d_sort_tmp = nullptr; h->d_nleft = nullptr; h->sort_tmp_bytes = 0;
   h->d_perm = nullptr; h->d_ck = nullptr; h->d_stop = nullptr; h->perm_valid = false; h->cost_valid = false;
   h->d_scal = h->d_lay = h->d_u0 = h->d_rec = h->d_fin = h->d_scores = nullptr;
@@ -311,6 +313,7 @@ extern "C" int lwfb_set_members(lwfb_handle* h, int64_t n_members, const int32_t
   CK(cudaMemcpy(h->d_lay, lay, (size_t)h->M * LWFB_PL * N * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_u0, u0, (size_t)h->M * L * sizeof(double), cudaMemcpyHostToDevice));
   { int rc = classify_members(h); if (rc) return rc; }
+  cudaFree(h->d_ntfli0); h->d_ntfli0 = nullptr;      // a warm du_NTFLI cache belongs to the members it was set for
   h->ran = false; h->sums_valid = false;
   h->cost_valid = false; h->perm_valid = false;   // counters / placement of the previous members say nothing about these
   return LWFB_OK;
@@ -331,6 +334,7 @@ static int alloc_members(lwfb_handle* h, int64_t n_members) {
   CK(cudaMalloc(&h->d_counters, (size_t)M * LWFB_NCOUNTERS * sizeof(long long)));
   CK(cudaMalloc(&h->d_scores, (size_t)M * LWFB_NSCORES * sizeof(double)));
   CK(cudaMalloc(&h->d_sacc, (size_t)M * 2 * LWFB_SA * sizeof(double)));
+  CK(cudaMalloc(&h->d_ntfli_out, (size_t)M * N * sizeof(double)));
   CK(cudaMalloc(&h->d_perm, (size_t)M * sizeof(int32_t)));
   CK(cudaMalloc(&h->d_ck, (size_t)M * (LWFB_CK + LWFB_CKL * N) * sizeof(double)));
   CK(cudaMalloc(&h->d_stop, 2 * sizeof(int)));
@@ -437,6 +441,8 @@ static DevData make_dev(lwfb_handle* h) {
   d.n_obs_layers = h->n_obs_days > 0 ? h->n_obs_layers : 0;
   d.obs_of_rec = h->d_obs_of_rec; d.obs_layer = h->d_obs_layer; d.obs_theta = h->d_obs_theta; d.obs_d18o = h->d_obs_d18o;
   d.sacc = h->d_sacc;
+  d.ntfli0 = h->d_ntfli0; d.ntfli_out = h->d_ntfli_out;
+  d.probe_frozen = nullptr; d.probe_ntfli = nullptr; d.probe_t = 0; d.probe_out = nullptr;
   if (const char* e = getenv("LWFB_CB_WAIT")) d.cb_wait = atoi(e);
   return d;
 }
@@ -486,14 +492,22 @@ static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) 
     const int64_t warps = ((d.n_slots > 0 ? d.n_slots : d.M) + mpw - 1) / mpw;
     const int wpb = LWFB_LANES_BLOCK / 32;
     const unsigned lgrid = (unsigned)((warps + wpb - 1) / wpb);
-    size_t smem = LWFB_SMEM_DOUBLES((size_t)wpb * mpw) * sizeof(double);   // columns + log table + member slots + forcing rows
+    const bool lean = h->lean && !h->force_general;
+    const bool lean_kernel = lean && (d.N == 5 || d.N == 7);
+    size_t smem = LWFB_SMEM_DOUBLES((size_t)wpb * mpw, lean_kernel) * sizeof(double);   // columns + log table + member slots + forcing rows
     if (const char* pad = getenv("LWFB_LANES_SMEM_PAD_KB")) smem += (size_t)atoi(pad) * 1024;   // profiling knob: fewer resident blocks
     // instantiations: general (run-time N, every flow path) and, for ensembles without optional flow paths, lean ones
     // with the layer count fixed at compile time for the layer counts of BASELINE.json's configurations
-    const bool lean = h->lean && !h->force_general;
+    // shared-memory carve-out: just enough for the resident blocks the kernel is built for (the rest of the 256 KB is
+    // L1, which the register spills live in; left to its own heuristics the driver has been seen to pick a carve-out
+    // that holds ONE block, halving the occupancy)
+    const size_t per_block = smem + 1024, sm_total = 228 * 1024;
+    const size_t n_res = per_block * LWFB_LANES_MINBLOCKS <= sm_total ? LWFB_LANES_MINBLOCKS : 1;
+    const int carve_pct = (int)((100 * per_block * n_res + sm_total - 1) / sm_total);
 #define LWFB_LAUNCH(...)                                                                                        \
     do {                                                                                                       \
       if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_lanes<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      cudaFuncSetAttribute(integrate_lanes<__VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct > 100 ? 100 : carve_pct); \
       integrate_lanes<__VA_ARGS__><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);                                    \
     } while (0)
 #ifndef LWFB_FIXED_N
@@ -908,6 +922,29 @@ extern "C" int lwfb_scores(lwfb_handle* h, int32_t n_obs_days, const int32_t* ob
   return LWFB_OK;
 }
 
+// The reference keeps du_NTFLI in `p` across simulate! calls on the same problem, so a second run starts its first ITER
+// from the net flows the first run left behind instead of NaN (golden G5 was produced that way,
+// test/01-unit-tests.jl:875, :904).  ntfli0 [n_members][N], or NULL for a fresh problem; applies to the following runs
+// until the members are set again.
+extern "C" int lwfb_set_ntfli0(lwfb_handle* h, const double* ntfli0) {
+  if (!h || h->M < 1) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  const size_t bytes = (size_t)h->M * h->o.n_layers * sizeof(double);
+  if (!ntfli0) { cudaFree(h->d_ntfli0); h->d_ntfli0 = nullptr; return LWFB_OK; }
+  if (!h->d_ntfli0) CK(cudaMalloc(&h->d_ntfli0, bytes));
+  CK(cudaMemcpy(h->d_ntfli0, ntfli0, bytes, cudaMemcpyHostToDevice));
+  return LWFB_OK;
+}
+
+// du_NTFLI as the last run left it: out [n_members][N]
+extern "C" int lwfb_get_ntfli(lwfb_handle* h, double* out) {
+  if (!h || !out || !h->ran) return LWFB_ERR_ARG;
+  CK(cudaSetDevice(h->o.device));
+  { int rc = ensure_done(h); if (rc) return rc; }
+  CK(cudaMemcpy(out, h->d_ntfli_out, (size_t)h->M * h->o.n_layers * sizeof(double), cudaMemcpyDeviceToHost));
+  return LWFB_OK;
+}
+
 extern "C" int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, const double* gwat, const double* frozen,
                              const double* ntfli_prev, double* du) {
   if (!h || h->M < 1 || !swati || !gwat || !frozen || !ntfli_prev || !du) return LWFB_ERR_ARG;
@@ -928,7 +965,29 @@ extern "C" int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, cons
   CK(cudaMemcpy(d_fr, frozen, n_fr * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_nt, ntfli_prev, n_sw * sizeof(double), cudaMemcpyHostToDevice));
   DevData d = make_dev(h);
-  launch_member_rhs(d, t, d_sw, d_gw, d_fr, d_nt, d_du);
+  if (use_lanes(h)) {
+    // the production kernel evaluates f once through its own stage-0 code (DevData::probe_*): state = u0 with SWATI and
+    // GWAT replaced by the arguments
+    const int L = h->L;
+    const SIdx ix(N, h->o.simulate_isotopes);
+    double* d_u0p = nullptr;
+    CK(cudaMalloc(&d_u0p, (size_t)M * L * sizeof(double)));
+    cudaError_t e = cudaMemcpy(d_u0p, h->d_u0, (size_t)M * L * sizeof(double), cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy2D(d_u0p + ix.SWATI, (size_t)L * sizeof(double), swati, (size_t)N * sizeof(double), (size_t)N * sizeof(double), (size_t)M, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy2D(d_u0p + ix.GWAT, (size_t)L * sizeof(double), gwat, sizeof(double), sizeof(double), (size_t)M, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d_u0p); h->err = std::string("lwfb_eval_rhs: ") + cudaGetErrorString(e); return LWFB_ERR_CUDA; }
+    d.u0 = d_u0p; d.rec = nullptr; d.perm = nullptr; d.n_obs_layers = 0; d.ntfli0 = nullptr; d.ntfli_out = nullptr;
+    d.iter_budget = 1;
+    d.probe_frozen = d_fr; d.probe_ntfli = d_nt; d.probe_t = t; d.probe_out = d_du;
+    int rc2 = launch_integrator(h, d, 0);
+    e = cudaDeviceSynchronize();
+    cudaFree(d_u0p);
+    h->ran = false; h->sums_valid = false; h->cost_valid = false;      // (fin / status / counters were used as scratch)
+    if (rc2) return rc2;
+    if (e != cudaSuccess) { h->err = std::string("lwfb_eval_rhs: ") + cudaGetErrorString(e); return LWFB_ERR_CUDA; }
+  } else {
+    launch_member_rhs(d, t, d_sw, d_gw, d_fr, d_nt, d_du);
+  }
   CK(cudaGetLastError());
   CK(cudaMemcpy(du, d_du, n_du * sizeof(double), cudaMemcpyDeviceToHost));
   return LWFB_OK;

@@ -109,6 +109,15 @@ struct DevData {
   const double* __restrict__ obs_theta;     // [n_obs_days][n_obs_layers] (null: not scored), NaN = missing
   const double* __restrict__ obs_d18o;      // likewise
   double* __restrict__ sacc;                // [M][2][LWFB_SA] running sums, theta then delta18O
+  // du_NTFLI cache of the reference's `p` across runs: the net layer flows that the first ITER of a run
+  // sees (null: NaN, a fresh problem) and the ones the run leaves behind
+  const double* __restrict__ ntfli0;        // [M][N] or null
+  double* __restrict__ ntfli_out;           // [M][N] or null
+  // unit-test probe of the lane kernel (lwfb_eval_rhs): one evaluation of f(u, t) with the given frozen fluxes
+  const double* __restrict__ probe_frozen;  // [M][N+3] = RNET, SMLT, SLVP, TRANI[N]   (null: normal run)
+  const double* __restrict__ probe_ntfli;   // [M][N]
+  double probe_t;
+  double* __restrict__ probe_out;           // [M][N+9]
 };
 // running sums of one scored variable, in the order they are accumulated: days outer, observed layers inner
 enum { LWFB_SA_N = 0, LWFB_SA_SE, LWFB_SA_SO, LWFB_SA_SS, LWFB_SA_SOO, LWFB_SA_SSS, LWFB_SA_SOS, LWFB_SA };

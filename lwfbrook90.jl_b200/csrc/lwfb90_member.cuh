@@ -41,6 +41,7 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
   Member<NT> mb;
   mb.load(d, m);
   const int N = mb.N, NE = N + 9, L = d.L;
+  if (d.ntfli0) for (int i = 0; i < N; i++) mb.NTFLI[i] = __ldg(d.ntfli0 + m * N + i);   // warm du_NTFLI cache
   const bool iso = d.iso != 0;
   const SIdx ix(N, d.iso);
   const double* __restrict__ forc = d.forc + (int64_t)__ldg(d.site + m) * d.n_rows * LWFB_F;
@@ -254,6 +255,7 @@ __device__ void integrate_member(const DevData& d, const int64_t m) {
       for (int j = 0; j < L; j++) rec_m[(int64_t)rec * L + j] = NAN;
   }
   write_record(d.fin + m * L);
+  if (d.ntfli_out) for (int i = 0; i < N; i++) d.ntfli_out[m * N + i] = mb.NTFLI[i];
   d.status[m] = status;
   d.counters[m * LWFB_NCOUNTERS + LWFB_C_NACCEPT] = naccept;
   d.counters[m * LWFB_NCOUNTERS + LWFB_C_NREJECT] = nreject;

@@ -68,6 +68,45 @@ def set_observations(n_days, obs_day=None, obs_layer=None, obs_theta=None, obs_d
                         None if d18 is None else _p(d18))
 
 
+def set_ntfli0(ntfli0=None):
+    """du_NTFLI cache seen by the first ITER of the following runs ([M, N]); None: fresh problem."""
+    L = lib()
+    L.lwfb_emul_set_ntfli0.argtypes = [_dp, C.c_int64]; L.lwfb_emul_set_ntfli0.restype = None
+    if ntfli0 is None:
+        L.lwfb_emul_set_ntfli0(None, 0)
+    else:
+        a = np.ascontiguousarray(ntfli0, dtype=np.float64)
+        L.lwfb_emul_set_ntfli0(_p(a), a.size)
+
+
+def get_ntfli(M, N):
+    L = lib()
+    L.lwfb_emul_get_ntfli.argtypes = [_dp, C.c_int64]; L.lwfb_emul_get_ntfli.restype = None
+    out = np.zeros((M, N))
+    L.lwfb_emul_get_ntfli(_p(out), out.size)
+    return out
+
+
+def eval_rhs(N, iso, forcing, site_of_member, scal, lay, u0, t, swati, gwat, frozen, ntfli_prev, warps_per_block=1):
+    """One evaluation of f(u, t) by the LANE kernel's own stage code (the probe behind lwfb_eval_rhs for 3 <= N <= 32):
+    du [M, N+9]."""
+    L = lib()
+    L.lwfb_emul_set_probe.argtypes = [_dp, _dp, C.c_double, _dp]; L.lwfb_emul_set_probe.restype = None
+    u0p = np.ascontiguousarray(u0, dtype=np.float64).copy()
+    M = u0p.shape[0]
+    k = 3 if iso else 1
+    u0p[:, :N] = swati
+    u0p[:, k * N] = gwat
+    fr = np.ascontiguousarray(frozen, dtype=np.float64); nt = np.ascontiguousarray(ntfli_prev, dtype=np.float64)
+    du = np.full((M, N + 9), np.nan)
+    L.lwfb_emul_set_probe(_p(fr), _p(nt), float(t), _p(du))
+    try:
+        run(LANES, N, iso, 0, 1, forcing, site_of_member, scal, lay, u0p, seg_len=1, warps_per_block=warps_per_block)
+    finally:
+        L.lwfb_emul_set_probe(None, None, 0.0, None)
+    return du
+
+
 def score_sums(M):
     """[M][2][7] running sums (n, se, so, ss, soo, sss, sos for theta and delta18O) of the last run."""
     L = lib()

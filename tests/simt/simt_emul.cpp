@@ -320,6 +320,17 @@ extern "C" void lwfb_emul_set_obs(int n_days, int n_obs_days, const int32_t* obs
   if (n_obs_days > 0 && obs_d18o) g_obs_d18o.assign(obs_d18o, obs_d18o + n);
   if (n_obs_days == 0) g_obs_layer.clear();
 }
+// du_NTFLI cache handed to the following runs / left by the last run (the emulator's lwfb_set_ntfli0 / lwfb_get_ntfli)
+static std::vector<double> g_ntfli0, g_ntfli_out;
+extern "C" void lwfb_emul_set_ntfli0(const double* p, int64_t n) { if (p && n > 0) g_ntfli0.assign(p, p + n); else g_ntfli0.clear(); }
+extern "C" void lwfb_emul_get_ntfli(double* out, int64_t n) { for (int64_t k = 0; k < n && k < (int64_t)g_ntfli_out.size(); k++) out[k] = g_ntfli_out[(size_t)k]; }
+// lane-kernel RHS probe of the next lwfb_emul_run (the emulator's lwfb_eval_rhs for 3 <= N <= 32): one launch, one pass
+static const double *g_probe_frozen = nullptr, *g_probe_ntfli = nullptr;
+static double g_probe_t = 0;
+static double* g_probe_out = nullptr;
+extern "C" void lwfb_emul_set_probe(const double* frozen, const double* ntfli, double t, double* out) {
+  g_probe_frozen = frozen; g_probe_ntfli = ntfli; g_probe_t = t; g_probe_out = out;
+}
 extern "C" void lwfb_emul_get_sums(double* out, int64_t n) { for (int64_t k = 0; k < n && k < (int64_t)g_sacc.size(); k++) out[k] = g_sacc[(size_t)k]; }
 
 extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days, int n_sites, int n_rows,
@@ -348,6 +359,10 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   d.obs_theta = g_obs_theta.empty() ? nullptr : g_obs_theta.data();
   d.obs_d18o = g_obs_d18o.empty() ? nullptr : g_obs_d18o.data();
   d.sacc = g_sacc.data();
+  g_ntfli_out.assign((size_t)M * N, 0.0);
+  d.ntfli0 = (g_ntfli0.size() == (size_t)M * N) ? g_ntfli0.data() : nullptr;
+  d.ntfli_out = g_ntfli_out.data();
+  d.probe_frozen = g_probe_frozen; d.probe_ntfli = g_probe_ntfli; d.probe_t = g_probe_t; d.probe_out = g_probe_out;
   {   // the library's classification (optional_paths_kernel); LWFB_EMUL_GENERAL=1 keeps the general instantiation
     bool used = false;
     for (int64_t m = 0; m < M; m++) {
@@ -389,7 +404,7 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
     std::vector<pthread_t> th(n_threads);
     for (int i = 0; i < n_threads; i++) pthread_create(&th[i], nullptr, worker, &job);
     for (int i = 0; i < n_threads; i++) pthread_join(th[i], nullptr);
-    if (!quanta) break;
+    if (!quanta || d.probe_out) break;
     int64_t left = 0;
     for (int64_t i = 0; i < M; i++)
       if (status[i] == LWFB_ST_OK && ck[(size_t)i * ck_rows + lwfb::LWFB_CK_T] < tend) perm2[(size_t)left++] = (int32_t)i;

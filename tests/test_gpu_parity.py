@@ -630,3 +630,131 @@ def test_setup_members_on_device(which, request):
     h.set_members(np.zeros(len(sub), np.int32), want[0][sub], want[1][sub], want[2][sub]); h.run()
     assert np.array_equal(fin_a, h.get_final(), equal_nan=True) and np.array_equal(cnt_a, h.get_status()[1])
     h.close()
+
+
+# ------------------------------------------------------------------------------ the reference's goldens, straight from the GPU
+def _gpu_single(sim, n_days=None, ntfli0=None, legacy=False):
+    nd = int(sim.tspan[1] - sim.tspan[0]) if n_days is None else n_days
+    h = capi.Handle(sim.N, sim.iso, int(sim.tspan[0]), nd)
+    if legacy:
+        h.force_legacy(True)
+    h.set_sites(sim.forcing); h.set_members([0], sim.scal, sim.lay, sim.u0)
+    if ntfli0 is not None:
+        h.set_ntfli0(ntfli0)
+    h.run()
+    rec = h.get_daily()[0]
+    st, cnt = h.get_status()
+    nt = h.get_ntfli()
+    h.close()
+    assert st[0] == 0
+    return rec, cnt[0], nt
+
+
+@pytest.mark.parametrize("modified", [False, True])
+def test_G2_G3_infexp1_golden_through_the_gpu(lw, infexp1, modified):
+    """Goldens G2 / G3 (examples/INFEXP1*_fluxes_referencedf.csv, run definition test/03-regression-tests.jl:352-367)
+    compared DIRECTLY with the GPU record (N = 42: thread-per-member kernel), with the bounds the oracle is held to."""
+    from test_oracle_golden import _flux_cmp
+    sim = infexp1
+    if modified:
+        sim = lw.remakeSPAC(sim, params=dict(BYPAR=1, QDEPTH_m=0.40, QFFC=0.2, QFPAR=0.3, GSC=0.05, GSP=0.2))
+    assert sim.N == 42
+    rec, _, _ = _gpu_single(sim)
+    name = "INFEXP1-modified_fluxes_referencedf.csv" if modified else "INFEXP1_fluxes_referencedf.csv"
+    hdr, mine, ref = _flux_cmp(rec, lo.StateIndex(42, False), outputs(name))
+    assert np.max(np.abs(mine[:232] - ref[:232])) < 1e-7          # well conditioned until the profile saturates (day 231)
+    for c in ("StorageSWAT", "StorageWATER"):
+        j = hdr.index(c)
+        assert np.max(np.abs(mine[:, j] - ref[:, j]) / ref[:, j]) < 2e-3
+    for c in ("cum_d_prec", "cum_d_rfal", "cum_d_sfal", "cum_d_rint", "cum_d_pint", "cum_d_irvp"):
+        j = hdr.index(c)
+        assert np.allclose(mine[:, j], ref[:, j], rtol=1e-4, atol=1e-4)
+
+
+def test_G4_dav2020_modified_golden_through_the_gpu(lw):
+    """Golden G4 (examples/DAV2020-full-modified_fluxes_referencedf.csv, test/03-regression-tests.jl:411-458; N = 40,
+    every optional flow path switched on) against the GPU record at the reference's own tolerance, all 30 series."""
+    from test_oracle_golden import _dav_modified, _flux_cmp
+    sim = _dav_modified(lw)
+    assert sim.N == 40
+    rec, _, _ = _gpu_single(sim)
+    _, mine, ref = _flux_cmp(rec, lo.StateIndex(40, True), outputs("DAV2020-full-modified_fluxes_referencedf.csv"))
+    assert np.all(np.abs(mine - ref) <= 1e-4 + 1e-4 * np.abs(ref))
+    assert np.max(np.abs(mine - ref)) < 1e-5
+
+
+def test_G5_second_simulate_on_the_gpu(lw):
+    """Golden G5 (inline tables of test/01-unit-tests.jl:907-1014) comes from the SECOND simulate! on one problem: the
+    first ITER sees the du_NTFLI the first run left in `p`.  lwfb_get_ntfli / lwfb_set_ntfli0 reproduce
+    that on the GPU (N = 22: the lane kernel's general instantiation); isotope table and water partitioning against the
+    golden, and the warm run bit for bit against the oracle's."""
+    import datetime as dt
+    import json
+    import os
+    from test_oracle_golden import GOLD, _g5_model
+    sim = _g5_model(lw)
+    cold, _, nt = _gpu_single(sim)
+    warm, cnt, _ = _gpu_single(sim, ntfli0=nt)
+    orc.use("elem")
+    o_cold = orc.run_member(sim.N, sim.iso, 0, 365, sim.forcing, sim.scal, sim.lay, sim.u0)
+    o_warm = orc.run_member(sim.N, sim.iso, 0, 365, sim.forcing, sim.scal, sim.lay, sim.u0, ntfli_init=o_cold[3])
+    assert np.array_equal(nt[0], o_cold[3]) and np.array_equal(warm, o_warm[0], equal_nan=True) and np.array_equal(cnt, o_warm[2])
+    gold = json.load(open(os.path.join(GOLD, "golden_inline.json")))
+    sim.solution = api.ODESolution(sim, np.arange(366.0), warm, 0, cnt)
+    sim.ODESolution_datetime = [sim.parametrizedSPAC.reference_date + dt.timedelta(days=k) for k in range(366)]
+    ref = np.array(gold["reference_isotopePlotPermutedDims"])
+    sol, ix = sim.solution, sim.solution.ix
+    days = [0, 9, 99, 299]
+    rec = np.array([sol.record_at(d) for d in days])
+    for j, n in enumerate(["INTS", "INTR", "SNOW", "GWAT", "RWU", "XYLEM"]):
+        assert np.allclose(rec[:, getattr(ix, n + "_d18O")], ref[6 + j], rtol=0, atol=1e-6)
+        assert np.allclose(rec[:, getattr(ix, n + "_d2H")], ref[12 + j], rtol=0, atol=1e-5)
+    assert np.max(np.abs(rec[:, ix.SWATI_d18O].T - ref[19:41])) < 1e-6
+    assert np.max(np.abs(rec[:, ix.SWATI_d2H].T - ref[41:63])) < 1e-5
+    daily, monthly, yearly = api.get_water_partitioning(sim)
+    cols = ["ETa", "Esoil", "Esnow", "Einterception", "Ta", "Precip", "Td", "D", "R", "Swat"]
+    for tab, key, rows in ((daily, "reference_daily_check", [9, 19, 99, 179, 249, 259]), (monthly, "reference_monthly_check", None),
+                           (yearly, "reference_yearly_check", None)):
+        rows = range(len(tab["year"])) if rows is None else rows
+        mine, want = np.array([[tab[c][r] for c in cols] for r in rows]), np.array(gold[key])
+        assert np.linalg.norm(mine - want) <= max(1e-5, 1e-5 * max(np.linalg.norm(mine), np.linalg.norm(want)))
+
+
+def test_rhs_by_both_kernels(dav_full):
+    """lwfb_eval_rhs runs the kernel that would integrate the members: the lane kernel (lean and general
+    instantiation) and, forced, the thread-per-member kernel give the same bits as the oracle."""
+    ens = en.make_ensemble(dav_full, 40)
+    N, M = ens.N, ens.M
+    rng = np.random.default_rng(9)
+    ix = lo.StateIndex(N, ens.iso)
+    swati = ens.u0[:, ix.SWATI_mm] * rng.uniform(0.5, 1.3, (M, N))
+    gwat = rng.uniform(0, 5, M)
+    frozen = np.concatenate([rng.uniform(0, 30, (M, 1)), rng.uniform(0, 2, (M, 1)), rng.uniform(0, 1, (M, 1)),
+                             rng.uniform(-0.01, 0.5, (M, N))], axis=1)
+    ntfli = rng.normal(0, 20, (M, N)); ntfli[::9] = np.nan
+    orc.use("elem")
+    want = np.stack([orc.eval_rhs(N, ens.scal[m], ens.lay[m], 3.25, swati[m], gwat[m], frozen[m], ntfli[m])[0] for m in range(M)])
+    h = capi.Handle(N, ens.iso, 0, 1)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    for mode in (0, 2, 1):                      # lean lane kernel, general lane kernel, thread-per-member kernel
+        h.force_legacy(mode)
+        assert np.array_equal(h.eval_rhs(3.25, swati, gwat, frozen, ntfli), want, equal_nan=True), mode
+    h.close()
+
+
+def test_simulate_keyword_arguments(dav_full):
+    """simulate_ forwards the solver keywords it supports and refuses what it cannot honour."""
+    import copy
+    sim = copy.copy(dav_full)
+    with pytest.raises(NotImplementedError, match="save_everystep"):
+        api.simulate_(sim, save_everystep=True)
+    with pytest.raises(NotImplementedError, match="day boundaries"):
+        api.simulate_(sim, saveat=[0.0, 1.5])
+    with pytest.raises(TypeError, match="unsupported"):
+        api.simulate_(sim, alg="Rodas5")
+    api.simulate_(sim, tspan=(0, 20), saveat=[0, 10, 20])
+    base = sim.solution.records.copy()
+    assert list(sim.solution.t) == [0.0, 10.0, 20.0]
+    api.simulate_(sim, tspan=(0, 20), saveat=[0, 10, 20], reltol=1e-7)
+    assert sim.solution.destats.naccept > 0 and not np.array_equal(sim.solution.records, base)
+    assert np.allclose(sim.solution.records[:, :5], base[:, :5], rtol=1e-4)

@@ -173,8 +173,8 @@ def test_G4_dav2020_modified_fluxes(lw):
 
 
 # ---------------------------------------------------------------- G5: inline tables of the unit tests
-@pytest.fixture(scope="module")
-def g5(lw):
+def _g5_model(lw):
+    """Run definition of the unit tests' inline tables, test/01-unit-tests.jl:858-875."""
     m5 = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=[0.05] * 22,
                      root_distribution=dict(beta=0.77, z_rootMax_m=-0.5),
                      IC_soil=dict(PSIM_init_kPa=-7.0, delta18O_init_permil=-10.11111, delta2H_init_permil=-91.1111),
@@ -183,6 +183,12 @@ def g5(lw):
                                                         LAI_perc_BtoC=95, LAI_perc_CtoB=70)))
     sim = lw.setup(m5)
     assert sim.N == 22 and sim.tspan == (0.0, 365.0)
+    return sim
+
+
+@pytest.fixture(scope="module")
+def g5(lw):
+    sim = _g5_model(lw)
     cold, cnt, nt = run(sim)
     # the golden comes from the SECOND simulate! on the same problem: warm du_NTFLI cache
     warm, cnt2, _ = run(sim, ntfli_init=nt)

@@ -246,3 +246,53 @@ def test_score_sums_accumulated_by_the_integrator(dav_full, seg_len):
     finally:
         emul.set_observations(nd)
     assert np.array_equal(rec2, rec, equal_nan=True) and np.array_equal(got2, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("which", ["dav_full", "bea"])
+def test_lane_kernel_rhs_probe(which, request):
+    """Unit test of the LANE kernel's right-hand side (the probe behind lwfb_eval_rhs): one evaluation of f(u, t) by
+    the production kernel's own stage code against the oracle, for perturbed, clamped and saturated states and a NaN
+    du_NTFLI cache."""
+    sim = request.getfixturevalue(which)
+    ens = en.make_ensemble(sim, 14)
+    N, M = ens.N, ens.M
+    rng = np.random.default_rng(5)
+    ix = lo.StateIndex(N, ens.iso)
+    smax = ens.lay[:, lo.L.SWATMAX]
+    swati = ens.u0[:, ix.SWATI_mm] * rng.uniform(0.5, 1.3, (M, N))
+    swati[::7] = smax[::7] * 1.01
+    swati[3::11, 0] = -0.1
+    gwat = rng.uniform(0, 5, M); gwat[::5] = 0.0
+    frozen = np.concatenate([rng.uniform(0, 30, (M, 1)), rng.uniform(0, 2, (M, 1)), rng.uniform(0, 1, (M, 1)),
+                             rng.uniform(-0.01, 0.5, (M, N))], axis=1)
+    ntfli = rng.normal(0, 20, (M, N)); ntfli[::9] = np.nan
+    orc.use("elem")
+    for t in (0.0, 0.3712, 10.999999):
+        du = emul.eval_rhs(N, ens.iso, ens.forcing, ens.site_of_member, ens.scal, ens.lay, ens.u0, t, swati, gwat, frozen, ntfli,
+                           warps_per_block=2)
+        for m in range(M):
+            ref, _ = orc.eval_rhs(N, ens.scal[m], ens.lay[m], t, swati[m], gwat[m], frozen[m], ntfli[m])
+            assert np.array_equal(du[m], ref, equal_nan=True), (t, m, du[m], ref)
+
+
+def test_warm_ntfli_cache_second_run(dav_full):
+    """a second simulate! on the same problem starts from the du_NTFLI the first run left behind.  The
+    lane kernel with lwfb_set_ntfli0 reproduces the oracle's warm-cache run bit for bit.  (Whether the records differ from
+    a cold run depends on whether ITER's limit binds in the first step; the RHS probe test covers the NaN / finite cases.)"""
+    ens = en.make_ensemble(dav_full, 6)
+    nd = 5
+    orc.use("elem")
+    cold = [orc.run_member(ens.N, ens.iso, 0, nd, ens.forcing[0], ens.scal[m], ens.lay[m], ens.u0[m]) for m in range(ens.M)]
+    warm = [orc.run_member(ens.N, ens.iso, 0, nd, ens.forcing[0], ens.scal[m], ens.lay[m], ens.u0[m], ntfli_init=cold[m][3])
+            for m in range(ens.M)]
+    rec1, st1, cnt1 = emul.run(emul.LANES, ens.N, ens.iso, 0, nd, ens.forcing, ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    nt1 = emul.get_ntfli(ens.M, ens.N)
+    assert np.array_equal(nt1, np.stack([c[3] for c in cold]))
+    emul.set_ntfli0(nt1)
+    try:
+        rec2, st2, cnt2 = emul.run(emul.LANES, ens.N, ens.iso, 0, nd, ens.forcing, ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    finally:
+        emul.set_ntfli0(None)
+    assert np.array_equal(rec2, np.stack([w[0] for w in warm]), equal_nan=True)
+    assert np.array_equal(cnt2, np.stack([w[2] for w in warm]))
+    assert np.array_equal(emul.get_ntfli(ens.M, ens.N), np.stack([w[3] for w in warm]))
