@@ -331,6 +331,42 @@ int lwfb_set_placement(lwfb_handle* h, int32_t mode);
 /* kernel launch statistics of the last lwfb_run: number of kernel launches, device ms */
 int lwfb_last_run_stats(lwfb_handle* h, int32_t* n_launches, float* device_ms);
 
+/* ---------------------------------------------------------------- several GPUs of one host behind one handle
+ * (SURVEY 8e, 8b "multi-GPU inside one call"; no reference analogue: the reference is single-threaded per problem).
+ * lwfb_multi owns one lwfb_handle per shard, deals the members to the shards, runs them concurrently (one host thread
+ * per shard, no collective during the integration) and all-gathers the per-member scores with peer-to-peer copies over
+ * NVLink, so that every device holds the scores of the whole ensemble.  No NCCL, no torch: callable from Julia with
+ * plain ccall.  devices [n_shards]: CUDA ordinals; one ordinal may appear more than once (several shards on one GPU).
+ * All per-member arrays are in the CALLER'S member order on both sides of every call. */
+typedef struct lwfb_multi lwfb_multi;
+int lwfb_multi_create(lwfb_multi** mh, const lwfb_opts* opts, int32_t n_shards, const int32_t* devices);
+void lwfb_multi_destroy(lwfb_multi* mh);
+const char* lwfb_multi_last_error(const lwfb_multi* mh);
+int32_t lwfb_multi_n_shards(const lwfb_multi* mh);
+lwfb_handle* lwfb_multi_shard(lwfb_multi* mh, int32_t shard);        /* the per-device handle (getters, records) */
+int lwfb_multi_set_sites(lwfb_multi* mh, int32_t n_sites, int32_t n_rows, const double* forcing);
+/* cost [n_members] or NULL.  NULL: contiguous blocks of members per shard.  Otherwise (e.g. the RHS-evaluation counts of
+ * a short probe run, lwfb_multi_get_status): members sorted by cost and dealt to the shards in a snake, so that every
+ * shard gets the same number of members and the same share of the expensive ones. */
+int lwfb_multi_set_members(lwfb_multi* mh, int64_t n_members, const int32_t* site_of_member, const double* scal,
+                           const double* lay, const double* u0, const double* cost);
+int lwfb_multi_setup_members(lwfb_multi* mh, int64_t n_members, const double* base_scal, const double* base_lay,
+                             const double* base_u0, const double* knobs, int32_t n_over, const int32_t* over_idx,
+                             int32_t n_profiles, const double* profiles, const double* psim_base, int32_t ilayer,
+                             const double* cost);
+int lwfb_multi_set_observations(lwfb_multi* mh, int32_t n_obs_days, const int32_t* obs_day, int32_t n_obs_layers,
+                                const int32_t* obs_layer, const double* obs_theta, const double* obs_d18o);
+int lwfb_multi_run(lwfb_multi* mh);
+/* arguments as lwfb_scores_device (n_obs_days = 0: the sums accumulated during the run); d_scores_of_shard [n_shards]
+ * (optional) receives, per shard, the device pointer of the [n_members][LWFB_NSCORES] block of the WHOLE ensemble;
+ * scores (optional) a host copy */
+int lwfb_multi_allgather_scores(lwfb_multi* mh, int32_t n_obs_days, const int32_t* obs_day, int32_t n_obs_layers,
+                                const int32_t* obs_layer, const double* obs_theta, const double* obs_d18o,
+                                double** d_scores_of_shard, double* scores);
+int lwfb_multi_get_status(lwfb_multi* mh, int32_t* status, int64_t* counters, int32_t* shard_of_member);
+int lwfb_multi_get_final(lwfb_multi* mh, double* out);
+int lwfb_multi_last_run_ms(lwfb_multi* mh, float* ms_of_shard, float* ms_max);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,7 +39,11 @@ SYMBOLS = ["lwfb_default_opts", "lwfb_create", "lwfb_destroy", "lwfb_last_error"
            "lwfb_get_status", "lwfb_scores", "lwfb_scores_device", "lwfb_eval_rhs", "lwfb_last_run_stats", "lwfb_elem_eval",
            "lwfb_fp64_peak", "lwfb_debug_get_block", "lwfb_debug_force_legacy", "lwfb_set_placement",
            "lwfb_water_partitioning", "lwfb_soil_state", "lwfb_set_observations", "lwfb_setup_members",
-           "lwfb_set_ntfli0", "lwfb_get_ntfli"]
+           "lwfb_set_ntfli0", "lwfb_get_ntfli",
+           "lwfb_multi_create", "lwfb_multi_destroy", "lwfb_multi_last_error", "lwfb_multi_n_shards", "lwfb_multi_shard",
+           "lwfb_multi_set_sites", "lwfb_multi_set_members", "lwfb_multi_setup_members", "lwfb_multi_set_observations",
+           "lwfb_multi_run", "lwfb_multi_allgather_scores", "lwfb_multi_get_status", "lwfb_multi_get_final",
+           "lwfb_multi_last_run_ms"]
 
 
 def lib():
@@ -70,6 +74,22 @@ def lib():
         L.lwfb_setup_members.restype = C.c_int
         L.lwfb_set_ntfli0.argtypes = [vp, _dp]; L.lwfb_set_ntfli0.restype = C.c_int
         L.lwfb_get_ntfli.argtypes = [vp, _dp]; L.lwfb_get_ntfli.restype = C.c_int
+        L.lwfb_multi_create.argtypes = [C.POINTER(vp), C.POINTER(LwfbOpts), C.c_int32, _ip]; L.lwfb_multi_create.restype = C.c_int
+        L.lwfb_multi_destroy.argtypes = [vp]; L.lwfb_multi_destroy.restype = None
+        L.lwfb_multi_last_error.argtypes = [vp]; L.lwfb_multi_last_error.restype = C.c_char_p
+        L.lwfb_multi_n_shards.argtypes = [vp]; L.lwfb_multi_n_shards.restype = C.c_int32
+        L.lwfb_multi_shard.argtypes = [vp, C.c_int32]; L.lwfb_multi_shard.restype = vp
+        L.lwfb_multi_set_sites.argtypes = [vp, C.c_int32, C.c_int32, _dp]; L.lwfb_multi_set_sites.restype = C.c_int
+        L.lwfb_multi_set_members.argtypes = [vp, C.c_int64, _ip, _dp, _dp, _dp, _dp]; L.lwfb_multi_set_members.restype = C.c_int
+        L.lwfb_multi_setup_members.argtypes = [vp, C.c_int64, _dp, _dp, _dp, _dp, C.c_int32, _ip, C.c_int32, _dp, _dp, C.c_int32, _dp]
+        L.lwfb_multi_setup_members.restype = C.c_int
+        L.lwfb_multi_set_observations.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp]; L.lwfb_multi_set_observations.restype = C.c_int
+        L.lwfb_multi_run.argtypes = [vp]; L.lwfb_multi_run.restype = C.c_int
+        L.lwfb_multi_allgather_scores.argtypes = [vp, C.c_int32, _ip, C.c_int32, _ip, _dp, _dp, C.POINTER(vp), _dp]
+        L.lwfb_multi_allgather_scores.restype = C.c_int
+        L.lwfb_multi_get_status.argtypes = [vp, _ip, _lp, _ip]; L.lwfb_multi_get_status.restype = C.c_int
+        L.lwfb_multi_get_final.argtypes = [vp, _dp]; L.lwfb_multi_get_final.restype = C.c_int
+        L.lwfb_multi_last_run_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]; L.lwfb_multi_last_run_ms.restype = C.c_int
         L.lwfb_eval_rhs.argtypes = [vp, C.c_double, _dp, _dp, _dp, _dp, _dp]; L.lwfb_eval_rhs.restype = C.c_int
         L.lwfb_last_run_stats.argtypes = [vp, _ip, C.POINTER(C.c_float)]; L.lwfb_last_run_stats.restype = C.c_int
         L.lwfb_elem_eval.argtypes = [C.c_int32, C.c_int32, C.c_int64, _dp, _dp, _dp]; L.lwfb_elem_eval.restype = C.c_int
@@ -323,3 +343,107 @@ class Handle:
         ms = C.c_float()
         self._ck(self._L.lwfb_last_run_stats(self._h, C.byref(n), C.byref(ms)))
         return int(n.value), float(ms.value)
+
+
+class MultiHandle:
+    """Several GPUs of one host behind one handle (lwfb_multi_* of include/lwfb90.h): shards the members over the listed
+    devices (a device may be listed more than once), runs the shards concurrently, all-gathers the scores peer to peer.
+    No torch, no NCCL."""
+
+    def __init__(self, N: int, iso: bool, t0_day: int, n_days: int, devices, *, record_daily: bool = False,
+                 reltol=1e-5, abstol=1e-6, dt_init=1e-3, dtmax=60 / 60 / 24, maxiters=1_000_000):
+        self._L = lib()
+        o = LwfbOpts()
+        self._L.lwfb_default_opts(C.byref(o))
+        o.n_layers, o.simulate_isotopes, o.t0_day, o.n_days = int(N), int(bool(iso)), int(t0_day), int(n_days)
+        o.reltol, o.abstol, o.dt_init, o.dtmax, o.maxiters = reltol, abstol, dt_init, dtmax, int(maxiters)
+        o.record_daily = int(bool(record_daily))
+        self.N, self.iso, self.n_days = int(N), bool(iso), int(n_days)
+        self.L = lo.state_len(self.N, self.iso)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        self.n_shards = len(dev)
+        self.M = 0
+        self._h = C.c_void_p()
+        rc = self._L.lwfb_multi_create(C.byref(self._h), C.byref(o), len(dev), _p(dev, _ip))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise LwfbError(f"lwfb_multi_create failed with code {rc}")
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._L.lwfb_multi_last_error(self._h)
+            raise LwfbError(f"liblwfb90 (multi) error {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.lwfb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_sites(self, forcing):
+        f = _f64(forcing)
+        if f.ndim == 2:
+            f = f[None]
+        self._ck(self._L.lwfb_multi_set_sites(self._h, f.shape[0], f.shape[1], _p(f)))
+
+    def set_members(self, site_of_member, scal, lay, u0, cost=None):
+        scal, lay, u0 = _f64(scal), _f64(lay), _f64(u0)
+        M = scal.shape[0]
+        som = np.ascontiguousarray(site_of_member, dtype=np.int32).reshape(M)
+        c = None if cost is None else _f64(cost).reshape(M)
+        self._ck(self._L.lwfb_multi_set_members(self._h, M, _p(som, _ip), _p(scal), _p(lay), _p(u0), None if c is None else _p(c)))
+        self.M = M
+
+    def setup_members(self, kb, cost=None):
+        knobs = _f64(kb.knobs)
+        M = knobs.shape[0]
+        oi = np.ascontiguousarray(kb.over_idx, dtype=np.int32)
+        pr = _f64(kb.profiles).reshape(-1, 2 * self.N + 1)
+        c = None if cost is None else _f64(cost).reshape(M)
+        self._ck(self._L.lwfb_multi_setup_members(self._h, M, _p(_f64(kb.base_scal)), _p(_f64(kb.base_lay)), _p(_f64(kb.base_u0)),
+                                                  _p(knobs), len(oi), _p(oi, _ip) if len(oi) else None, pr.shape[0],
+                                                  _p(pr) if pr.size else None, _p(_f64(kb.psim_base)), int(kb.ilayer),
+                                                  None if c is None else _p(c)))
+        self.M = M
+
+    def set_observations(self, obs_day, obs_layer, obs_theta=None, obs_d18o=None):
+        od = np.ascontiguousarray(obs_day, dtype=np.int32)
+        ol = np.ascontiguousarray(obs_layer, dtype=np.int32)
+        th = None if obs_theta is None else _f64(obs_theta).reshape(len(od), len(ol))
+        d18 = None if obs_d18o is None else _f64(obs_d18o).reshape(len(od), len(ol))
+        self._ck(self._L.lwfb_multi_set_observations(self._h, len(od), _p(od, _ip), len(ol), _p(ol, _ip),
+                                                     None if th is None else _p(th), None if d18 is None else _p(d18)))
+
+    def run(self):
+        self._ck(self._L.lwfb_multi_run(self._h))
+
+    def allgather_scores(self):
+        """Scores of the whole ensemble (from the sums of the run), gathered on every device; returns the host copy and
+        the per-shard device pointers."""
+        out = np.empty((self.M, lo.NSCORES))
+        ptrs = (C.c_void_p * self.n_shards)()
+        self._ck(self._L.lwfb_multi_allgather_scores(self._h, 0, None, 0, None, None, None, ptrs, _p(out)))
+        return out, [int(p) for p in ptrs]
+
+    def get_status(self):
+        st = np.empty(self.M, dtype=np.int32)
+        cnt = np.empty((self.M, lo.NCOUNTERS), dtype=np.int64)
+        sh = np.empty(self.M, dtype=np.int32)
+        self._ck(self._L.lwfb_multi_get_status(self._h, _p(st, _ip), _p(cnt, _lp), _p(sh, _ip)))
+        return st, cnt, sh
+
+    def get_final(self):
+        out = np.empty((self.M, self.L))
+        self._ck(self._L.lwfb_multi_get_final(self._h, _p(out)))
+        return out
+
+    def last_run_ms(self):
+        ms = (C.c_float * self.n_shards)()
+        mx = C.c_float()
+        self._ck(self._L.lwfb_multi_last_run_ms(self._h, ms, C.byref(mx)))
+        return [float(x) for x in ms], float(mx.value)

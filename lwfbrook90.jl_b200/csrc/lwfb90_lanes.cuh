@@ -358,7 +358,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 #endif
 
   double* const rec_m = d.rec ? d.rec + m * (int64_t)(d.n_days + 1) * L : nullptr;   // the member's records [n_days+1][L]
-  if (d.rec && live && !resume) for (int j = i; j < L; j += N) rec_m[j] = U0(j);     // record 0 = raw u0
+  if (d.rec && live && !resume) for (int j = i; j < L; j += N) __stcs(rec_m + j, U0(j));     // record 0 = raw u0
   __syncwarp(LFULL);
   if (!resume) score_rec(0, true, U0(ix.SWATI + i), iso ? U0(ix.SWATI + N + i) : 0.0);
   { const int d0 = (int)floor(t); stage_row(d0); stage_row(d0 + 1); staged_wait(); }
@@ -858,7 +858,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         if (d.rec && live) {
           // 8 L contiguous bytes per member-day; the lanes of the group write neighbouring words, L2 merges the sectors
           double* __restrict__ dst = rec_m + (int64_t)rec * L;
-          for (int j = i; j < L; j += N) dst[j] = FIN(j);
+          // streaming stores (evict-first): the record is written once and must not push the blocks' local memory and
+          // the members' live state out of L2
+          for (int j = i; j < L; j += N) __stcs(dst + j, FIN(j));
         }
         SETM(KM_REC, (double)(rec + 1));
         if (t < tend) {
@@ -981,7 +983,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       // the member ended in this launch before the end of the record: the records it did not reach are NaN
       for (; rec <= d.n_days; rec++) {
         double* dst = rec_m + (int64_t)rec * L;
-        for (int j = i; j < L; j += N) dst[j] = NAN;
+        for (int j = i; j < L; j += N) __stcs(dst + j, NAN);
       }
     }
     flush_state();

@@ -34,6 +34,7 @@ int warps_per_block();                                      // warps the emulato
 }  // namespace simt
 
 template <typename T> static inline T __ldg(const T* p) { return *p; }
+template <typename T> static inline void __stcs(T* p, T v) { *p = v; }
 static inline double __longlong_as_double(long long i) { double x; memcpy(&x, &i, 8); return x; }
 static inline long long __double_as_longlong(double x) { long long i; memcpy(&i, &x, 8); return i; }
 static inline uint32_t __float_as_uint(float x) { uint32_t i; memcpy(&i, &x, 4); return i; }

@@ -758,3 +758,47 @@ def test_simulate_keyword_arguments(dav_full):
     api.simulate_(sim, tspan=(0, 20), saveat=[0, 10, 20], reltol=1e-7)
     assert sim.solution.destats.naccept > 0 and not np.array_equal(sim.solution.records, base)
     assert np.allclose(sim.solution.records[:, :5], base[:, :5], rtol=1e-4)
+
+
+@pytest.mark.parametrize("balanced", [False, True])
+def test_multi_handle_shards_and_allgathers(dav_full, balanced):
+    """lwfb_multi_* (several GPUs of one host behind the C ABI, no torch / NCCL): shards dealt contiguously or balanced
+    by a cost estimate, run concurrently, scores all-gathered peer to peer - everything in the caller's member order and
+    bit-identical to one handle.  Uses every visible GPU, and at least two shards (two on one device if need be)."""
+    import torch
+    n_dev = torch.cuda.device_count()
+    devices = list(range(n_dev)) if n_dev >= 2 else [0, 0]
+    ens = en.make_ensemble(dav_full, 301)
+    nd = 25
+    obs_day = np.array([3, 10, 24], dtype=np.int32); obs_layer = np.array([0, 2], dtype=np.int32)
+    th = np.full((3, 2), 0.21); d18 = np.full((3, 2), -11.0)
+    h = capi.Handle(ens.N, ens.iso, 0, nd, record_daily=False)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    h.set_observations(obs_day, obs_layer, th, d18)
+    h.run()
+    want_sc, want_fin = h.scores(), h.get_final()
+    want_st, want_cnt = h.get_status()
+    h.close()
+    mh = capi.MultiHandle(ens.N, ens.iso, 0, nd, devices)
+    mh.set_sites(ens.forcing)
+    cost = want_cnt[:, 2].astype(float) if balanced else None
+    mh.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0, cost=cost)
+    mh.set_observations(obs_day, obs_layer, th, d18)
+    mh.run()
+    sc, ptrs = mh.allgather_scores()
+    st, cnt, shard = mh.get_status()
+    assert np.array_equal(sc, want_sc, equal_nan=True) and np.array_equal(st, want_st) and np.array_equal(cnt, want_cnt)
+    assert np.array_equal(mh.get_final(), want_fin, equal_nan=True)
+    sizes = np.bincount(shard, minlength=len(devices))
+    assert sizes.max() - sizes.min() <= 1 and len(set(ptrs)) == len(devices)
+    if balanced:      # every shard carries the same share of the cost (snake deal of the sorted members)
+        load = np.array([cost[shard == s].sum() for s in range(len(devices))])
+        assert load.max() / load.min() < 1.02
+    else:
+        assert (np.diff(shard) >= 0).all()
+    # the gathered block on every device equals the host copy
+    for s, p in enumerate(ptrs):
+        from lwfbrook90.jl_b200.parallel import DeviceArray
+        t = torch.as_tensor(DeviceArray(p, sc.shape), device=f"cuda:{devices[s]}")
+        assert np.array_equal(t.cpu().numpy(), sc, equal_nan=True)
+    mh.close()
