@@ -983,7 +983,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       // the member ended in this launch before the end of the record: the records it did not reach are NaN
       for (; rec <= d.n_days; rec++) {
         double* dst = rec_m + (int64_t)rec * L;
-        for (int j = i; j < L; j += N) __stcs(dst + j, NAN);
+        for (int j = i; j < L; j += N) __stcs(dst + j, (double)NAN);
       }
     }
     flush_state();
