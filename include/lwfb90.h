@@ -169,7 +169,11 @@ typedef struct lwfb_opts {
   int32_t record_daily;       /* 1: keep the full daily record in HBM; 0: scores only */
 } lwfb_opts;
 
-#define LWFB_MAX_LAYERS 64
+/* Layer counts: 3..32 run in the lane-per-layer kernel, 33..LWFB_MAX_LAYERS in the warp-per-member kernel (a member's
+ * per-layer arrays live in shared memory; the reference's integration tests go up to N = 400,
+ * test/02-integration-tests.jl:383), 1..2 (and, for testing, up to LWFB_MEMBER_MAX_LAYERS) in the thread-per-member kernel. */
+#define LWFB_MAX_LAYERS 512
+#define LWFB_MEMBER_MAX_LAYERS 64
 
 typedef struct lwfb_handle lwfb_handle;
 

@@ -20,7 +20,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 # produced wrong results in this kernel twice (round 1: a select between the addresses of two local arrays; round 2:
 # isoBEA2016 member 22 goes NaN in its first step while -O1, -O0, the host build of the same text and the lane kernel agree
 # with the oracle bit for bit, tools/legacy_diag.py).  Both builds are checked against the oracle by the GPU tests.
-UNITS = [("lwfb90.cu", []), ("lwfb90_member.cu", ["-Xcicc", "-O1"]), ("lwfb90_multi.cu", [])]
+UNITS = [("lwfb90.cu", []), ("lwfb90_member.cu", ["-Xcicc", "-O1"]), ("lwfb90_multi.cu", []),
+         ("lwfb90_wide.cu", ["-DLWFB_CB_SCRATCH=1"])]
 
 
 def _deps():

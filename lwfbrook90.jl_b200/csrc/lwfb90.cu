@@ -246,6 +246,7 @@ extern "C" int lwfb_create(lwfb_handle** out, const lwfb_opts* opts) {
   *out = nullptr;
   if (opts->n_layers < 1 || opts->n_layers > LWFB_MAX_LAYERS) return LWFB_ERR_UNSUPPORTED;
   if (opts->n_days < 1 || opts->t0_day < 0) return LWFB_ERR_ARG;
+  if (opts->n_layers > 32 && opts->n_layers > wide_max_layers(opts->device)) return LWFB_ERR_UNSUPPORTED;   // member block > shared memory of an SM
   lwfb_handle* h = new lwfb_handle();
   h->o = *opts;
   h->L = LWFB_STATE_LEN(opts->n_layers, opts->simulate_isotopes);
@@ -448,6 +449,8 @@ static DevData make_dev(lwfb_handle* h) {
 }
 
 static bool use_lanes(const lwfb_handle* h) { return h->o.n_layers >= 3 && h->o.n_layers <= 32 && !h->force_legacy; }
+// deep profiles: one warp per member, per-layer arrays in shared memory (lwfb90_wide.cuh)
+static bool use_wide(const lwfb_handle* h) { return h->o.n_layers > 32 && !h->force_legacy; }
 
 // Sorting concentrates the expensive members in few blocks: good when the blocks outnumber the resident slots several
 // times (the block scheduler balances), bad for a launch of one or two waves (it only makes the slowest block slower).
@@ -520,8 +523,11 @@ static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) 
     else if (d.N == 8) LWFB_LAUNCH(8, 1);
     else LWFB_LAUNCH(32, 1);
 #undef LWFB_LAUNCH
+  } else if (use_wide(h)) {
+    cudaError_t e = launch_wide_integrate(d, h->o.device, st);   // warp-per-member, 32 < N <= LWFB_MAX_LAYERS
+    if (e != cudaSuccess) { h->err = std::string("wide kernel: ") + cudaGetErrorString(e); return LWFB_ERR_CUDA; }
   } else {
-    launch_member_integrate(d, st);   // thread-per-member, runtime layer count (N < 3 or N > 32)
+    launch_member_integrate(d, st);   // thread-per-member, runtime layer count (N < 3; testing: N <= LWFB_MEMBER_MAX_LAYERS)
   }
   CK(cudaGetLastError());
   h->n_launches++;
@@ -965,7 +971,7 @@ extern "C" int lwfb_eval_rhs(lwfb_handle* h, double t, const double* swati, cons
   CK(cudaMemcpy(d_fr, frozen, n_fr * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_nt, ntfli_prev, n_sw * sizeof(double), cudaMemcpyHostToDevice));
   DevData d = make_dev(h);
-  if (use_lanes(h)) {
+  if (use_lanes(h) || use_wide(h)) {
     // the production kernel evaluates f once through its own stage-0 code (DevData::probe_*): state = u0 with SWATI and
     // GWAT replaced by the arguments
     const int L = h->L;
@@ -1051,6 +1057,7 @@ extern "C" int lwfb_fp64_peak(int32_t device, int32_t reps, double* tflops) {
 // testing aid: select the thread-per-member kernel (the second, independent CUDA implementation)
 extern "C" int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on) {
   if (!h) return LWFB_ERR_ARG;
+  if (on == 1 && h->o.n_layers > LWFB_MEMBER_MAX_LAYERS) { h->err = "the thread-per-member kernel holds at most LWFB_MEMBER_MAX_LAYERS layers"; return LWFB_ERR_UNSUPPORTED; }
   h->force_legacy = on == 1;        // 1: thread-per-member kernel
   h->force_general = on == 2;       // 2: lane kernel, but never its lean / fixed-N instantiations
   return LWFB_OK;

@@ -177,7 +177,7 @@ struct SIdx {
 // ---------------------------------------------------------------------------------------------
 template <int NT>
 struct Member {
-  static constexpr int NMAX = NT > 0 ? NT : LWFB_MAX_LAYERS;
+  static constexpr int NMAX = NT > 0 ? NT : LWFB_MEMBER_MAX_LAYERS;
   int N;
   int64_t m, M;
   const double* __restrict__ scal;
@@ -654,15 +654,35 @@ __device__ inline void snowpack(double RTHR, double STHR, double PSNVP, double S
 }
 
 // TBYLAYER src/module_EVP.jl:301-419.  FLAG kept as a bit mask (N <= 64).
+//
+// LWFB_CB_SCRATCH (the wide kernel's translation unit, any layer count): the per-layer work arrays of the daily callback
+// (here RI and the layer flags, in cb_core RELDEN, RROOTI, ALPHA, ATRI2) live in a workspace the caller provides
+// (ParamView::scratch, LWFB_CB_SCRATCH_ROWS rows of N doubles) instead of thread-local arrays of a compile-time size,
+// and the flags are one word per layer.  Without it the text below is what it has always been.
+#ifdef LWFB_CB_SCRATCH
+#define LWFB_CB_SCRATCH_ROWS 7
+#define LWFB_CB_ARR(name, n, row) double* const name = pv.scratch + (size_t)(row) * pv.N
+#define LWFB_TBY_WS_PARAM , double* tby_ws
+#define LWFB_TBY_WS_ARG , pv.scratch + (size_t)5 * pv.N
+#define LWFB_TBY_DECL double* const RI = tby_ws; double* const FLAGW = tby_ws + N; for (int i_ = 0; i_ < N; i_++) FLAGW[i_] = 0.0
+#define LWFB_TBY_SET(i) (FLAGW[i] = 1.0)
+#define LWFB_TBY_TEST(i) (FLAGW[i] != 0.0)
+#else
+#define LWFB_CB_ARR(name, n, row) double name[n]
+#define LWFB_TBY_WS_PARAM
+#define LWFB_TBY_WS_ARG
+#define LWFB_TBY_DECL unsigned long long FLAG = 0ull; double RI[NMAX]
+#define LWFB_TBY_SET(i) (FLAG |= (1ull << (i)))
+#define LWFB_TBY_TEST(i) (((FLAG >> (i)) & 1ull) != 0ull)
+#endif
 template <int NMAX>
 __device__ inline double tbylayer(int N, int J, double PTR, double DISPC, const double* ALPHA, const double* KK,
                                   const double* RROOTI, double RXYLEM, const double* PSITI, double PSICR,
-                                  bool NOOUTF, double* ATRANI) {
-  unsigned long long FLAG = 0ull;
-  double RI[NMAX];
+                                  bool NOOUTF, double* ATRANI LWFB_TBY_WS_PARAM) {
+  LWFB_TBY_DECL;
   for (int i = 0; i < N; i++) {
-    if (RROOTI[i] > 1E+15) FLAG |= (1ull << i);
-    else if (NOOUTF && PSITI[i] / 1000. <= PSICR) FLAG |= (1ull << i);
+    if (RROOTI[i] > 1E+15) LWFB_TBY_SET(i);
+    else if (NOOUTF && PSITI[i] / 1000. <= PSICR) LWFB_TBY_SET(i);
     RI[i] = 0; ATRANI[i] = 0;
   }
   double ATR = 0.0;
@@ -670,14 +690,14 @@ __device__ inline double tbylayer(int N, int J, double PTR, double DISPC, const 
     bool NEGFLAG = false;
     double SUM = 0;
     for (int i = 0; i < N; i++) {
-      if (!((FLAG >> i) & 1ull)) { RI[i] = RROOTI[i] + ALPHA[i] / KK[i]; SUM = SUM + 1.0 / RI[i]; }
+      if (!LWFB_TBY_TEST(i)) { RI[i] = RROOTI[i] + ALPHA[i] / KK[i]; SUM = SUM + 1.0 / RI[i]; }
       else ATRANI[i] = 0.0;
     }
     if (SUM < 1E-20) { ATR = 0.; break; }
     double RT = 1.0 / SUM;
     double PSIT = 0;
     for (int i = 0; i < N; i++)
-      if (!((FLAG >> i) & 1ull)) PSIT = PSIT + RT * PSITI[i] / RI[i];
+      if (!LWFB_TBY_TEST(i)) PSIT = PSIT + RT * PSITI[i] / RI[i];
     double SUPPLY = (PSIT / 1000 - PSICR - p_RHOWG * DISPC) / (RT + RXYLEM);
     if (J == 1) {
       double R = (2 / p_PI) * (SUPPLY / PTR);
@@ -689,7 +709,7 @@ __device__ inline double tbylayer(int N, int J, double PTR, double DISPC, const 
       else ATR = jmin(SUPPLY, PTR);
     }
     for (int i = 0; i < N; i++) {
-      if ((FLAG >> i) & 1ull) ATRANI[i] = 0;
+      if (LWFB_TBY_TEST(i)) ATRANI[i] = 0;
       else {
         ATRANI[i] = ((PSITI[i] - PSIT) / 1000 + RT * ATR) / RI[i];
         if (ATRANI[i] < -0.000001) NEGFLAG = true;
@@ -700,7 +720,7 @@ __device__ inline double tbylayer(int N, int J, double PTR, double DISPC, const 
       double TRMIN = 0;
       for (int i = 0; i < N; i++)
         if (ATRANI[i] < TRMIN) { TRMIN = ATRANI[i]; IDEL = i; }
-      FLAG |= (1ull << IDEL);
+      LWFB_TBY_SET(IDEL);
     } else break;
   }
   return ATR;
@@ -723,6 +743,9 @@ struct ParamView {
   int64_t m, M;
   const double* __restrict__ scal;
   const double* __restrict__ lay;
+#ifdef LWFB_CB_SCRATCH
+  double* scratch;   // [LWFB_CB_SCRATCH_ROWS][N] work arrays of the daily callback
+#endif
   __device__ __forceinline__ double S(int k) const { return __ldg(scal + m * LWFB_PS + k); }
   __device__ __forceinline__ double Lp(int k, int i) const { return __ldg(lay + (m * LWFB_PL + k) * N + i); }
 };
@@ -748,7 +771,7 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
   double LAI = frow[LWFB_F_LAI_REL] * pv.S(LWFB_S_MAXLAI);
   double SAI = frow[LWFB_F_SAI_REL] * pv.S(LWFB_S_SAI_BASELINE);
   // relative root density of the day (HammelKennel_lateral_rootgrowth, src/func_DiffEq_definition_p.jl:606-628)
-  double RELDEN[NMAX];
+  LWFB_CB_ARR(RELDEN, NMAX, 0);
   if (pv.S(LWFB_S_RELDEN_CONST) != 0.0) {
     for (int i = 0; i < N; i++) RELDEN[i] = pv.Lp(LWFB_L_TINI, i) > 1e19 ? 0.0 : pv.Lp(LWFB_L_RELDEN, i);
   } else {
@@ -769,7 +792,8 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
   double RPLANT = 1 / KPL;
   double LAIeff0 = DENSEF * LAI;
   double SNOFRC = snofrac(TMAX, TMIN, pv.S(LWFB_S_RSTEMP));
-  double RROOTI[NMAX], ALPHA[NMAX];
+  LWFB_CB_ARR(RROOTI, NMAX, 1);
+  LWFB_CB_ARR(ALPHA, NMAX, 2);
   double RXYLEM = pv.S(LWFB_S_FXYLEM) * RPLANT;
   {
     double sumRD = 0;
@@ -857,7 +881,11 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
   }
   // ---- MSBDAYNIGHT
   double PTR[2], GER[2], PIR[2], GIR[2], PGER[2];
+#ifdef LWFB_CB_SCRATCH
+  double* const ATRI2[2] = {pv.scratch + (size_t)3 * pv.N, pv.scratch + (size_t)4 * pv.N};
+#else
   double ATRI2[2][NMAX];      // day / night uptake by layer
+#endif
   double C1 = pv.S(LWFB_S_C1), C2 = pv.S(LWFB_S_C2), C3 = pv.S(LWFB_S_C3), CR = pv.S(LWFB_S_CR);
   double GLMIN = pv.S(LWFB_S_GLMIN), PSICR = pv.S(LWFB_S_PSICR);
   bool NOOUTF = pv.S(LWFB_S_NOOUTF) != 0.0;
@@ -881,7 +909,7 @@ __device__ LWFB_CB_INLINE void cb_core(const ParamView& pv, const double* __rest
     swpe(AA, ASUBS, VPD, RAA, RAC, RAS, RSC, 0, DELTA, dmy, PGER[J - 1]);
     double* ATRI = ATRI2[J - 1];
     if (PTR[J - 1] > 0.001) {
-      double ATR = tbylayer<NMAX>(N, J, PTR[J - 1], DISPC, ALPHA, kk, RROOTI, RXYLEM, psiti, PSICR, NOOUTF, ATRI);
+      double ATR = tbylayer<NMAX>(N, J, PTR[J - 1], DISPC, ALPHA, kk, RROOTI, RXYLEM, psiti, PSICR, NOOUTF, ATRI LWFB_TBY_WS_ARG);
       if (ATR < PTR[J - 1]) GER[J - 1] = swge(AA, ASUBS, VPD, RAA, RAS, RSS, DELTA, ATR);
     } else {
       PTR[J - 1] = 0;
@@ -979,7 +1007,7 @@ __device__ __forceinline__ double dxdt_to_dddt(double dxdt, double x, double R) 
 // isotope state carried between steps: delta of SWATI[N], GWAT, RWU, XYLEM for 18O and 2H
 template <int NT>
 struct IsoState {
-  static constexpr int NMAX = NT > 0 ? NT : LWFB_MAX_LAYERS;
+  static constexpr int NMAX = NT > 0 ? NT : LWFB_MEMBER_MAX_LAYERS;
   double dS[2][NMAX];
   double dG[2], dRWU[2], dXY[2];
 };

@@ -52,6 +52,7 @@ template <typename T> static inline T simt_shfl(T v, int src, int op) { return s
 #define __shfl_sync(mask, v, src) simt_shfl((v), (src), LWFB_OP_ID)
 #define __shfl_up_sync(mask, v, delta) simt_shfl((v), simt::lane_id() - (int)(delta), LWFB_OP_ID)
 #define __shfl_down_sync(mask, v, delta) simt_shfl((v), simt::lane_id() + (int)(delta), LWFB_OP_ID)
+#define __shfl_xor_sync(mask, v, o) simt_shfl((v), simt::lane_id() ^ (int)(o), LWFB_OP_ID)
 #define __ballot_sync(mask, p) simt::vote((p), LWFB_OP_ID)
 #define __any_sync(mask, p) (simt::vote((p), LWFB_OP_ID) != 0u)
 #define __all_sync(mask, p) (simt::vote((p), LWFB_OP_ID) == 0xffffffffu)

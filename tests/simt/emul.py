@@ -15,36 +15,58 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(os.path.dirname(_HERE))
 _SO = os.path.join(_HERE, "_build", "libsimt_emul.so")
+_SO_WIDE = os.path.join(_HERE, "_build", "libsimt_emul_wide.so")     # the warp-per-member kernel (N > 32): own build, see simt_emul.cpp
 _lib = None
+_lib_wide = None
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 _lp = C.POINTER(C.c_int64)
 
-LANES, MEMBER = 0, 1
+LANES, MEMBER, WIDE = 0, 1, 2
 
 
-def build(force: bool = False) -> str:
+def build(force: bool = False, wide: bool = False) -> str:
+    _SO = _SO_WIDE if wide else globals()["_SO"]
     deps = [os.path.join(_HERE, "simt_emul.cpp")] + glob.glob(os.path.join(_ROOT, "lwfbrook90.jl_b200", "csrc", "*.cuh")) \
         + glob.glob(os.path.join(_ROOT, "lwfbrook90.jl_b200", "csrc", "*.h")) + glob.glob(os.path.join(_ROOT, "include", "*.h"))
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(f) for f in deps):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
         fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read().split() else []
         subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", *fma, "-fPIC", "-shared",
-                               "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"), "-lpthread"])
+                               *(["-DLWFB_EMUL_WIDE=1"] if wide else []), "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"), "-lpthread"])
     return _SO
 
 
-def lib():
-    global _lib
+def _load(path):
+    L = C.CDLL(path)
+    L.lwfb_emul_run.restype = C.c_int
+    L.lwfb_emul_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int64, _ip,
+                                _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int,
+                                _dp, _ip, _lp, _ip, C.c_int, C.c_int, C.c_int64, C.c_int]
+    return L
+
+
+_current_wide = False     # which build the helper calls (set_observations, set_ntfli0, eval_rhs ...) address
+
+
+def lib(wide=None):
+    global _lib, _lib_wide
+    if wide is None:
+        wide = _current_wide
+    if wide:
+        if _lib_wide is None:
+            _lib_wide = _load(build(wide=True))
+        return _lib_wide
     if _lib is None:
-        build()
-        _lib = C.CDLL(_SO)
-        _lib.lwfb_emul_run.restype = C.c_int
-        _lib.lwfb_emul_run.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp, C.c_int64, _ip,
-                                       _dp, _dp, _dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, C.c_int,
-                                       _dp, _ip, _lp, _ip, C.c_int, C.c_int, C.c_int64, C.c_int]
+        _lib = _load(build())
     return _lib
+
+
+def use_wide(on: bool):
+    """Route the helper calls and run() to the build that holds the warp-per-member kernel (N > 32)."""
+    global _current_wide
+    _current_wide = bool(on)
 
 
 def _p(a, t=_dp):
@@ -87,7 +109,7 @@ def get_ntfli(M, N):
     return out
 
 
-def eval_rhs(N, iso, forcing, site_of_member, scal, lay, u0, t, swati, gwat, frozen, ntfli_prev, warps_per_block=1):
+def eval_rhs(N, iso, forcing, site_of_member, scal, lay, u0, t, swati, gwat, frozen, ntfli_prev, warps_per_block=1, kernel=LANES):
     """One evaluation of f(u, t) by the LANE kernel's own stage code (the probe behind lwfb_eval_rhs for 3 <= N <= 32):
     du [M, N+9]."""
     L = lib()
@@ -101,7 +123,7 @@ def eval_rhs(N, iso, forcing, site_of_member, scal, lay, u0, t, swati, gwat, fro
     du = np.full((M, N + 9), np.nan)
     L.lwfb_emul_set_probe(_p(fr), _p(nt), float(t), _p(du))
     try:
-        run(LANES, N, iso, 0, 1, forcing, site_of_member, scal, lay, u0p, seg_len=1, warps_per_block=warps_per_block)
+        run(kernel, N, iso, 0, 1, forcing, site_of_member, scal, lay, u0p, seg_len=1 if kernel == LANES else 0, warps_per_block=warps_per_block)
     finally:
         L.lwfb_emul_set_probe(None, None, 0.0, None)
     return du
@@ -139,6 +161,7 @@ def run(kernel, N, iso, t0_day, n_days, forcing, site_of_member, scal, lay, u0, 
     out = np.empty((M, n_days + 1, L))
     status = np.zeros(M, dtype=np.int32)
     counters = np.zeros((M, 3), dtype=np.int64)
+    assert (kernel == WIDE) == _current_wide, "use_wide(True) selects the build that holds the warp-per-member kernel"
     rc = lib().lwfb_emul_run(int(kernel), N, int(iso), int(t0_day), int(n_days), n_sites, n_rows, _p(forcing), M, _p(som, _ip),
                              _p(scal), _p(lay), _p(u0), reltol, abstol, dt_init, dtmax, maxiters, int(n_threads), _p(out),
                              _p(status, _ip), _p(counters, _lp),

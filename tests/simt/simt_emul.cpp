@@ -23,9 +23,19 @@
 #include <vector>
 
 #include "../../lwfbrook90.jl_b200/csrc/lwfb90_simt.h"
+#ifdef LWFB_EMUL_WIDE
+// second build of this file (libsimt_emul_wide.so): the warp-per-member kernel for N > 32, whose translation unit is
+// compiled with the workspace form of the daily callback (as lwfb90_wide.cu is); kernel id 2, nothing else
+#define LWFB_CB_SCRATCH 1
+#include "../../lwfbrook90.jl_b200/csrc/lwfb90_device.cuh"
+#include "../../lwfbrook90.jl_b200/csrc/lwfb90_wide.cuh"
+#define LWFB_LANES_BLOCK 256
+namespace lwfb { enum { KC_COUNT = 1, KM_COUNT = 1 }; }
+#else
 #include "../../lwfbrook90.jl_b200/csrc/lwfb90_device.cuh"
 #include "../../lwfbrook90.jl_b200/csrc/lwfb90_lanes.cuh"
 #include "../../lwfbrook90.jl_b200/csrc/lwfb90_member.cuh"
+#endif
 
 namespace {
 constexpr int WARP = 32;
@@ -263,6 +273,12 @@ struct Job {
 
 struct WarpArg { const lwfb::DevData* d; int64_t block; int warps; double* cst; bool by_budget; bool lean; double* msm; };
 
+#ifdef LWFB_EMUL_WIDE
+void lanes_entry(void* a, int tid) {             // one warp = one member; cst: the member's shared-memory block
+  WarpArg* wa = (WarpArg*)a;
+  lwfb::wide_body(*wa->d, tid & 31, wa->block, wa->cst);
+}
+#else
 void lanes_entry(void* a, int tid) {             // tid = thread index within the emulated block
   WarpArg* wa = (WarpArg*)a;
   const lwfb::DevData& d = *wa->d;
@@ -278,12 +294,20 @@ void lanes_entry(void* a, int tid) {             // tid = thread index within th
   else b = lwfb::lanes_body<32, 1>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
   if (tid == 0) wa->by_budget = b;
 }
+#endif
 
 void* worker(void* p) {
   Job* j = (Job*)p;
   for (;;) {
     int64_t u = j->next.fetch_add(1);
     if (u >= j->n_units) break;
+#ifdef LWFB_EMUL_WIDE
+    {
+      std::vector<double> blk(LWFB_WIDE_DOUBLES_PER_MEMBER(j->d.N));
+      WarpArg wa{&j->d, u, 1, blk.data(), false, false, nullptr};
+      run_block(lanes_entry, &wa, 1);
+    }
+#else
     if (j->kernel == 0) {
       std::vector<double> cst((size_t)lwfb::KC_COUNT * LWFB_LANES_BLOCK);
       std::vector<double> msm((size_t)(lwfb::KM_COUNT + 2 * LWFB_F) * j->warps * (32 / j->d.N));
@@ -296,6 +320,7 @@ void* worker(void* p) {
     } else {
       lwfb::integrate_member<0>(j->d, u);
     }
+#endif
   }
   return nullptr;
 }
@@ -343,6 +368,12 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
   (void)n_sites;
   const int L = LWFB_STATE_LEN(N, iso);
   if (kernel == 0 && (N < 3 || N > 32)) return -1;
+#ifdef LWFB_EMUL_WIDE
+  if (kernel != 2) return -1;
+#else
+  if (kernel == 2) return -1;
+  if (kernel == 1 && N > LWFB_MEMBER_MAX_LAYERS) return -1;
+#endif
   // the device layouts are member-major = the layouts of the arguments: the kernels read and write them in place
   std::vector<double> fin((size_t)M * L);
   static_assert(sizeof(long long) == sizeof(int64_t), "counter width");

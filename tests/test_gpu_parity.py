@@ -138,11 +138,14 @@ def test_ensemble_bit_identical_to_oracle(which, M, nd, request):
 
 
 def test_generic_layer_count_kernels_bit_identical(lw, infexp1):
-    """N = 42 (INFEXP1, saturation/bypass regime incl.) and N = 13 (DAV2020-bare-minimum) go through the
-    runtime-N kernel."""
+    """N = 42 (INFEXP1, saturation/bypass regime incl.) through the warp-per-member kernel (N > 32) and, forced, through
+    the thread-per-member kernel; N = 13 (DAV2020-bare-minimum) through the lane kernel's general instantiation."""
     e = en.batched_setup(infexp1, params={"DRAIN": np.array([1.0, 0.6, 0.3])})
     h, sub, nd = gpu_run(e, 260)
-    assert_bit_identical(h, sub, nd)
+    gpu = assert_bit_identical(h, sub, nd)
+    h.force_legacy(True)
+    h.run()
+    assert np.array_equal(h.get_daily(), gpu, equal_nan=True)
     h.close()
     m = lw.loadSPAC(inputs("DAV2020-bare-minimum"), "DAV2020-minimal", simulate_isotopes=False, Δz_thickness_m=[0.1] * 11,
                     root_distribution=dict(beta=0.77, z_rootMax_m=-0.5), IC_soil=dict(PSIM_init_kPa=-7.0),
@@ -160,6 +163,40 @@ def test_generic_layer_count_kernels_bit_identical(lw, infexp1):
     h, sub, nd = gpu_run(e)
     assert_bit_identical(h, sub, nd)
     h.close()
+
+
+@pytest.mark.parametrize("N,nd,M", [(40, 20, 40), (100, 4, 5), (400, 1, 3)])
+def test_wide_kernel_deep_profiles(lw, N, nd, M):
+    """The warp-per-member kernel (lwfb90_wide.cuh: 32 < N <= LWFB_MAX_LAYERS, per-layer arrays in shared memory, layers
+    strided over the lanes) with isotopes on refined DAV2020-full grids up to the 400 layers of the reference's
+    Hammel_sand-NLayer-400 integration test (test/02-integration-tests.jl:383): records, status, counters, du_NTFLI and
+    the scores accumulated during the run, bit for bit against the oracle; one member aborts."""
+    m = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=aligned_grid(N),
+                    root_distribution=dict(beta=0.97, z_rootMax_m=None),
+                    IC_soil=dict(PSIM_init_kPa=-6.0, delta18O_init_permil=-12.0, delta2H_init_permil=-90.0))
+    s = lw.setup(m, ε=0.001, requested_tspan=(100, 100 + nd))
+    assert s.N == N
+    e = en.make_ensemble(s, M)
+    e.u0[M - 1, N // 3] = np.nan                      # Unstable at its first step
+    rng = np.random.default_rng(N)
+    obs_day, obs_layer = np.arange(0, nd + 1), np.array([0, N // 2, N - 1])
+    th, d18 = rng.uniform(0.1, 0.4, (nd + 1, 3)), rng.uniform(-14, -8, (nd + 1, 3))
+    h = capi.Handle(e.N, e.iso, e.t0_day, nd)
+    h.set_sites(e.forcing); h.set_members(e.site_of_member, e.scal, e.lay, e.u0)
+    h.set_observations(obs_day, obs_layer, th, d18)
+    h.run()
+    gpu = assert_bit_identical(h, e, nd)
+    st, _ = h.get_status()
+    assert st[M - 1] == lo.ST.UNSTABLE and (st[:-1] == 0).all()
+    from_sums = h.scores()
+    nt = h.get_ntfli()
+    orc.use("elem")
+    o = orc.run_member(e.N, e.iso, e.t0_day, nd, e.forcing[0], e.scal[0], e.lay[0], e.u0[0])
+    assert np.array_equal(nt[0], o[3])
+    h2 = capi.Handle(e.N, e.iso, e.t0_day, nd)          # the record-based scorer on the same records
+    h2.set_sites(e.forcing); h2.set_members(e.site_of_member, e.scal, e.lay, e.u0); h2.run()
+    assert np.array_equal(from_sums, h2.scores(obs_day, obs_layer, th, d18), equal_nan=True)
+    h.close(); h2.close()
 
 
 def test_thread_per_member_kernel_agrees_with_lane_per_layer_kernel(dav_full, bea, isobea):
@@ -653,7 +690,7 @@ def _gpu_single(sim, n_days=None, ntfli0=None, legacy=False):
 @pytest.mark.parametrize("modified", [False, True])
 def test_G2_G3_infexp1_golden_through_the_gpu(lw, infexp1, modified):
     """Goldens G2 / G3 (examples/INFEXP1*_fluxes_referencedf.csv, run definition test/03-regression-tests.jl:352-367)
-    compared DIRECTLY with the GPU record (N = 42: thread-per-member kernel), with the bounds the oracle is held to."""
+    compared DIRECTLY with the GPU record (N = 42: warp-per-member kernel), with the bounds the oracle is held to."""
     from test_oracle_golden import _flux_cmp
     sim = infexp1
     if modified:
@@ -673,7 +710,8 @@ def test_G2_G3_infexp1_golden_through_the_gpu(lw, infexp1, modified):
 
 def test_G4_dav2020_modified_golden_through_the_gpu(lw):
     """Golden G4 (examples/DAV2020-full-modified_fluxes_referencedf.csv, test/03-regression-tests.jl:411-458; N = 40,
-    every optional flow path switched on) against the GPU record at the reference's own tolerance, all 30 series."""
+    every optional flow path switched on: warp-per-member kernel) against the GPU record at the reference's own tolerance,
+    all 30 series."""
     from test_oracle_golden import _dav_modified, _flux_cmp
     sim = _dav_modified(lw)
     assert sim.N == 40

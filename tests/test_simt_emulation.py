@@ -25,8 +25,12 @@ def check(ens, n_days, kernel, members=None):
     orc.use("elem")
     ref, st_o, cnt_o = orc.run(sub.N, sub.iso, sub.t0_day, n_days, sub.forcing, sub.site_of_member, sub.scal, sub.lay,
                                sub.u0, n_threads=8)
-    got, st, cnt = emul.run(kernel, sub.N, sub.iso, sub.t0_day, n_days, sub.forcing, sub.site_of_member, sub.scal,
-                            sub.lay, sub.u0)
+    emul.use_wide(kernel == emul.WIDE)
+    try:
+        got, st, cnt = emul.run(kernel, sub.N, sub.iso, sub.t0_day, n_days, sub.forcing, sub.site_of_member, sub.scal,
+                                sub.lay, sub.u0)
+    finally:
+        emul.use_wide(False)
     assert np.array_equal(st, st_o)
     assert np.array_equal(cnt, cnt_o), "accepted / rejected / RHS-evaluation counters differ"
     same = (got == ref) | (np.isnan(got) & np.isnan(ref))
@@ -99,6 +103,93 @@ def test_member_kernel_generic_layer_count(lw, dav_full):
     e = en.batched_setup(infexp(lw, 42), params={"DRAIN": np.array([1.0, 0.3])})
     check(e, 20, emul.MEMBER)
     check(en.make_ensemble(dav_full, 6), 10, emul.MEMBER)
+
+
+def test_wide_kernel_saturation_bypass_groundwater(lw):
+    """Warp-per-member kernel (N > 32, lwfb90_wide.cuh): INFEXP1 on its 42-layer grid through the infiltration pulse -
+    saturated layers, the bottom-up INFLOW limiter (lane 0 walks the chain only when a warp vote says a layer limits),
+    bypass flow, groundwater feedback, ITER's clamped chain, hundreds of rejected steps."""
+    s = infexp(lw, 42)
+    assert s.N == 42
+    e = en.batched_setup(s, params={"DRAIN": np.array([1.0, 0.6, 0.3, 0.8]), "BYPAR": np.array([0., 1., 1., 0.]),
+                                    "QFPAR": np.array([0.3, 0.3, 0.1, 0.3]), "QFFC": np.array([0.2, 0.2, 0.4, 0.2])})
+    e.t0_day, e.n_days = 226, 6
+    ref, cnt = check(e, e.n_days, emul.WIDE)
+    ix = lo.StateIndex(e.N, e.iso)
+    assert (ref[:, :, ix.SWATI_mm] / e.lay[:, None, lo.L.SWATMAX, :] >= 1.0).any(), "the window must contain saturated layers"
+    assert (cnt[:, 1] > 10).all(), "the window must contain rejected steps"
+
+
+@pytest.mark.parametrize("N", [40, 70])
+def test_wide_kernel_isotopes_deep_profiles(lw, N):
+    """Warp-per-member kernel with isotopes: 40 layers (the layer count of golden G4) and 70 (three layers per lane for
+    some lanes, two for others), scores accumulated at observation days, du_NTFLI left behind, one aborting member."""
+    m = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=aligned_grid(N),
+                    root_distribution=dict(beta=0.97, z_rootMax_m=None),
+                    IC_soil=dict(PSIM_init_kPa=-6.0, delta18O_init_permil=-12.0, delta2H_init_permil=-90.0))
+    s = lw.setup(m, ε=0.001, requested_tspan=(100, 103))
+    assert s.N == N
+    e = en.make_ensemble(s, 3)
+    e.u0[2, 7] = np.nan                       # member 2: NaN in SWATI -> Unstable at its first step
+    nd = 3 if N == 40 else 1
+    orc.use("elem")
+    obs_day, obs_layer = np.array([0, 1]), np.array([0, N // 2, N - 1])
+    rng = np.random.default_rng(2)
+    th, d18 = rng.uniform(0.1, 0.4, (2, 3)), rng.uniform(-14, -8, (2, 3))
+    ref, st_o, cnt_o, sums_o, nt_o = [], [], [], [], []
+    for k in range(e.M):
+        r = orc.run_member(e.N, e.iso, e.t0_day, nd, e.forcing[0], e.scal[k], e.lay[k], e.u0[k])
+        ref.append(r[0]); st_o.append(r[1]); cnt_o.append(r[2]); nt_o.append(r[3])
+    emul.use_wide(True)
+    try:
+        emul.set_observations(nd, obs_day, obs_layer, th, d18)
+        got, st, cnt = emul.run(emul.WIDE, e.N, e.iso, e.t0_day, nd, e.forcing, e.site_of_member, e.scal, e.lay, e.u0)
+        sums = emul.score_sums(e.M)
+        nt = emul.get_ntfli(e.M, e.N)
+        emul.set_observations(nd)
+    finally:
+        emul.use_wide(False)
+    assert list(st) == st_o and st_o[2] != 0 and st_o[0] == 0
+    assert np.array_equal(cnt, np.array(cnt_o)) and np.array_equal(got, np.array(ref), equal_nan=True)
+    assert np.array_equal(nt[:2], np.array(nt_o)[:2], equal_nan=True)
+    # the sums: the same additions in the same order as a scorer walking the record (days outer, layers inner)
+    ix = lo.StateIndex(N, True)
+    for k in range(2):
+        a = np.zeros(7); b = np.zeros(7)
+        for j, dday in enumerate(obs_day):
+            for l, il in enumerate(obs_layer):
+                sw = got[k, dday, ix.SWATI_mm][il]
+                ths, thr, smax = e.lay[k, lo.L.THSAT, il], e.lay[k, lo.L.THR, il], e.lay[k, lo.L.SWATMAX, il]
+                w = min((ths * sw / smax - thr) / (ths - thr), 1.0)
+                for acc, sim_, o in ((a, w * (ths - thr) + thr, th[j, l]), (b, got[k, dday, ix.SWATI_d18O][il], d18[j, l])):
+                    err = sim_ - o
+                    acc += np.array([1, err * err, o, sim_, o * o, sim_ * sim_, o * sim_])
+        assert np.allclose(sums[k, 0], a, rtol=1e-14) and np.allclose(sums[k, 1], b, rtol=1e-14)
+
+
+def test_wide_kernel_rhs_probe(lw):
+    """One evaluation of f(u, t) by the warp-per-member kernel's own RHS (the probe behind lwfb_eval_rhs for N > 32)."""
+    e = en.batched_setup(infexp(lw, 42), params={"DRAIN": np.linspace(0.1, 1, 6), "BYPAR": np.array([0., 1., 0., 1., 0., 1.])})
+    N, M = e.N, e.M
+    rng = np.random.default_rng(5)
+    ix = lo.StateIndex(N, e.iso)
+    smax = e.lay[:, lo.L.SWATMAX]
+    swati = e.u0[:, ix.SWATI_mm] * rng.uniform(0.5, 1.3, (M, N))
+    swati[0] = smax[0] * 1.01; swati[3, 0] = -0.1
+    gwat = rng.uniform(0, 5, M); gwat[1] = 0.0
+    frozen = np.concatenate([rng.uniform(0, 30, (M, 1)), rng.uniform(0, 2, (M, 1)), rng.uniform(0, 1, (M, 1)),
+                             rng.uniform(-0.01, 0.5, (M, N))], axis=1)
+    ntfli = rng.normal(0, 20, (M, N)); ntfli[2] = np.nan
+    orc.use("elem")
+    emul.use_wide(True)
+    try:
+        du = emul.eval_rhs(N, e.iso, e.forcing, e.site_of_member, e.scal, e.lay, e.u0, 0.3712, swati, gwat, frozen, ntfli,
+                           kernel=emul.WIDE)
+    finally:
+        emul.use_wide(False)
+    for m in range(M):
+        ref, _ = orc.eval_rhs(N, e.scal[m], e.lay[m], 0.3712, swati[m], gwat[m], frozen[m], ntfli[m])
+        assert np.array_equal(du[m], ref, equal_nan=True), m
 
 
 def test_lane_kernel_placement_does_not_change_results(dav_full):
