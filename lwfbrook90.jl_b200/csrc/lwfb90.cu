@@ -622,6 +622,10 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   h->sums_valid = h->n_obs_days > 0;
   int64_t n_left = h->M;
   const bool cold = !h->cost_valid;
+  // diagnostics: LWFB_TRACE=<file> writes one line per launch (members left, blocks, budget, front blocks, slots, ms)
+  const char* trace_path = getenv("LWFB_TRACE");
+  struct TraceRow { int64_t n_left, nb, budget, prio, slots; cudaEvent_t e0, e1; };
+  std::vector<TraceRow> trace;
   for (int launch = 0; n_left > 0; launch++) {
     // a cold handle knows nothing about its members: the first quanta are short (128, 256, ... passes, no front blocks)
     // so that the first regroupings come early
@@ -689,11 +693,32 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
       d.stop = h->d_stop;
       d.resident = R;
     }
+    if (trace_path) {
+      TraceRow r{n_left, nb, (int64_t)d.iter_budget, (int64_t)d.prio_blocks, (int64_t)d.n_slots, nullptr, nullptr};
+      cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+      cudaEventRecord(r.e0, st);
+      trace.push_back(r);
+    }
     int rc = launch_integrator(h, d, st);
     if (rc) return rc;
+    if (trace_path) cudaEventRecord(trace.back().e1, st);
     if ((rc = regroup_by_progress(h, st, &n_left))) return rc;
   }
   CK(cudaEventRecord(h->ev1, st));
+  if (trace_path) {
+    cudaEventSynchronize(h->ev1);
+    if (FILE* f = fopen(trace_path, "a")) {
+      fprintf(f, "# run: M=%lld N=%d days=%d; launch n_left blocks budget front_blocks slots kernel_ms\n", (long long)h->M, h->o.n_layers, h->o.n_days);
+      for (size_t k = 0; k < trace.size(); k++) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, trace[k].e0, trace[k].e1);
+        fprintf(f, "%zu %lld %lld %lld %lld %lld %.3f\n", k, (long long)trace[k].n_left, (long long)trace[k].nb, (long long)trace[k].budget,
+                (long long)trace[k].prio, (long long)trace[k].slots, ms);
+      }
+      fclose(f);
+    }
+    for (auto& r : trace) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  }
   h->perm_valid = false;       // d_perm now holds a partial order of the last launch
   h->ran = true;
   h->cost_valid = true;

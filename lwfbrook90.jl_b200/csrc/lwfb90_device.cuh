@@ -97,7 +97,7 @@ struct DevData {
                                      // raises the flag, and every block checkpoints at its next pass: no slot idles
                                      // at the end of a launch, front blocks need no budget of their own
   long long resident;                // blocks the device holds at a time (for the "no block left" test)
-  int cb_wait;                       // bounded waiting at the day boundary, in passes (LWFB_CB_WAIT)
+  int cb_wait;                       // callback-phase policy parameter (env LWFB_CB_WAIT; 0: the kernel's default), see lwfb90_lanes.cuh
   long long n_slots;                 // slots in use: perm[0 .. n_slots) are the members of this launch (0: all M)
   int resume;                        // 1: continue from fin / ck
   double* __restrict__ ck;           // [M][LWFB_CK + LWFB_CKL * N] checkpoint block (null: single launch, nothing saved)

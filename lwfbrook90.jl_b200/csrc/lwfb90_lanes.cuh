@@ -79,6 +79,7 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
 // instruction stream next to the stepping loop costs more than the waiting it saves; profiles/r02_notes.md.)
 #if !defined(LWFB_LANES_FREE_RUNNING) && (defined(__CUDACC__) || defined(LWFB_SIMT_EMUL))
 #define LWFB_VOTE_ANY(p) (__syncthreads_or((p) ? 1 : 0) != 0)
+#define LWFB_VOTE_COUNT(p) __syncthreads_count((p) ? 1 : 0)
 #ifdef LWFB_SIMT_EMUL
 // the stage barrier is reached from two places (stage loop / warps that idle through a pass): the hardware matches
 // barriers by number, the emulator by this id
@@ -88,18 +89,28 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
 #endif
 #else
 #define LWFB_VOTE_ANY(p) __any_sync(LFULL, (p))
+#define LWFB_VOTE_COUNT(p) __popc(__ballot_sync(LFULL, (p)))
 #define LWFB_STAGE_SYNC() ((void)0)
 #endif
-// A member that has reached its day boundary waits at most this many step iterations of its block for the others;
-// then the daily callback phase runs for the members that are waiting (the rest of the block idles through it).
-// Bounds the cost of one member's bad day for the members that share its block.  Results do not depend on it.
+// When does the block run its (block-uniform) daily callback phase?  A member that has reached its day boundary idles
+// until the phase runs; the phase itself costs every member of the block about 1.5 step passes, whether it takes part or
+// not.  Round 1 bounded the waiting per member (LWFB_CB_POLICY_WAIT: a phase runs when nobody can step or somebody has
+// waited LWFB_CB_WAIT = 32 passes): on BEA2016, where a day takes 25 steps for most members and thousands for a few, the
+// fast members then idle 32 passes per 25 steps.  Now the block weighs the two costs against each other (the ski-rental
+// rule): it counts the member-passes idled at the day boundary since the last phase and runs the phase as soon as they
+// reach LWFB_CB_WASTE2 / 2 passes for each member that still steps - i.e. when waiting has cost what the phase will cost
+// (tools/cb_policy_sim.py replays measured step counts: executed / needed member-passes 1.24 -> 1.10 on BEA2016, 1.35 ->
+// 1.20 on ungrouped DAV2020 members).  Results do not depend on the policy: a member that waits does not change state.
 #ifndef LWFB_CB_WAIT
 #define LWFB_CB_WAIT 32
+#endif
+#ifndef LWFB_CB_WASTE2
+#define LWFB_CB_WASTE2 3
 #endif
 
 // per-thread constant column (shared memory): element k of this thread is cst[k * LWFB_LANES_BLOCK]
 enum {
-  KC_THSAT = 0, KC_THR, KC_DTH, KC_SWATMAX, KC_E1, KC_E2, KC_E3, KC_E4, KC_TORT, KC_CPSI, KC_KSAT, KC_PSIG,
+  KC_THSAT = 0, KC_THR, KC_DTH, KC_SWATMAX, KC_E1, KC_E2, KC_E3, KC_TORT, KC_CPSI, KC_KSAT, KC_PSIG,
   KC_THICK, KC_OMS, KC_INFRAC, KC_THICK_DN, KC_KSAT_DN, KC_TSUM, KC_THALF, KC_STFAC, KC_CITER,
   KC_RDZ_UP, KC_RDZ_DN, KC_RTHS2, KC_RSWATMAX, KC_RDTH, KC_RTSUM, KC_RTHALF,   // R...: reciprocals (div_c, LWFB_RCP)
   // isotope state of the lane (touched once per accepted step): delta18O / delta2H of SWATI[i]
@@ -131,7 +142,10 @@ enum {
   // registers that the stage loop needs: every spilled register costs a trip to L2 here).  All lanes of the group write
   // the same value; read-modify-write sequences read into locals, __syncwarp, then write (no lane may see a value
   // another lane of its group has already advanced).  Counters are stored as doubles (exact).
-  KM_TSTOP, KM_DT, KM_QOLD, KM_ITER, KM_NACCEPT, KM_NREJECT, KM_NF, KM_REC, KM_WAITED, KM_STATUS,
+  KM_TSTOP, KM_DT, KM_QOLD, KM_ITER, KM_NACCEPT, KM_NREJECT, KM_NF, KM_REC, KM_STATUS,
+#ifdef LWFB_CB_POLICY_WAIT
+  KM_WAITED,
+#endif
   KM_COUNT
 };
 #define LC(k) (*(const volatile double*)(cst + (k) * LWFB_LANES_BLOCK))
@@ -143,8 +157,9 @@ enum {
 #define LWFB_WARPS_PER_BLOCK (LWFB_LANES_BLOCK / 32)
 #endif
 #define LWFB_BLOCK_OF_WARP(w) ((w) / LWFB_WARPS_PER_BLOCK)
-// shared memory of a block (doubles): per-thread columns, log table, per-member slots, forcing rows of two days per member
-#define LWFB_SMEM_DOUBLES(mpb, lean) ((size_t)((lean) ? KC_COUNT_LEAN : KC_COUNT) * LWFB_LANES_BLOCK + 3 * LWFB_LOG_TAB_N + (size_t)(KM_COUNT + 2 * LWFB_F) * (mpb))
+// shared memory of a block (doubles): per-thread columns, log and exp tables, per-member slots, forcing rows of two days per member
+#define LWFB_SMEM_TABLES (3 * LWFB_LOG_TAB_N + 2 * LWFB_EXP_TAB_N)
+#define LWFB_SMEM_DOUBLES(mpb, lean) ((size_t)((lean) ? KC_COUNT_LEAN : KC_COUNT) * LWFB_LANES_BLOCK + LWFB_SMEM_TABLES + (size_t)(KM_COUNT + 2 * LWFB_F) * (mpb))
 
 // NX > 0: the layer count is the compile-time constant NX (index arithmetic and the broadcast loops resolve at compile
 // time); 0: run-time N <= NMAX.  LEAN: the ensemble uses none of the optional flow paths - no bypass flow (BYPAR), no
@@ -154,6 +169,7 @@ enum {
 template <int NMAX, int EQ, int NX = 0, bool LEAN = false>
 __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, const int64_t warp_g, double* cst,
                                            const double* ltab /* log table (shared-memory copy on the device) */,
+                                           const double* etab /* exp table (likewise) */,
                                            double* msm_block /* per-member slots + forcing rows of the block */) {
   const int N = NX > 0 ? NX : d.N;
   const int mpw = 32 / N;                            // members per warp
@@ -201,7 +217,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     const double THICK_dn = pv.Lp(LWFB_L_THICK, idn), STONEF_dn = pv.Lp(LWFB_L_STONEF, idn);
     SETC(KC_THSAT, THSAT); SETC(KC_THR, THR); SETC(KC_DTH, THSAT - THR); SETC(KC_SWATMAX, SWATMAX);
     SETC(KC_RSWATMAX, LWFB_RCP(SWATMAX)); SETC(KC_RDTH, LWFB_RCP(THSAT - THR));
-    SETC(KC_E1, -1.0 / MPAR); SETC(KC_E2, E2); SETC(KC_E3, NPAR / (NPAR - 1.0)); SETC(KC_E4, 1.0 - E2);
+    SETC(KC_E1, -1.0 / MPAR); SETC(KC_E2, E2); SETC(KC_E3, NPAR / (NPAR - 1.0));
     SETC(KC_TORT, pv.Lp(LWFB_L_TORT, i)); SETC(KC_CPSI, 9.81 * (-1.0 / pv.Lp(LWFB_L_ALPHA, i)));
     SETC(KC_KSAT, pv.Lp(LWFB_L_KSAT, i)); SETC(KC_PSIG, pv.Lp(LWFB_L_PSIG, i));
     SETC(KC_THICK, THICK); SETC(KC_OMS, 1 - STONEF); SETC(KC_INFRAC, pv.Lp(LWFB_L_INFRAC, i));
@@ -339,7 +355,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
   SETM(KM_ITER, resume ? CKP(LWFB_CK_ITER) : 0.0); SETM(KM_NACCEPT, resume ? CKP(LWFB_CK_NACCEPT) : 0.0);
   SETM(KM_NREJECT, resume ? CKP(LWFB_CK_NREJECT) : 0.0); SETM(KM_NF, resume ? CKP(LWFB_CK_NF) : 0.0);
   SETM(KM_REC, resume ? CKP(LWFB_CK_REC) : 1.0);
+#ifdef LWFB_CB_POLICY_WAIT
   SETM(KM_WAITED, 0.0);                              // step iterations spent waiting at the day boundary
+#endif
   bool reeval = false, at_boundary = true, cand_nan = (y != y);
   const int status_in = resume ? d.status[m] : LWFB_ST_OK;
   SETM(KM_STATUS, (double)status_in);
@@ -349,7 +367,12 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     cand_nan = CKL(LWFB_CKL_NAN) != 0.0;
   }
   bool by_budget = false;
+#ifdef LWFB_CB_POLICY_WAIT
   const int cb_wait = d.cb_wait > 0 ? d.cb_wait : LWFB_CB_WAIT;
+#else
+  const int cb_waste2 = d.cb_wait > 0 ? d.cb_wait : LWFB_CB_WASTE2;
+  int idle_acc = 0;                                  // member-passes idled at the day boundary since the last callback phase (block-uniform)
+#endif
   // block-uniform: every thread of a block makes the same passes
   long long passes_left = d.iter_budget > 0 ? (LWFB_BLOCK_OF_WARP(warp_g) < d.prio_blocks ? d.prio_budget : d.iter_budget) : -1;
 #ifdef LWFB_DEBUG_ITERS
@@ -373,7 +396,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 
   for (;;) {
     const int status = (int)LM(KM_STATUS);
+#ifdef LWFB_CB_POLICY_WAIT
     const int waited = (int)LM(KM_WAITED);
+#endif
     const bool active = ((status == LWFB_ST_OK) && (t < tend)) || probe;
     if (passes_left == 0) { by_budget = true; break; }   // quantum used up: checkpoint, the host regroups and relaunches
     if (passes_left > 0) passes_left--;
@@ -382,9 +407,19 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     if (!LWFB_VOTE_ANY(active && live && go_on)) break;
     const bool can_step = active && !at_boundary;
     const bool at_cb = active && at_boundary;        // waits for (or is about to get) its daily callback
+#ifdef LWFB_CB_POLICY_WAIT
     // (two votes: __syncthreads_or returns a truth value, not the OR of the arguments)
     const bool any_step = LWFB_VOTE_ANY(can_step && live);
     const bool any_overdue = LWFB_VOTE_ANY(at_cb && live && waited >= cb_wait);
+#else
+    // members of the block that step / that idle at their day boundary (one lane per member counts)
+    const int n_step = LWFB_VOTE_COUNT(can_step && live && top);
+    const int n_wait = LWFB_VOTE_COUNT(at_cb && live && top);
+    const bool any_step = n_step > 0;
+    idle_acc += n_wait;
+    const bool any_overdue = n_wait > 0 && 2 * idle_acc >= cb_waste2 * n_step;
+    if (!any_step || any_overdue) idle_acc = 0;
+#endif
 
     if (!any_step || any_overdue) {
       if (!__any_sync(LFULL, at_cb)) continue;       // nothing to do in this warp
@@ -416,7 +451,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
                     TRANIst_a, nRWU, cbst);
       __syncwarp(LFULL);                            // every lane has read the day-constant states before lane 0 overwrites them
       if (at_cb) {
+#ifdef LWFB_CB_POLICY_WAIT
         SETM(KM_WAITED, 0.0);
+#endif
         y = sw;
         SETK(KC_TRANI, TRANI_a[i]);
         {
@@ -462,7 +499,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 #ifdef LWFB_DEBUG_ITERS
     dbg_iters++;
 #endif
+#ifdef LWFB_CB_POLICY_WAIT
     if (at_cb) SETM(KM_WAITED, (double)(waited + 1));
+#endif
     // ============================== one attempted step (all lanes execute, only `do_step` lanes commit)
     // loopheader! (dt already holds the controller's proposal / the shrunk step after a rejection)
     double dt_s = LM(KM_DT);
@@ -551,7 +590,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       const double la = lwfb_log_main_t(a, ltab);
       const double TORT = LC(KC_TORT);
       double p1, p3, pT;                                      // a^(-1/m), a^(n/(n-1)), a^l: three chains interleaved
-      lwfb_exp3(LC(KC_E1) * la, LC(KC_E3) * la, TORT * la, &p1, &p3, &pT);
+      lwfb_exp3_t(LC(KC_E1) * la, LC(KC_E3) * la, TORT * la, &p1, &p3, &pT, etab);
       pT = (TORT == 0.0) ? 1.0 : pT;                          // x^0 = 1 also where exp(0 * log x) would not say so
       const double x1 = p1 - 1.0, x3 = 1.0 - p3;             // both are 0 at saturation (log -> -inf, power -> 0)
       double l1, l3;
@@ -561,7 +600,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         if (lwfb_log_isspecial(x3)) l3 = lwfb_log_cold(x3);
       }
       double e1, e3;
-      lwfb_exp2(E2 * l1, LC(KC_E4) * l3, &e1, &e3);
+      lwfb_exp2_t(E2 * l1, (1.0 - E2) * l3, &e1, &e3, etab);
       const double psim = LC(KC_CPSI) * e1;
       const double theta = w * DTH + THR;
       const double inner = 1.0 - e3;
@@ -600,7 +639,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       double V0;
       {
         const double THICK = LC(KC_THICK), DRAIN = LM(KM_DRAIN);
-        double kkmean = lwfb_exp(div_c(LC(KC_THICK_DN) * lk + THICK * lk_dn, LC(KC_TSUM), LC(KC_RTSUM)));
+        double kkmean = lwfb_exp_t(div_c(LC(KC_THICK_DN) * lk + THICK * lk_dn, LC(KC_TSUM), LC(KC_RTSUM)), etab);
         kkmean = jminc(jminc(kkmean, KSAT), LC(KC_KSAT_DN));   // (a NaN conductivity has made kkmean NaN already)
         const double dpsi = nodn ? 1.0 : (psit - psit_dn);     // no layer below: value unused, keep the divisions on their fast path
         const double grad = div_c(dpsi, LC(KC_THALF), LC(KC_RTHALF));
@@ -894,7 +933,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       const double th1 = w1 * DTH + THR;
       const double sumT = LM(KM_SUMT), sumT_V = LM(KM_SUMT_V);
       const double TRANI = LC(KC_TRANI), SLVP = LM(KM_SLVP);
-      const double tauth = lwfb_pow(th1, 7.0 / 3) * LC(KC_RTHS2);
+      const double tauth = lwfb_pow_t(th1, 7.0 / 3, ltab, etab) * LC(KC_RTHS2);
       const double aq = LM(KM_LAM) * fabs(VV * LWFB_RCP(1000.0));
       const double VN = bcast(VV, N - 1);
       const double VV_up = __shfl_up_sync(LFULL, VV, 1);
@@ -1007,15 +1046,17 @@ template <int NMAX, int EQ, int NX = 0, bool LEAN = false>
 __global__ void __launch_bounds__(LWFB_LANES_BLOCK, LWFB_LANES_MINBLOCKS) integrate_lanes(DevData d) {
   extern __shared__ double lanes_smem[];
   double* ltab = lanes_smem + (size_t)(LEAN ? KC_COUNT_LEAN : KC_COUNT) * LWFB_LANES_BLOCK;     // shared-memory copy of the log table
-  double* msm_block = ltab + 3 * LWFB_LOG_TAB_N;                       // per-member slots, then the staged forcing rows
+  double* etab = ltab + 3 * LWFB_LOG_TAB_N;                            // ... and of the exp table
+  double* msm_block = etab + 2 * LWFB_EXP_TAB_N;                       // per-member slots, then the staged forcing rows
   for (int k = threadIdx.x; k < 3 * LWFB_LOG_TAB_N; k += LWFB_LANES_BLOCK) ltab[k] = lwfb_log_tab_d[k];
+  for (int k = threadIdx.x; k < 2 * LWFB_EXP_TAB_N; k += LWFB_LANES_BLOCK) etab[k] = lwfb_exp_tab_d[k];
   __syncthreads();
   unsigned tid = threadIdx.x;
   asm volatile("" : "+r"(tid));     // opaque copy of %tid: the column address stays in a register (it would be re-derived
                                     // from %tid at every use otherwise) and is still known to point to shared memory
   const bool by_budget =
       lanes_body<NMAX, EQ, NX, LEAN>(d, threadIdx.x & 31, ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, lanes_smem + tid, ltab,
-                                     msm_block);
+                                     etab, msm_block);
   if (d.stop) {
     __syncthreads();
     if (threadIdx.x == 0) {

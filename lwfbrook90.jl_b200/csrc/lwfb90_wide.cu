@@ -12,7 +12,7 @@
 using namespace lwfb;
 
 // one warp per member, `wpb` warps per block; shared memory: wpb blocks of LWFB_WIDE_DOUBLES_PER_MEMBER(N) doubles
-__global__ void __launch_bounds__(256) integrate_wide(DevData d, int wpb) {
+__global__ void __launch_bounds__(256, 2) integrate_wide(DevData d, int wpb) {
   extern __shared__ double wide_smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m = (int64_t)blockIdx.x * wpb + w;

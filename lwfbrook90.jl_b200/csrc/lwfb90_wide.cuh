@@ -288,6 +288,13 @@ struct Wide {
   }
 };
 
+// the scalar core of the daily callback (lane 0): out of line, so that its registers do not burden the stepping loop
+static __device__ __noinline__ void wide_cb(const ParamView& pv, const double* __restrict__ frow, double t, double psim0,
+                                            const double* psiti, const double* kk, DayState& ds, double* TRANI, double* out4,
+                                            double* TRANIst, double& RWUst, int& cbst) {
+  cb_core<1>(pv, frow, t, psim0, psiti, kk, ds, TRANI, out4[0], out4[1], out4[2], out4[3], TRANIst, RWUst, cbst);
+}
+
 // The whole integration of member m by one warp.  `smem`: the member's block of LWFB_WIDE_DOUBLES_PER_MEMBER(N) doubles.
 __device__ __forceinline__ void wide_body(const DevData& d, const int lane, const int64_t m, double* smem) {
   Wide mb;
@@ -386,11 +393,10 @@ __device__ __forceinline__ void wide_body(const DevData& d, const int lane, cons
       if (i == 0) psim0 = psim;
     }
     __syncwarp(LFULL);
-    double nRNET = 0, nSMLT = 0, nSLVP = 0, nTA = 0;
+    double o4[4] = {0, 0, 0, 0};               // RNET, SMLT, SLVP, TA
     int cbst = LWFB_ST_OK;
     if (l0) {
-      cb_core<1>(mb.pv, forc + (int64_t)day * LWFB_F, t, psim0, mb.A(WA_PSITI), mb.A(WA_KK), ds, mb.A(WA_TRANI), nRNET, nSMLT,
-                 nSLVP, nTA, TRANIst, RWUst, cbst);
+      wide_cb(mb.pv, forc + (int64_t)day * LWFB_F, t, psim0, mb.A(WA_PSITI), mb.A(WA_KK), ds, mb.A(WA_TRANI), o4, TRANIst, RWUst, cbst);
       for (int q8 = 0; q8 < 8; q8++) y[N + 1 + q8] = 0.0;
       if (iso) {
         double dp[2];
@@ -399,9 +405,9 @@ __device__ __forceinline__ void wide_body(const DevData& d, const int lane, cons
       }
     }
     __syncwarp(LFULL);
-    mb.RS = __shfl_sync(LFULL, nRNET + nSMLT, 0);
-    mb.SLVP = __shfl_sync(LFULL, nSLVP, 0);
-    mb.TA = __shfl_sync(LFULL, nTA, 0);
+    mb.RS = __shfl_sync(LFULL, o4[0] + o4[1], 0);
+    mb.SLVP = __shfl_sync(LFULL, o4[2], 0);
+    mb.TA = __shfl_sync(LFULL, o4[3], 0);
     cbst = __shfl_sync(LFULL, cbst, 0);
     if (cbst != LWFB_ST_OK) status = cbst;
   };

@@ -34,7 +34,7 @@ def build(force: bool = False, wide: bool = False) -> str:
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
         fma = ["-mfma"] if "fma" in open("/proc/cpuinfo").read().split() else []
         subprocess.check_call(["g++", "-O2", "-g", "-std=c++17", "-fno-fast-math", "-ffp-contract=off", *fma, "-fPIC", "-shared",
-                               *(["-DLWFB_EMUL_WIDE=1"] if wide else []), "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"), "-lpthread"])
+                               *(["-DLWFB_EMUL_WIDE=1"] if wide else []), *os.environ.get("LWFB_EMUL_CFLAGS", "").split(), "-o", _SO, os.path.join(_HERE, "simt_emul.cpp"), "-lpthread"])
     return _SO
 
 

@@ -286,12 +286,12 @@ void lanes_entry(void* a, int tid) {             // tid = thread index within th
   const int lane = tid & 31;
   const int64_t warp_g = wa->block * wa->warps + (tid >> 5);
   bool b;
-  if (wa->lean && d.N == 5) b = lwfb::lanes_body<8, 2, 5, true>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
-  else if (wa->lean && d.N == 7) b = lwfb::lanes_body<8, 2, 7, true>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
-  else if (d.N == 3) b = lwfb::lanes_body<8, 3>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
-  else if (d.N < 8) b = lwfb::lanes_body<8, 2>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
-  else if (d.N == 8) b = lwfb::lanes_body<8, 1>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
-  else b = lwfb::lanes_body<32, 1>(d, lane, warp_g, cst, lwfb_log_tab_h, wa->msm);
+  if (wa->lean && d.N == 5) b = lwfb::lanes_body<8, 2, 5, true>(d, lane, warp_g, cst, lwfb_log_tab_h, lwfb_exp_tab_h, wa->msm);
+  else if (wa->lean && d.N == 7) b = lwfb::lanes_body<8, 2, 7, true>(d, lane, warp_g, cst, lwfb_log_tab_h, lwfb_exp_tab_h, wa->msm);
+  else if (d.N == 3) b = lwfb::lanes_body<8, 3>(d, lane, warp_g, cst, lwfb_log_tab_h, lwfb_exp_tab_h, wa->msm);
+  else if (d.N < 8) b = lwfb::lanes_body<8, 2>(d, lane, warp_g, cst, lwfb_log_tab_h, lwfb_exp_tab_h, wa->msm);
+  else if (d.N == 8) b = lwfb::lanes_body<8, 1>(d, lane, warp_g, cst, lwfb_log_tab_h, lwfb_exp_tab_h, wa->msm);
+  else b = lwfb::lanes_body<32, 1>(d, lane, warp_g, cst, lwfb_log_tab_h, lwfb_exp_tab_h, wa->msm);
   if (tid == 0) wa->by_budget = b;
 }
 #endif

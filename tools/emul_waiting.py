@@ -1,6 +1,7 @@
 """Lock-step waiting of the production kernel measured in the block emulator (CPU, no GPU needed): passes of the
 blocks against the members' own attempted steps, for one launch and for work quanta with regrouping.
-usage: emul_waiting.py [members] [days] [quantum,...] [warps_per_block]   (members: multiple of 48 for DAV2020-full)"""
+usage: emul_waiting.py [members] [days] [quantum,...] [warps_per_block] [config: dav|bea|isobea]
+(members: multiple of 48 for DAV2020-full, of 32 for the BEA2016 configurations)"""
 import os, sys, time, warnings
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "simt")):
@@ -14,7 +15,9 @@ from lwfbrook90.jl_b200 import ensemble as en
 M = int(sys.argv[1]) if len(sys.argv) > 1 else 768
 D = int(sys.argv[2]) if len(sys.argv) > 2 else 30
 quanta = [int(q) for q in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 128]
-sim = lw.setup(lw.loadSPAC(os.path.join(ROOT, "tests", "golden", "inputs", "DAV2020-full"), "DAV2020-full", simulate_isotopes=True))
+cfg = sys.argv[5] if len(sys.argv) > 5 else "dav"
+name, iso = {"dav": ("DAV2020-full", True), "bea": ("BEA2016-reset-FALSE", False), "isobea": ("isoBEA2016-reset-FALSE", True)}[cfg]
+sim = lw.setup(lw.loadSPAC(os.path.join(ROOT, "tests", "golden", "inputs", name + "-input" if "BEA" in name else name), name, simulate_isotopes=iso))
 ens = en.make_ensemble(sim, M)
 L = emul.lib(); L.lwfb_emul_stage_syncs.restype = C.c_long; L.lwfb_emul_votes.restype = C.c_long
 wpb = int(sys.argv[4]) if len(sys.argv) > 4 else 8       # lock-step group: warps that vote and barrier together
