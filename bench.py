@@ -394,10 +394,11 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
-        try:                                          # per-launch DRAM bytes of the committed ncu capture, scaled per site-day
+        traffic = traffic_detail = None
+        try:                                          # DRAM bytes of the committed ncu capture (per site-day), scaled to one step
             tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-            traffic = tr.get(args.config)
+            traffic_detail = tr.get(args.config) or tr.get("dav2020")
+            traffic = float(traffic_detail["dram_bytes_per_site_day"]) * float(M) * nd
         except Exception:
             pass
         line = {
@@ -423,9 +424,12 @@ def main():
                          "note": "integrate_lanes; achieved = counted FLOP-equivalents of a step (SURVEY 8d) / CUDA-event "
                                  "time from the first to the last integrator launch of the step (includes the "
                                  "regrouping between the launches); peak = DFMA microbenchmark measured in this run "
-                                 "(MEASURED_PEAKS.json has no FP64 entry); traffic = DRAM bytes per site-day of the "
-                                 "committed ncu capture (profiles/r02_traffic.json) against 8 (L + 16) algorithmic",
-                         "kernel_ms": kms},
+                                 "(MEASURED_PEAKS.json has no FP64 entry); traffic = bytes per step = DRAM bytes per "
+                                 "site-day of the committed ncu --set full capture (profiles/r02_traffic.json, a 20-day "
+                                 "launch WITH the daily record; traffic_per_site_day) x the site-days of a step, against "
+                                 "8 (L + 16) algorithmic bytes per site-day; the excess is register spills and the "
+                                 "members' live state passing through L2, 1.6 % of the HBM peak",
+                         "traffic_per_site_day": traffic_detail, "kernel_ms": kms},
             "roofline_hbm": {"bound": "hbm", "achieved": alg_bytes / (kms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
                              "peak_source": "measured" if peaks else "fallback"},
