@@ -93,14 +93,20 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
 #define LWFB_STAGE_SYNC() ((void)0)
 #endif
 // When does the block run its (block-uniform) daily callback phase?  A member that has reached its day boundary idles
-// until the phase runs; the phase itself costs every member of the block about 1.5 step passes, whether it takes part or
-// not.  Round 1 bounded the waiting per member (LWFB_CB_POLICY_WAIT: a phase runs when nobody can step or somebody has
-// waited LWFB_CB_WAIT = 32 passes): on BEA2016, where a day takes 25 steps for most members and thousands for a few, the
-// fast members then idle 32 passes per 25 steps.  Now the block weighs the two costs against each other (the ski-rental
-// rule): it counts the member-passes idled at the day boundary since the last phase and runs the phase as soon as they
-// reach LWFB_CB_WASTE2 / 2 passes for each member that still steps - i.e. when waiting has cost what the phase will cost
-// (tools/cb_policy_sim.py replays measured step counts: executed / needed member-passes 1.24 -> 1.10 on BEA2016, 1.35 ->
-// 1.20 on ungrouped DAV2020 members).  Results do not depend on the policy: a member that waits does not change state.
+// until the phase runs; the phase itself costs every member of the block a few step passes, whether it takes part or not,
+// and the members it releases leave the block's common rhythm.
+//  * One launch over the whole record (lwfb_run_async, small ensembles): nothing ever brings the members of a block back
+//    together, so the block waits for everybody - but at most LWFB_CB_WAIT = 32 passes (the oldest waiter's), which bounds
+//    the cost of one member's bad day for the others (round 1).  On DAV2020 this keeps a block at one phase per day.
+//  * Work quanta (lwfb_run): the members of a block are regrouped by progress every LWFB_QUANTUM passes, they reach the
+//    day boundary together and fall apart only when one of them has a bad day.  Here the block weighs the two costs
+//    against each other (ski-rental rule): it counts the member-passes idled at the day boundary since the last phase
+//    and runs the phase as soon as they reach LWFB_CB_WASTE2 / 2 passes for each member that still steps.  Measured on
+//    the B200 against the 32-pass bound (profiles/r02_notes.md): DAV2020 127872 x 365 d 2827 -> 2768 ms, isoBEA2016
+//    100000 x 366 d 17.0 -> 16.2 s, BEA2016 10000 6.39 -> 6.26 s; in ONE launch of unsorted DAV2020 members it loses
+//    (74 -> 91 ms on the profile workload), hence the two modes.  Emulator (tools/emul_waiting.py, BEA2016 in quanta):
+//    executed / needed member-steps 1.242 -> 1.124.
+// Results do not depend on any of this: a member that waits does not change state.
 #ifndef LWFB_CB_WAIT
 #define LWFB_CB_WAIT 32
 #endif
@@ -370,8 +376,11 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 #ifdef LWFB_CB_POLICY_WAIT
   const int cb_wait = d.cb_wait > 0 ? d.cb_wait : LWFB_CB_WAIT;
 #else
+  const bool waste_rule = d.iter_budget > 0;         // work quanta: weigh idling against the phase; one launch: bounded waiting
   const int cb_waste2 = d.cb_wait > 0 ? d.cb_wait : LWFB_CB_WASTE2;
+  const int cb_wait = (!waste_rule && d.cb_wait > 0) ? d.cb_wait : LWFB_CB_WAIT;
   int idle_acc = 0;                                  // member-passes idled at the day boundary since the last callback phase (block-uniform)
+  int oldest_wait = 0;                               // passes the longest-waiting member has idled (block-uniform: a phase releases all)
 #endif
   // block-uniform: every thread of a block makes the same passes
   long long passes_left = d.iter_budget > 0 ? (LWFB_BLOCK_OF_WARP(warp_g) < d.prio_blocks ? d.prio_budget : d.iter_budget) : -1;
@@ -417,8 +426,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     const int n_wait = LWFB_VOTE_COUNT(at_cb && live && top);
     const bool any_step = n_step > 0;
     idle_acc += n_wait;
-    const bool any_overdue = n_wait > 0 && 2 * idle_acc >= cb_waste2 * n_step;
-    if (!any_step || any_overdue) idle_acc = 0;
+    oldest_wait = n_wait > 0 ? oldest_wait + 1 : 0;
+    const bool any_overdue = n_wait > 0 && (oldest_wait > cb_wait || (waste_rule && 2 * idle_acc >= cb_waste2 * n_step));
+    if (!any_step || any_overdue) { idle_acc = 0; oldest_wait = 0; }
 #endif
 
     if (!any_step || any_overdue) {
