@@ -487,8 +487,9 @@ static int sort_placement(lwfb_handle* h, bool by_cost, cudaStream_t st, int64_t
 // members that share a block (and wait for each other at every step) have similar step counts
 static int sort_members_by_cost(lwfb_handle* h, cudaStream_t st) { return sort_placement(h, true, st, nullptr); }
 
-// one launch of the integrator over the slots [0, d.n_slots)
-static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) {
+// one launch of the integrator over the slots [0, d.n_slots); latency: the 1-block-per-SM (255 register) build of the lane
+// kernel, for launches that do not fill the device
+static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st, bool latency = false) {
   if (use_lanes(h)) {
     // production path: one lane per soil layer, 32/N members per warp; per-thread constants in shared memory
     const int mpw = 32 / d.N;
@@ -505,24 +506,31 @@ static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st) 
     // L1, which the register spills live in; left to its own heuristics the driver has been seen to pick a carve-out
     // that holds ONE block, halving the occupancy)
     const size_t per_block = smem + 1024, sm_total = 228 * 1024;
-    const size_t n_res = per_block * LWFB_LANES_MINBLOCKS <= sm_total ? LWFB_LANES_MINBLOCKS : 1;
+    const size_t want_res = latency ? 1 : LWFB_LANES_MINBLOCKS;
+    const size_t n_res = per_block * want_res <= sm_total ? want_res : 1;
     const int carve_pct = (int)((100 * per_block * n_res + sm_total - 1) / sm_total);
-#define LWFB_LAUNCH(...)                                                                                        \
+#define LWFB_LAUNCH1(...)                                                                                       \
     do {                                                                                                       \
       if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_lanes<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
       cudaFuncSetAttribute(integrate_lanes<__VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_pct > 100 ? 100 : carve_pct); \
       integrate_lanes<__VA_ARGS__><<<lgrid, LWFB_LANES_BLOCK, smem, st>>>(d);                                    \
+    } while (0)
+#define LWFB_LAUNCH(NMAX_, EQ_, NX_, LEAN_)                                                                     \
+    do {                                                                                                       \
+      if (latency) LWFB_LAUNCH1(NMAX_, EQ_, NX_, LEAN_, 1);                                                     \
+      else LWFB_LAUNCH1(NMAX_, EQ_, NX_, LEAN_, LWFB_LANES_MINBLOCKS);                                          \
     } while (0)
 #ifndef LWFB_FIXED_N
 #define LWFB_FIXED_N 1           // experiment knob: 0 = lean instantiations with a run-time layer count
 #endif
     if (lean && d.N == 5) LWFB_LAUNCH(8, 2, LWFB_FIXED_N ? 5 : 0, true);
     else if (lean && d.N == 7) LWFB_LAUNCH(8, 2, LWFB_FIXED_N ? 7 : 0, true);
-    else if (d.N == 3) LWFB_LAUNCH(8, 3);
-    else if (d.N < 8) LWFB_LAUNCH(8, 2);
-    else if (d.N == 8) LWFB_LAUNCH(8, 1);
-    else LWFB_LAUNCH(32, 1);
+    else if (d.N == 3) LWFB_LAUNCH(8, 3, 0, false);
+    else if (d.N < 8) LWFB_LAUNCH(8, 2, 0, false);
+    else if (d.N == 8) LWFB_LAUNCH(8, 1, 0, false);
+    else LWFB_LAUNCH(32, 1, 0, false);
 #undef LWFB_LAUNCH
+#undef LWFB_LAUNCH1
   } else if (use_wide(h)) {
     cudaError_t e = launch_wide_integrate(d, h->o.device, st);   // warp-per-member, 32 < N <= LWFB_MAX_LAYERS
     if (e != cudaSuccess) { h->err = std::string("wide kernel: ") + cudaGetErrorString(e); return LWFB_ERR_CUDA; }
@@ -597,13 +605,15 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   if (const char* e = getenv("LWFB_SPREAD")) spread = atoi(e) != 0;
   int thin_front = 0;                                 // experimental: warps with members per FRONT block of a full device (0: all)
   if (const char* e = getenv("LWFB_THIN_FRONT")) thin_front = atoi(e);
+  bool latency_kernel = LWFB_LANES_MINBLOCKS > 1;     // what no longer fills ONE block per SM runs in the 255-register build
+  if (const char* e = getenv("LWFB_LATENCY_KERNEL")) latency_kernel = latency_kernel && atoi(e) != 0;
   int n_sm = 148;
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->o.device);
-  const int64_t R = (int64_t)n_sm * LWFB_LANES_MINBLOCKS;                       // resident blocks
+  const int64_t R_full = (int64_t)n_sm * LWFB_LANES_MINBLOCKS;                  // resident blocks of the throughput build
   const int64_t mpw = 32 / (h->o.n_layers > 0 && h->o.n_layers <= 32 ? h->o.n_layers : 32);   // members per warp
   const int64_t wpb = LWFB_LANES_BLOCK / 32;
   const int64_t mpb = wpb * mpw;                                                 // members per block
-  const bool enough = h->placement == 2 || (h->M + mpb - 1) / mpb >= (int64_t)min_waves * R;
+  const bool enough = h->placement == 2 || (h->M + mpb - 1) / mpb >= (int64_t)min_waves * R_full;
   const bool quanta = use_lanes(h) && h->placement >= 1 && quantum > 0 && enough;
   if (!quanta) {
     int rc = lwfb_run_async(h, cuda_stream);
@@ -637,6 +647,8 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
     d.resume = launch > 0;
     d.n_slots = n_left;
     const int64_t nb = (n_left + mpb - 1) / mpb;
+    const bool latency = latency_kernel && nb <= (int64_t)n_sm;
+    const int64_t R = latency ? (int64_t)n_sm : R_full;                             // slots of this launch
     if (nb <= R) {
       // every block has a slot: longer quanta the emptier the device (regrouping only thins the blocks out)
       int64_t f = R / nb;
@@ -699,7 +711,7 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
       cudaEventRecord(r.e0, st);
       trace.push_back(r);
     }
-    int rc = launch_integrator(h, d, st);
+    int rc = launch_integrator(h, d, st, latency);
     if (rc) return rc;
     if (trace_path) cudaEventRecord(trace.back().e1, st);
     if ((rc = regroup_by_progress(h, st, &n_left))) return rc;

@@ -111,7 +111,7 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
 #define LWFB_CB_WAIT 32
 #endif
 #ifndef LWFB_CB_WASTE2
-#define LWFB_CB_WASTE2 3
+#define LWFB_CB_WASTE2 5
 #endif
 
 // per-thread constant column (shared memory): element k of this thread is cst[k * LWFB_LANES_BLOCK]
@@ -448,30 +448,31 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       const double inner = 1.0 - lwfb_pow(1.0 - p3, 1.0 - E2);
       const double kkv = LC(KC_KSAT) * lwfb_pow_from_log(a, la, LC(KC_TORT)) * (inner * inner);
       const double psit = psim + LC(KC_PSIG);
-      double psiti_a[NMAX], kk_a[NMAX], TRANI_a[NMAX], TRANIst_a[NMAX];
+      // The scalar core of the callback (canopy, snow, interception, uptake by layer: ~10^4 operations that do not
+      // parallelise over layers) runs in ONE lane per member - the top lane of a member that is at its boundary - while the
+      // other lanes of the warp idle; it posts what the other lanes need in shared memory.  (Rounds 1 / 2 ran it
+      // redundantly in every lane: the same time, but N copies of its thread-local work arrays per member and day,
+      // 5 kB per DAV2020 site-day of local-memory stores that L2 evicted to DRAM - 7x the algorithmic write traffic.)
+      double psiti_a[NMAX], kk_a[NMAX];
       for (int j = 0; j < N; j++) { psiti_a[j] = bcast(psit, j); kk_a[j] = bcast(kkv, j); }
       const double psim0 = bcast(psim, 0);
       const int day = (int)floor(t + 0.5);
-      double nRNET, nSMLT, nSLVP, nTA, nRWU;
-      int cbst = LWFB_ST_OK;
-      DayState nds;
-      nds.INTS = FIN(ix.INTS); nds.INTR = FIN(ix.INTR); nds.SNOW = FIN(ix.SNOW); nds.CC = FIN(ix.CC); nds.SNOWLQ = FIN(ix.SNOWLQ);
       staged_wait();                                // row `day` was requested at the previous callback (or at the start)
-      cb_core<NMAX>(pv, frow2 + (day & 1) * LWFB_F, t, psim0, psiti_a, kk_a, nds, TRANI_a, nRNET, nSMLT, nSLVP, nTA,
-                    TRANIst_a, nRWU, cbst);
-      __syncwarp(LFULL);                            // every lane has read the day-constant states before lane 0 overwrites them
-      if (at_cb) {
-#ifdef LWFB_CB_POLICY_WAIT
-        SETM(KM_WAITED, 0.0);
-#endif
-        y = sw;
-        SETK(KC_TRANI, TRANI_a[i]);
-        {
-          double sT = 0;                         // sum of the layer uptakes and its ratio to the xylem volume (isotope step)
-          for (int j = 0; j < N; j++) sT += TRANI_a[j];
-          SETM(KM_SUMT, sT);
-          SETM(KM_SUMT_V, sT / LM(KM_VXYLEM));
+      if (at_cb && top && lane_valid) {
+        double TRANI_a[NMAX], TRANIst_a[NMAX];
+        double nRNET, nSMLT, nSLVP, nTA, nRWU;
+        int cbst = LWFB_ST_OK;
+        DayState nds;
+        nds.INTS = FIN(ix.INTS); nds.INTR = FIN(ix.INTR); nds.SNOW = FIN(ix.SNOW); nds.CC = FIN(ix.CC); nds.SNOWLQ = FIN(ix.SNOWLQ);
+        cb_core<NMAX>(pv, frow2 + (day & 1) * LWFB_F, t, psim0, psiti_a, kk_a, nds, TRANI_a, nRNET, nSMLT, nSLVP, nTA,
+                      TRANIst_a, nRWU, cbst);
+        double sT = 0;                           // sum of the layer uptakes and its ratio to the xylem volume (isotope step)
+        for (int j = 0; j < N; j++) {
+          (cst + j)[KC_TRANI * LWFB_LANES_BLOCK] = TRANI_a[j];      // the frozen uptake of layer j, into lane j's column
+          sT += TRANI_a[j];
         }
+        SETM(KM_SUMT, sT);
+        SETM(KM_SUMT_V, sT / LM(KM_VXYLEM));
         SETM(KM_RS, nRNET + nSMLT); SETM(KM_SLVP, nSLVP);
         {
           // molecular diffusivities of the day (soil temperature = daily mean air temperature)
@@ -481,22 +482,27 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
           SETM(KM_D0_2H, 0.98331 * 1e-9 * ee * 3600 * 24);
         }
         if (cbst != LWFB_ST_OK) SETM(KM_STATUS, (double)cbst);
-#pragma unroll
-        for (int j = 0; j < EQ; j++) Q[j] = 0.0;
         if (live) {
-          FIN(ix.TRANI + i) = TRANIst_a[i];
-          if (top) {
-            FIN(ix.INTS) = nds.INTS; FIN(ix.INTR) = nds.INTR; FIN(ix.SNOW) = nds.SNOW; FIN(ix.CC) = nds.CC;
-            FIN(ix.SNOWLQ) = nds.SNOWLQ; FIN(ix.RWU) = nRWU;
-            for (int a2 = 0; a2 < LWFB_A_STORAGESWAT; a2++) FIN(ix.ACC + a2) = nds.acc[a2];
-            if (iso) {
-              double dp[2];
-              prec_delta(t, dp);
+          for (int j = 0; j < N; j++) FIN(ix.TRANI + j) = TRANIst_a[j];
+          FIN(ix.INTS) = nds.INTS; FIN(ix.INTR) = nds.INTR; FIN(ix.SNOW) = nds.SNOW; FIN(ix.CC) = nds.CC;
+          FIN(ix.SNOWLQ) = nds.SNOWLQ; FIN(ix.RWU) = nRWU;
+          for (int a2 = 0; a2 < LWFB_A_STORAGESWAT; a2++) FIN(ix.ACC + a2) = nds.acc[a2];
+          if (iso) {
+            double dp[2];
+            prec_delta(t, dp);
 #pragma unroll
-              for (int s = 0; s < 2; s++) { FIN(ix.INTS + 1 + s) = dp[s]; FIN(ix.INTR + 1 + s) = dp[s]; FIN(ix.SNOW + 1 + s) = dp[s]; }
-            }
+            for (int s = 0; s < 2; s++) { FIN(ix.INTS + 1 + s) = dp[s]; FIN(ix.INTR + 1 + s) = dp[s]; FIN(ix.SNOW + 1 + s) = dp[s]; }
           }
         }
+      }
+      __syncwarp(LFULL);
+      if (at_cb) {
+#ifdef LWFB_CB_POLICY_WAIT
+        SETM(KM_WAITED, 0.0);
+#endif
+        y = sw;
+#pragma unroll
+        for (int j = 0; j < EQ; j++) Q[j] = 0.0;
         reeval = true;
         at_boundary = false;
         SETM(KM_TSTOP, fmin(tstop0 + 1.0, tend));
@@ -1052,8 +1058,13 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 }
 
 #ifdef __CUDACC__
-template <int NMAX, int EQ, int NX = 0, bool LEAN = false>
-__global__ void __launch_bounds__(LWFB_LANES_BLOCK, LWFB_LANES_MINBLOCKS) integrate_lanes(DevData d) {
+// MINB = resident blocks per SM the register allocation is sized for.  LWFB_LANES_MINBLOCKS (2: 128 registers, 16 warps
+// per SM) is the throughput build.  MINB = 1 (255 registers, hardly any spills) is the LATENCY build for what is left
+// when the unfinished members no longer fill the device - the critical path of the slowest members, where a pass of a
+// block is a chain of dependent instructions and every spill reload is waited for: BEA2016 10000 members 6.36 -> 5.23 s
+// (profiles/r02_notes.md), while a full device runs 26 % slower with it.
+template <int NMAX, int EQ, int NX = 0, bool LEAN = false, int MINB = LWFB_LANES_MINBLOCKS>
+__global__ void __launch_bounds__(LWFB_LANES_BLOCK, MINB) integrate_lanes(DevData d) {
   extern __shared__ double lanes_smem[];
   double* ltab = lanes_smem + (size_t)(LEAN ? KC_COUNT_LEAN : KC_COUNT) * LWFB_LANES_BLOCK;     // shared-memory copy of the log table
   double* etab = ltab + 3 * LWFB_LOG_TAB_N;                            // ... and of the exp table
