@@ -560,7 +560,16 @@ extern "C" int lwfb_run_async(lwfb_handle* h, void* cuda_stream) {
   CK(cudaEventRecord(h->ev0, st));
   if (d.n_obs_layers > 0) CK(cudaMemsetAsync(h->d_sacc, 0, (size_t)h->M * 2 * LWFB_SA * sizeof(double), st));
   h->sums_valid = d.n_obs_layers > 0;
-  int rc = launch_integrator(h, d, st);
+  // an ensemble that does not fill one block per SM is a latency problem: the 255-register build (see integrate_lanes)
+  bool latency = false;
+  if (lanes && LWFB_LANES_MINBLOCKS > 1) {
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->o.device);
+    const int64_t members_per_block = (int64_t)(LWFB_LANES_BLOCK / 32) * (32 / h->o.n_layers);
+    latency = (h->M + members_per_block - 1) / members_per_block <= (int64_t)n_sm;
+    if (const char* e = getenv("LWFB_LATENCY_KERNEL")) latency = latency && atoi(e) != 0;
+  }
+  int rc = launch_integrator(h, d, st, latency);
   if (rc) return rc;
   CK(cudaEventRecord(h->ev1, st));
   h->ran = true;

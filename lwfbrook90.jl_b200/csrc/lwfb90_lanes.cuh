@@ -471,6 +471,9 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
           (cst + j)[KC_TRANI * LWFB_LANES_BLOCK] = TRANI_a[j];      // the frozen uptake of layer j, into lane j's column
           sT += TRANI_a[j];
         }
+        // the surplus lanes of the warp shadow layer 0 of its first member: they must see a finite uptake as well, or their
+        // (never committed) state turns NaN and drags the whole warp through the cold paths of exp / log at every call
+        if (g == 0) for (int l = mpw * N; l < 32; l++) (cst + l)[KC_TRANI * LWFB_LANES_BLOCK] = TRANI_a[0];
         SETM(KM_SUMT, sT);
         SETM(KM_SUMT_V, sT / LM(KM_VXYLEM));
         SETM(KM_RS, nRNET + nSMLT); SETM(KM_SLVP, nSLVP);

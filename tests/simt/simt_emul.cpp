@@ -330,6 +330,8 @@ void* worker(void* p) {
 // profiling aid: stage barriers executed by thread 0 of all blocks since the last call (6 or 7 per step pass of a block)
 extern "C" long lwfb_emul_stage_syncs() { return simt::g_stage_syncs.exchange(0); }
 extern "C" long lwfb_emul_votes() { return simt::g_votes.exchange(0); }
+// calls of the cold paths of exp / log (per lane) since the last call
+extern "C" long lwfb_emul_cold_calls() { return __atomic_exchange_n(&lwfb_cold_calls, 0, __ATOMIC_RELAXED); }
 
 // observations scored during the following runs (the emulator's lwfb_set_observations) and the sums of the last run
 static std::vector<int32_t> g_obs_of_rec, g_obs_layer;

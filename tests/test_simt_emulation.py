@@ -43,6 +43,22 @@ def test_lane_kernel_dav2020_isotopes(dav_full):
     check(en.make_ensemble(dav_full, 16), 8, emul.LANES)
 
 
+def test_lane_kernel_stays_on_the_main_paths_of_exp_and_log(dav_full):
+    """No lane may compute with NaN garbage: results would not show it (such lanes never commit), but every exp / log of
+    the warp would go through the out-of-line cold paths (round 2: the surplus lanes of a warp once did, after the
+    callback core moved to one lane per member; 2x the run time on the GPU).  Healthy DAV2020 members take the cold path
+    only for saturated or dry layers: far less than once per RHS evaluation and lane."""
+    import ctypes as C
+    e = en.make_ensemble(dav_full, 12)
+    L = emul.lib()
+    L.lwfb_emul_cold_calls.restype = C.c_long
+    L.lwfb_emul_cold_calls()
+    _, st, cnt = emul.run(emul.LANES, e.N, e.iso, e.t0_day, 6, e.forcing, e.site_of_member, e.scal, e.lay, e.u0)
+    cold = L.lwfb_emul_cold_calls()
+    assert (st == 0).all()
+    assert cold < 0.01 * cnt[:, 2].sum() * e.N, f"{cold} cold-path calls for {cnt[:, 2].sum()} RHS evaluations"
+
+
 def test_lane_kernel_bea_no_isotopes(bea):
     """N = 7 (4 members per warp, 4 surplus lanes), no isotopes."""
     check(en.make_ensemble(bea, 6), 10, emul.LANES)
