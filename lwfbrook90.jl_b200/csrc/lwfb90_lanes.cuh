@@ -615,8 +615,8 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       double l1, l3;
       lwfb_log_main2_t(x1, x3, &l1, &l3, ltab);               // two interleaved chains, then the rare fix-ups
       if (lwfb_log_isspecial(x1) | lwfb_log_isspecial(x3)) {                // one test for both (rare: saturation)
-        if (lwfb_log_isspecial(x1)) l1 = lwfb_log_cold(x1);
-        if (lwfb_log_isspecial(x3)) l3 = lwfb_log_cold(x3);
+        if (lwfb_log_isspecial(x1)) l1 = lwfb_log_rare(x1);
+        if (lwfb_log_isspecial(x3)) l3 = lwfb_log_rare(x3);
       }
       double e1, e3;
       lwfb_exp2_t(E2 * l1, (1.0 - E2) * l3, &e1, &e3, etab);
@@ -626,7 +626,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       const double KSAT = LC(KC_KSAT);
       const double kkv = KSAT * pT * (inner * inner);
       double lk = lwfb_log_main_t(kkv, ltab);
-      if (lwfb_log_isspecial(kkv)) lk = lwfb_log_cold(kkv);
+      if (lwfb_log_isspecial(kkv)) lk = lwfb_log_rare(kkv);
       const double psit = psim + LC(KC_PSIG);
       double BYFRAC = 0;
       if (any_bypar) {
