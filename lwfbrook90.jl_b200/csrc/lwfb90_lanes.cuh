@@ -706,47 +706,57 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       }
       // INFLOW
       const double INFRAC = LC(KC_INFRAC);
-      double BYFLI = LEAN ? 0.0 : SLFL * INFRAC * BYFRAC;
-      INFLI = LEAN ? SLFL * INFRAC : SLFL * INFRAC * (1.0 - BYFRAC);
+      const double BYFLI0 = LEAN ? 0.0 : SLFL * INFRAC * BYFRAC;
+      const double INFLI0 = LEAN ? SLFL * INFRAC : SLFL * INFRAC * (1.0 - BYFRAC);
+      double BYFLI = BYFLI0;
+      INFLI = INFLI0;
       VV = V0;
       {
+        // INFLOW's oversaturation limiter.  The reference walks the layers bottom-up: layer j, given its own (posterior)
+        // outflow, may cut the flux it receives from layer j-1, which changes what layer j-1 can take, and so on.  Here
+        // every layer takes its decision at once from its current outflow, the cut fluxes move up one lane, and the sweep
+        // repeats until nothing changes: the bottom outflow is fixed, so after k sweeps the k lowest layers are final,
+        // every final decision is the reference's expression of the reference's inputs (same bits), and the number of
+        // sweeps is the longest cascade + 1 instead of N.  No layer limits (DAV2020: always) -> no sweep at all; BEA2016
+        // keeps one layer saturated and limits in 79 % of the evaluations, with cascades of one layer in 98 % of them
+        // (block emulator): 2 sweeps instead of 7 chain steps.
         const double room = (SWATMAX - sw) / DTI;
-        // no layer limits (the common case) <=> every layer passes its test with the unmodified fluxes
         const double TRANI = LC(KC_TRANI), SLVP = LM(KM_SLVP);
         double MAXIN = room + V0 + DSFLI + TRANI;
         if (top) MAXIN = MAXIN + SLVP;
-        const bool limited = top ? (INFLI > MAXIN) : (V0_up + INFLI > MAXIN);
-        if (__any_sync(LFULL, limited)) {
-          // bottom-up chain: layer j fixes the posterior flux from layer j-1
-          for (int j = N - 1; j >= 0; j--) {
+        const bool limited = top ? (INFLI0 > MAXIN) : (V0_up + INFLI0 > MAXIN);
+        if (__any_sync(LFULL, limited && lane_valid)) {
+          for (int sweep = 0; sweep < N; sweep++) {
             double MX = room + VV + DSFLI + TRANI;
             double VVup = V0_up;
-            if (j == 0) {
+            INFLI = INFLI0; BYFLI = BYFLI0;
+            if (top) {
               MX = MX + SLVP;
-              if (i == 0 && INFLI > MX) {
-                const double too = INFLI - MX;
-                INFLI = INFLI - too;
-                BYFLI = BYFLI + too;
+              if (INFLI0 > MX) {
+                const double too = INFLI0 - MX;
+                INFLI = INFLI0 - too;
+                BYFLI = BYFLI0 + too;
               }
-            } else {
-              if (i == j && V0_up + INFLI > MX) {
-                if (BYFRAC > 0) {
-                  if (V0_up < MX) {
-                    const double too = INFLI + V0_up - MX;
-                    INFLI = INFLI - too;
-                    BYFLI = BYFLI + too;
-                  } else {
-                    VVup = MX;
-                    BYFLI = BYFLI + INFLI;
-                    INFLI = 0;
-                  }
+            } else if (V0_up + INFLI0 > MX) {
+              if (BYFRAC > 0) {
+                if (V0_up < MX) {
+                  const double too = INFLI0 + V0_up - MX;
+                  INFLI = INFLI0 - too;
+                  BYFLI = BYFLI0 + too;
                 } else {
-                  VVup = MX - INFLI;
+                  VVup = MX;
+                  BYFLI = BYFLI0 + INFLI0;
+                  INFLI = 0;
                 }
+              } else {
+                VVup = MX - INFLI0;
               }
             }
-            const double recv = __shfl_down_sync(LFULL, VVup, 1);   // lane j-1 receives its posterior outflow
-            if (j >= 1 && i == j - 1) VV = recv;
+            const double recv = __shfl_down_sync(LFULL, VVup, 1);   // every lane receives its posterior outflow from below
+            const double VVnew = bot ? V0 : recv;
+            const bool changed = lane_valid && (__double_as_longlong(VVnew) != __double_as_longlong(VV));
+            VV = VVnew;
+            if (!__any_sync(LFULL, changed)) break;
           }
         }
       }

@@ -127,13 +127,19 @@ def test_dav2020_full_single_member_vs_golden_G1(lw):
 
 
 @pytest.mark.parametrize("which,M,nd", [("dav_full", 96, None), ("bea", 48, None), ("isobea", 48, None)])
-def test_ensemble_bit_identical_to_oracle(which, M, nd, request):
+def test_ensemble_bit_identical_to_oracle(which, M, nd, request, monkeypatch):
+    """Whole records of the three BASELINE site definitions, through both builds of the lane kernel: an ensemble that does
+    not fill one block per SM runs in the latency build (one block per SM, 255 registers), LWFB_LATENCY_KERNEL=0 forces
+    the throughput build (two blocks per SM, 128 registers) that large ensembles run in."""
     sim = request.getfixturevalue(which)
     ens = en.make_ensemble(sim, M)
     h, sub, nd = gpu_run(ens, nd)
     gpu = assert_bit_identical(h, sub, nd)
     # get_final returns the last record
     assert np.array_equal(h.get_final(), gpu[:, -1], equal_nan=True)
+    monkeypatch.setenv("LWFB_LATENCY_KERNEL", "0")
+    h.run()
+    assert np.array_equal(h.get_daily(), gpu, equal_nan=True)
     h.close()
 
 
