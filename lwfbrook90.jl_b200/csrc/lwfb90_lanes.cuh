@@ -88,9 +88,7 @@ __device__ constexpr int lAccPos[8] = {LWFB_A_FLOW, LWFB_A_SEEP, LWFB_A_SRFL, LW
 #define LWFB_STAGE_SYNC() __syncthreads()
 #endif
 #else
-#define LWFB_VOTE_ANY(p) __any_sync(LFULL, (p))
-#define LWFB_VOTE_COUNT(p) __popc(__ballot_sync(LFULL, (p)))
-#define LWFB_STAGE_SYNC() ((void)0)
+#error "LWFB_LANES_FREE_RUNNING: the daily callback is a block-level phase (one member per lane over the whole block); the free-running experiment of rounds 1 / 2 is kept as kernel text under profiles/"
 #endif
 // When does the block run its (block-uniform) daily callback phase?  A member that has reached its day boundary idles
 // until the phase runs; the phase itself costs every member of the block a few step passes, whether it takes part or not,
@@ -432,73 +430,104 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 #endif
 
     if (!any_step || any_overdue) {
-      if (!__any_sync(LFULL, at_cb)) continue;       // nothing to do in this warp
-      // ============================== warp-synchronous daily callback at t = tstop
-      // soil state of the own layer (SWCHEK clamps the state itself), then all layers gathered
+      // ============================== block-synchronous daily callback at t = tstop
+      // (1) every lane: soil state of its own layer (SWCHEK clamps the state itself), posted in shared memory
       const double SWATMAX = LC(KC_SWATMAX), E2 = LC(KC_E2);
       const double tstop0 = LM(KM_TSTOP);
       double sw = y;
       if (sw <= 0.0) sw = 0.0; else if (sw > SWATMAX) sw = SWATMAX;
-      const double w = jminc(div_c(div_c(LC(KC_THSAT) * sw, SWATMAX, LC(KC_RSWATMAX)) - LC(KC_THR), LC(KC_DTH), LC(KC_RDTH)), 1.0);
-      const double a = jmaxc(w, 1.e-6);
-      const double la = lwfb_log(a);
-      const double p1 = lwfb_pow_from_log(a, la, LC(KC_E1));
-      const double psim = LC(KC_CPSI) * lwfb_pow(p1 - 1.0, E2);
-      const double p3 = lwfb_pow_from_log(a, la, LC(KC_E3));
-      const double inner = 1.0 - lwfb_pow(1.0 - p3, 1.0 - E2);
-      const double kkv = LC(KC_KSAT) * lwfb_pow_from_log(a, la, LC(KC_TORT)) * (inner * inner);
-      const double psit = psim + LC(KC_PSIG);
-      // The scalar core of the callback (canopy, snow, interception, uptake by layer: ~10^4 operations that do not
-      // parallelise over layers) runs in ONE lane per member - the top lane of a member that is at its boundary - while the
-      // other lanes of the warp idle; it posts what the other lanes need in shared memory.  (Rounds 1 / 2 ran it
-      // redundantly in every lane: the same time, but N copies of its thread-local work arrays per member and day,
-      // 5 kB per DAV2020 site-day of local-memory stores that L2 evicted to DRAM - 7x the algorithmic write traffic.)
-      double psiti_a[NMAX], kk_a[NMAX];
-      for (int j = 0; j < N; j++) { psiti_a[j] = bcast(psit, j); kk_a[j] = bcast(kkv, j); }
-      const double psim0 = bcast(psim, 0);
       const int day = (int)floor(t + 0.5);
-      staged_wait();                                // row `day` was requested at the previous callback (or at the start)
-      if (at_cb && top && lane_valid) {
-        double TRANI_a[NMAX], TRANIst_a[NMAX];
-        double nRNET, nSMLT, nSLVP, nTA, nRWU;
-        int cbst = LWFB_ST_OK;
-        DayState nds;
-        nds.INTS = FIN(ix.INTS); nds.INTR = FIN(ix.INTR); nds.SNOW = FIN(ix.SNOW); nds.CC = FIN(ix.CC); nds.SNOWLQ = FIN(ix.SNOWLQ);
-        cb_core<NMAX>(pv, frow2 + (day & 1) * LWFB_F, t, psim0, psiti_a, kk_a, nds, TRANI_a, nRNET, nSMLT, nSLVP, nTA,
-                      TRANIst_a, nRWU, cbst);
-        double sT = 0;                           // sum of the layer uptakes and its ratio to the xylem volume (isotope step)
-        for (int j = 0; j < N; j++) {
-          (cst + j)[KC_TRANI * LWFB_LANES_BLOCK] = TRANI_a[j];      // the frozen uptake of layer j, into lane j's column
-          sT += TRANI_a[j];
+      if (__any_sync(LFULL, at_cb)) {
+        const double w = jminc(div_c(div_c(LC(KC_THSAT) * sw, SWATMAX, LC(KC_RSWATMAX)) - LC(KC_THR), LC(KC_DTH), LC(KC_RDTH)), 1.0);
+        const double a = jmaxc(w, 1.e-6);
+        const double la = lwfb_log(a);
+        const double p1 = lwfb_pow_from_log(a, la, LC(KC_E1));
+        const double psim = LC(KC_CPSI) * lwfb_pow(p1 - 1.0, E2);
+        const double p3 = lwfb_pow_from_log(a, la, LC(KC_E3));
+        const double inner = 1.0 - lwfb_pow(1.0 - p3, 1.0 - E2);
+        const double kkv = LC(KC_KSAT) * lwfb_pow_from_log(a, la, LC(KC_TORT)) * (inner * inner);
+        const double psit = psim + LC(KC_PSIG);
+        if (at_cb && lane_valid) {
+          // total potential and conductivity of the layer: into the lane's exchange slot and its frozen-uptake slot (the
+          // uptake of the day that ends is dead; the callback writes the new one there)
+          cst[KC_XCH * LWFB_LANES_BLOCK] = psit;
+          cst[KC_TRANI * LWFB_LANES_BLOCK] = kkv;
         }
-        // the surplus lanes of the warp shadow layer 0 of its first member: they must see a finite uptake as well, or their
-        // (never committed) state turns NaN and drags the whole warp through the cold paths of exp / log at every call
-        if (g == 0) for (int l = mpw * N; l < 32; l++) (cst + l)[KC_TRANI * LWFB_LANES_BLOCK] = TRANI_a[0];
-        SETM(KM_SUMT, sT);
-        SETM(KM_SUMT_V, sT / LM(KM_VXYLEM));
-        SETM(KM_RS, nRNET + nSMLT); SETM(KM_SLVP, nSLVP);
-        {
-          // molecular diffusivities of the day (soil temperature = daily mean air temperature)
-          const double Tk = nTA + 273.15;
-          const double ee = lwfb_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
-          SETM(KM_D0_18O, 0.96691 * 1e-9 * ee * 3600 * 24);
-          SETM(KM_D0_2H, 0.98331 * 1e-9 * ee * 3600 * 24);
+        if (top && lane_valid) {
+          // the member's request, in its (transient) accumulator-rate slots: 0 none, 1 compute only, 2 compute and commit
+          SETM(KM_RATE0 + 0, at_cb ? (live ? 2.0 : 1.0) : 0.0);
+          SETM(KM_RATE0 + 1, t); SETM(KM_RATE0 + 2, (double)m); SETM(KM_RATE0 + 3, psim);
         }
-        if (cbst != LWFB_ST_OK) SETM(KM_STATUS, (double)cbst);
-        if (live) {
-          for (int j = 0; j < N; j++) FIN(ix.TRANI + j) = TRANIst_a[j];
-          FIN(ix.INTS) = nds.INTS; FIN(ix.INTR) = nds.INTR; FIN(ix.SNOW) = nds.SNOW; FIN(ix.CC) = nds.CC;
-          FIN(ix.SNOWLQ) = nds.SNOWLQ; FIN(ix.RWU) = nRWU;
-          for (int a2 = 0; a2 < LWFB_A_STORAGESWAT; a2++) FIN(ix.ACC + a2) = nds.acc[a2];
-          if (iso) {
-            double dp[2];
-            prec_delta(t, dp);
+      } else if (top && lane_valid) SETM(KM_RATE0 + 0, 0.0);
+      staged_wait();                                // forcing row `day` was requested at the previous callback (or at the start)
+      __syncthreads();
+      // (2) The scalar core of the callback (canopy, snow, interception, uptake by layer: ~2 10^4 operations per member that
+      // do not parallelise over layers) runs with ONE MEMBER PER LANE: thread k of the block takes member k of the block,
+      // so the 48 members of a DAV2020 block fill two warps instead of occupying six lanes in each of eight.  A callback
+      // phase is bound by instruction issue (every warp walks the whole core), so its cost falls with the number of warps
+      // that walk it: measured 94 us = 3.9 step passes per phase with one lane per member in every warp
+      // (profiles/r02_exp_callback_phase_cost.log).  Rounds 1 / 2 ran the core redundantly in every lane of a member.
+      {
+        const int tib = (int)(warp_g % LWFB_WARPS_PER_BLOCK) * 32 + lane;     // thread within the block = member it serves
+        double* const cst_blk = cst - tib;                                     // column 0 of the block
+        double* const msm2 = msm_block + tib;
+        const double req = tib < mpb ? *(const volatile double*)(msm2 + (KM_RATE0 + 0) * mpb) : 0.0;
+        if (req != 0.0) {
+          const double t2 = msm2[(KM_RATE0 + 1) * mpb];
+          const int64_t m2 = (int64_t)msm2[(KM_RATE0 + 2) * mpb];
+          const double psim0 = msm2[(KM_RATE0 + 3) * mpb];
+          const bool live2 = req == 2.0;
+          double* const col0 = cst_blk + (tib / mpw) * 32 + (tib % mpw) * N;  // column of the member's layer 0
+          const double* frow_m = msm_block + (size_t)KM_COUNT * mpb + (size_t)tib * 2 * LWFB_F;
+          const int day2 = (int)floor(t2 + 0.5);
+          const ParamView pv2{N, m2, M, d.scal, d.lay};
+          double* const fin2 = fin + m2 * L;
+          double psiti_a[NMAX], kk_a[NMAX], TRANI_a[NMAX], TRANIst_a[NMAX];
+          for (int j = 0; j < N; j++) { psiti_a[j] = col0[j + KC_XCH * LWFB_LANES_BLOCK]; kk_a[j] = col0[j + KC_TRANI * LWFB_LANES_BLOCK]; }
+          double nRNET, nSMLT, nSLVP, nTA, nRWU;
+          int cbst = LWFB_ST_OK;
+          DayState nds;
+          nds.INTS = fin2[ix.INTS]; nds.INTR = fin2[ix.INTR]; nds.SNOW = fin2[ix.SNOW]; nds.CC = fin2[ix.CC]; nds.SNOWLQ = fin2[ix.SNOWLQ];
+          cb_core<NMAX>(pv2, frow_m + (day2 & 1) * LWFB_F, t2, psim0, psiti_a, kk_a, nds, TRANI_a, nRNET, nSMLT, nSLVP, nTA,
+                        TRANIst_a, nRWU, cbst);
+          double sT = 0;                         // sum of the layer uptakes and its ratio to the xylem volume (isotope step)
+          for (int j = 0; j < N; j++) {
+            col0[j + KC_TRANI * LWFB_LANES_BLOCK] = TRANI_a[j];      // the frozen uptake of layer j, into that lane's column
+            sT += TRANI_a[j];
+          }
+          // the surplus lanes of a warp shadow layer 0 of its first member: they must see a finite uptake as well, or their
+          // (never committed) state turns NaN and drags the whole warp through the cold paths of exp / log at every call
+          if (tib % mpw == 0) for (int l = mpw * N; l < 32; l++) (cst_blk + (tib / mpw) * 32 + l)[KC_TRANI * LWFB_LANES_BLOCK] = TRANI_a[0];
+          msm2[KM_SUMT * mpb] = sT;
+          msm2[KM_SUMT_V * mpb] = sT / msm2[KM_VXYLEM * mpb];
+          msm2[KM_RS * mpb] = nRNET + nSMLT; msm2[KM_SLVP * mpb] = nSLVP;
+          {
+            // molecular diffusivities of the day (soil temperature = daily mean air temperature)
+            const double Tk = nTA + 273.15;
+            const double ee = lwfb_exp(-535400 / (Tk * Tk) + 1393.3 / Tk + 2.1876);
+            msm2[KM_D0_18O * mpb] = 0.96691 * 1e-9 * ee * 3600 * 24;
+            msm2[KM_D0_2H * mpb] = 0.98331 * 1e-9 * ee * 3600 * 24;
+          }
+          if (cbst != LWFB_ST_OK) msm2[KM_STATUS * mpb] = (double)cbst;
+          if (live2) {
+            for (int j = 0; j < N; j++) fin2[ix.TRANI + j] = TRANIst_a[j];
+            fin2[ix.INTS] = nds.INTS; fin2[ix.INTR] = nds.INTR; fin2[ix.SNOW] = nds.SNOW; fin2[ix.CC] = nds.CC;
+            fin2[ix.SNOWLQ] = nds.SNOWLQ; fin2[ix.RWU] = nRWU;
+            for (int a2 = 0; a2 < LWFB_A_STORAGESWAT; a2++) fin2[ix.ACC + a2] = nds.acc[a2];
+            if (iso) {
+              // delta of precipitation at t2 (the value of forcing row r holds for t in (r - 0.5, r + 0.5])
+              int r = (int)ceil(t2 - 0.5);
+              r = r < 0 ? 0 : (r > d.n_rows - 1 ? d.n_rows - 1 : r);
+              const double* row = frow_m + (r & 1) * LWFB_F;
+              const double dp[2] = {row[LWFB_F_D18O], row[LWFB_F_D2H]};
 #pragma unroll
-            for (int s = 0; s < 2; s++) { FIN(ix.INTS + 1 + s) = dp[s]; FIN(ix.INTR + 1 + s) = dp[s]; FIN(ix.SNOW + 1 + s) = dp[s]; }
+              for (int s = 0; s < 2; s++) { fin2[ix.INTS + 1 + s] = dp[s]; fin2[ix.INTR + 1 + s] = dp[s]; fin2[ix.SNOW + 1 + s] = dp[s]; }
+            }
           }
         }
       }
-      __syncwarp(LFULL);
+      __syncthreads();
+      // (3) the lanes of the members that had their callback start the new day
       if (at_cb) {
 #ifdef LWFB_CB_POLICY_WAIT
         SETM(KM_WAITED, 0.0);
@@ -706,57 +735,51 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       }
       // INFLOW
       const double INFRAC = LC(KC_INFRAC);
-      const double BYFLI0 = LEAN ? 0.0 : SLFL * INFRAC * BYFRAC;
-      const double INFLI0 = LEAN ? SLFL * INFRAC : SLFL * INFRAC * (1.0 - BYFRAC);
-      double BYFLI = BYFLI0;
-      INFLI = INFLI0;
+      double BYFLI = LEAN ? 0.0 : SLFL * INFRAC * BYFRAC;
+      INFLI = LEAN ? SLFL * INFRAC : SLFL * INFRAC * (1.0 - BYFRAC);
       VV = V0;
       {
-        // INFLOW's oversaturation limiter.  The reference walks the layers bottom-up: layer j, given its own (posterior)
-        // outflow, may cut the flux it receives from layer j-1, which changes what layer j-1 can take, and so on.  Here
-        // every layer takes its decision at once from its current outflow, the cut fluxes move up one lane, and the sweep
-        // repeats until nothing changes: the bottom outflow is fixed, so after k sweeps the k lowest layers are final,
-        // every final decision is the reference's expression of the reference's inputs (same bits), and the number of
-        // sweeps is the longest cascade + 1 instead of N.  No layer limits (DAV2020: always) -> no sweep at all; BEA2016
-        // keeps one layer saturated and limits in 79 % of the evaluations, with cascades of one layer in 98 % of them
-        // (block emulator): 2 sweeps instead of 7 chain steps.
         const double room = (SWATMAX - sw) / DTI;
+        // no layer limits (DAV2020: always) <=> every layer passes its test with the unmodified fluxes.  (Surplus lanes do
+        // not vote: their garbage entered the chain in 18 % of the BEA2016 evaluations.  BEA2016 keeps one layer saturated
+        // and limits in 79 % of the evaluations, a cascade of one layer in 98 % of them; sweeping all layers at once until
+        // nothing changes - 2 sweeps instead of N chain steps - was measured 5 % SLOWER there: a sweep costs every lane
+        // what a chain step costs one, profiles/r02_notes.md.)
         const double TRANI = LC(KC_TRANI), SLVP = LM(KM_SLVP);
         double MAXIN = room + V0 + DSFLI + TRANI;
         if (top) MAXIN = MAXIN + SLVP;
-        const bool limited = top ? (INFLI0 > MAXIN) : (V0_up + INFLI0 > MAXIN);
+        const bool limited = top ? (INFLI > MAXIN) : (V0_up + INFLI > MAXIN);
         if (__any_sync(LFULL, limited && lane_valid)) {
-          for (int sweep = 0; sweep < N; sweep++) {
+          // bottom-up chain: layer j fixes the posterior flux from layer j-1
+          for (int j = N - 1; j >= 0; j--) {
             double MX = room + VV + DSFLI + TRANI;
             double VVup = V0_up;
-            INFLI = INFLI0; BYFLI = BYFLI0;
-            if (top) {
+            if (j == 0) {
               MX = MX + SLVP;
-              if (INFLI0 > MX) {
-                const double too = INFLI0 - MX;
-                INFLI = INFLI0 - too;
-                BYFLI = BYFLI0 + too;
+              if (i == 0 && INFLI > MX) {
+                const double too = INFLI - MX;
+                INFLI = INFLI - too;
+                BYFLI = BYFLI + too;
               }
-            } else if (V0_up + INFLI0 > MX) {
-              if (BYFRAC > 0) {
-                if (V0_up < MX) {
-                  const double too = INFLI0 + V0_up - MX;
-                  INFLI = INFLI0 - too;
-                  BYFLI = BYFLI0 + too;
+            } else {
+              if (i == j && V0_up + INFLI > MX) {
+                if (BYFRAC > 0) {
+                  if (V0_up < MX) {
+                    const double too = INFLI + V0_up - MX;
+                    INFLI = INFLI - too;
+                    BYFLI = BYFLI + too;
+                  } else {
+                    VVup = MX;
+                    BYFLI = BYFLI + INFLI;
+                    INFLI = 0;
+                  }
                 } else {
-                  VVup = MX;
-                  BYFLI = BYFLI0 + INFLI0;
-                  INFLI = 0;
+                  VVup = MX - INFLI;
                 }
-              } else {
-                VVup = MX - INFLI0;
               }
             }
-            const double recv = __shfl_down_sync(LFULL, VVup, 1);   // every lane receives its posterior outflow from below
-            const double VVnew = bot ? V0 : recv;
-            const bool changed = lane_valid && (__double_as_longlong(VVnew) != __double_as_longlong(VV));
-            VV = VVnew;
-            if (!__any_sync(LFULL, changed)) break;
+            const double recv = __shfl_down_sync(LFULL, VVup, 1);   // lane j-1 receives its posterior outflow
+            if (j >= 1 && i == j - 1) VV = recv;
           }
         }
       }

@@ -9,6 +9,8 @@ Two comparisons:
     algorithm itself is reproducible, which is established per member by re-running the oracle with a
     1e-15 relative perturbation of KSAT (see DESIGN.md "Parity").
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -846,3 +848,54 @@ def test_multi_handle_shards_and_allgathers(dav_full, balanced):
         t = torch.as_tensor(DeviceArray(p, sc.shape), device=f"cuda:{devices[s]}")
         assert np.array_equal(t.cpu().numpy(), sc, equal_nan=True)
     mh.close()
+
+
+def test_c_host_drives_the_multi_gpu_abi(isobea, tmp_path):
+    """A C program (tests/c/multi_host.c, compiled with gcc against include/lwfb90.h; no Python, torch or NCCL in its
+    process) shards an ensemble over lwfb_multi_* with a cost-balanced deal, integrates, all-gathers the scores peer to
+    peer and returns everything in the caller's member order: bit-equal to a single handle driven from Python.  Uses two
+    shards (both GPUs if the box has two, else two shards on device 0)."""
+    import subprocess
+    import torch
+    ens = en.make_ensemble(isobea, 70)
+    nd = 40
+    N, L, M = ens.N, ens.u0.shape[1], ens.M
+    obs_day = np.array([0, 5, 17, 40], dtype=np.int32); obs_layer = np.array([0, 3, 6], dtype=np.int32)
+    rng = np.random.default_rng(21)
+    th = 0.25 + 0.05 * rng.random((4, 3)); d18 = -10 + rng.random((4, 3))
+    cost = rng.random(M)
+    src, out = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(src, "wb") as f:
+        def put(a, dt):
+            b = np.ascontiguousarray(a, dtype=dt).tobytes()
+            f.write(b + b"\0" * (-len(b) % 8))
+        put([N, int(ens.iso), ens.t0_day, nd, ens.forcing.shape[-2], len(obs_day), len(obs_layer), 0], np.int32)
+        put([M], np.int64)
+        put(ens.forcing.reshape(-1, ens.forcing.shape[-1]), np.float64); put(ens.site_of_member, np.int32)
+        put(ens.scal, np.float64); put(ens.lay, np.float64); put(ens.u0, np.float64); put(cost, np.float64)
+        put(obs_day, np.int32); put(obs_layer, np.int32); put(th, np.float64); put(d18, np.float64)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(capi.LIB_PATH)
+    exe = tmp_path / "multi_host"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-O1", "-o", str(exe), os.path.join(root, "tests", "c", "multi_host.c"),
+                           "-L", libdir, "-l:" + os.path.basename(capi.LIB_PATH), "-Wl,-rpath," + libdir])
+    devices = ["0", "1"] if torch.cuda.device_count() >= 2 else ["0", "0"]
+    r = subprocess.run([str(exe), str(src), str(out)] + devices, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    raw = open(out, "rb").read()
+    o = 0
+    def take(n, dt):
+        nonlocal o
+        a = np.frombuffer(raw, dtype=dt, count=n, offset=o); o += a.nbytes
+        return a
+    fin = take(M * L, np.float64).reshape(M, L); scores = take(M * 4, np.float64).reshape(M, 4)
+    counters = take(M * 3, np.int64).reshape(M, 3); status = take(M, np.int32); shard = take(M, np.int32)
+    assert sorted(np.bincount(shard, minlength=2)) == [35, 35]
+    h = capi.Handle(N, ens.iso, ens.t0_day, nd, record_daily=False)
+    h.set_sites(ens.forcing); h.set_members(ens.site_of_member, ens.scal, ens.lay, ens.u0)
+    h.set_observations(obs_day, obs_layer, th, d18)
+    h.run()
+    st, cnt = h.get_status()
+    assert np.array_equal(status, st) and np.array_equal(counters, cnt)
+    assert np.array_equal(fin, h.get_final(), equal_nan=True) and np.array_equal(scores, h.scores(), equal_nan=True)
+    h.close()
