@@ -30,8 +30,9 @@ for q in quanta:
     syncs = L.lwfb_emul_stage_syncs(); votes = L.lwfb_emul_votes()
     steps = (cnt[:, 0] + cnt[:, 1]).sum()
     # a step pass makes 4 block votes and 6 stage barriers (7 right after a callback: FSAL re-evaluation), a callback
-    # phase 3 votes; with one re-evaluation pass per callback phase: syncs = 6 P_step + P_cb, votes = 4 P_step + 3 P_cb
-    cb_passes = (votes - 2.0 * syncs / 3.0) / (7.0 / 3.0)
+    # phase 3 votes + 2 block barriers (counted with the votes); with one re-evaluation pass per callback phase:
+    # syncs = 6 P_step + P_cb, votes = 4 P_step + 5 P_cb
+    cb_passes = (votes - 2.0 * syncs / 3.0) / (13.0 / 3.0)
     passes = (syncs - cb_passes) / 6.0
     print(f"{wpb} warps per block, quantum {q:5d}: block passes x slots = {passes * mpb:.3e}, member steps = {steps:.3e}, "
           f"executed / needed = {passes * mpb / steps:.3f}, callback phases per block and day = "
