@@ -444,8 +444,18 @@ extern "C" int lwfb_emul_run(int kernel, int N, int iso, int t0_day, int n_days,
     if (left == 0) break;
     d.resume = 1;
     if (resort) {
-      std::stable_sort(perm2.begin(), perm2.begin() + left, [&](int32_t a, int32_t b) {
-        return ck[(size_t)a * ck_rows + lwfb::LWFB_CK_T] < ck[(size_t)b * ck_rows + lwfb::LWFB_CK_T]; });
+      // experiment knob LWFB_EMUL_KEY=1: (day, passes to the day boundary at the current step size, most first) instead of t
+      static const int key_mode = getenv("LWFB_EMUL_KEY") ? atoi(getenv("LWFB_EMUL_KEY")) : 0;
+      auto keyf = [&](int32_t a) {
+        const double* c = ck.data() + (size_t)a * ck_rows;
+        const double ta = c[lwfb::LWFB_CK_T];
+        if (key_mode == 0) return ta;
+        const double left_p = std::min(65535.0, std::max(0.0, (c[lwfb::LWFB_CK_TSTOP] - ta) / c[lwfb::LWFB_CK_DT]));
+        const int fl = (int)c[lwfb::LWFB_CK_FLAGS];
+        const double dayk = floor(ta) + ((fl & 2) ? -0.0 : 0.0);
+        return dayk * 65536.0 + (65535.0 - left_p);
+      };
+      std::stable_sort(perm2.begin(), perm2.begin() + left, [&](int32_t a, int32_t b) { return keyf(a) < keyf(b); });
       d.perm = perm2.data();
       d.n_slots = left;
     }
