@@ -70,6 +70,15 @@ static inline unsigned simt_reduce_min(unsigned mask, unsigned v, int op) {
   return r;
 }
 #define __reduce_min_sync(mask, v) simt_reduce_min((mask), (v), LWFB_OP_ID)
+static inline unsigned simt_reduce_max(unsigned mask, unsigned v, int op) {
+  unsigned r = 0u;
+  for (int l = 0; l < 32; l++) {
+    const unsigned vl = (unsigned)simt::exchange(v, l, op * 64 + l);
+    if ((mask >> l) & 1u) r = vl > r ? vl : r;
+  }
+  return r;
+}
+#define __reduce_max_sync(mask, v) simt_reduce_max((mask), (v), LWFB_OP_ID)
 static inline int __double2hiint(double x) { long long i; memcpy(&i, &x, 8); return (int)(i >> 32); }
 static inline int __double2loint(double x) { long long i; memcpy(&i, &x, 8); return (int)(i & 0xffffffffLL); }
 static inline double __hiloint2double(int hi, int lo) { long long i = ((long long)hi << 32) | (unsigned)lo; double x; memcpy(&x, &i, 8); return x; }
