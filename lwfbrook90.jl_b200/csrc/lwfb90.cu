@@ -508,7 +508,13 @@ static int launch_integrator(lwfb_handle* h, const DevData& d, cudaStream_t st, 
     const size_t per_block = smem + 1024, sm_total = 228 * 1024;
     const size_t want_res = latency ? 1 : LWFB_LANES_MINBLOCKS;
     const size_t n_res = per_block * want_res <= sm_total ? want_res : 1;
-    const int carve_pct = (int)((100 * per_block * n_res + sm_total - 1) / sm_total);
+    // the carve-out comes in steps (KB); ask for the smallest step that holds the resident blocks, as a percentage that
+    // rounds UP to exactly that step (a percentage computed from the bytes can land just above a step: 86 % of 228 KB is
+    // 196.08 KB, which selects 228 KB and leaves 28 KB of L1 instead of 60)
+    static const int carve_steps_kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+    int carve_kb = 228;
+    for (int k = 0; k < 10; k++) if ((size_t)carve_steps_kb[k] * 1024 >= per_block * n_res) { carve_kb = carve_steps_kb[k]; break; }
+    const int carve_pct = carve_kb * 100 / 228;
 #define LWFB_LAUNCH1(...)                                                                                       \
     do {                                                                                                       \
       if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_lanes<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \

@@ -147,6 +147,10 @@ enum {
   // the same value; read-modify-write sequences read into locals, __syncwarp, then write (no lane may see a value
   // another lane of its group has already advanced).  Counters are stored as doubles (exact).
   KM_TSTOP, KM_DT, KM_QOLD, KM_ITER, KM_NACCEPT, KM_NREJECT, KM_NF, KM_REC, KM_STATUS,
+  // GWAT of the member and its Runge-Kutta bookkeeping in the lean N = 7 kernel (no groundwater feedback: GWAT is a pure
+  // quadrature of the bottom flux and no stage needs it).  One lane per member - the top lane - accumulates in these
+  // slots; in registers the six values would be replicated in every lane, 12 registers of a kernel that spills at its cap.
+  KM_G, KM_KFG, KM_AEG, KM_SBG, KM_KCG,
 #ifdef LWFB_CB_POLICY_WAIT
   KM_WAITED,
 #endif
@@ -272,6 +276,12 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
     kFQ[j] = resume ? CKL(LWFB_CKL_KFQ + j) : 0.0;
   }
   double kFy = resume ? CKL(LWFB_CKL_KFY) : 0.0, kFG = resume ? CKP(LWFB_CK_KFG) : 0.0;   // FSAL derivative of SWATI / GWAT
+  // GWAT bookkeeping in shared slots (KM_G ...): measured on the same box, isoBEA2016 (N = 7) 13.93 -> 13.52 s, DAV2020
+  // (N = 5) 2576 -> 2596 ms (profiles/r02_exp_gwat_slots_ab.log) - the seven-layer kernel spills more and gains, the
+  // five-layer kernel pays for the extra shared-memory traffic: on for the N = 7 instantiation only
+  constexpr bool GWS = LEAN && NX == 7;
+  const bool gw_lane = top && lane_valid;            // GWS: the lane that keeps the member's GWAT bookkeeping in shared slots
+  if (GWS) { SETM(KM_G, G); SETM(KM_KFG, kFG); }     // (from here on such a kernel does not use the registers G, kFG)
   auto SETK = [&](int k, double v) { cst[k * LWFB_LANES_BLOCK] = v; };
   for (int s = 0; s < 2; s++) {
     SETK(KC_DS_18O + s, iso ? FIN(ix.SWATI + (s + 1) * N + i) : 0.0);
@@ -307,7 +317,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 #pragma unroll
     for (int j = 0; j < EQ; j++) if (qe[j] < 8) FIN(ix.ACC + lAccPos[qe[j] & 7]) = Q[j];
     if (top) {
-      FIN(ix.GWAT) = G;
+      FIN(ix.GWAT) = GWS ? LM(KM_G) : G;
       if (iso) { FIN(ix.GWAT + 1) = LM(KM_DG_18O); FIN(ix.GWAT + 2) = LM(KM_DG_2H); FIN(ix.XYLEM + 1) = LM(KM_DXY_18O); FIN(ix.XYLEM + 2) = LM(KM_DXY_2H); }
     }
   };
@@ -598,8 +608,12 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       // ---- stage input
       if (s == 1) {
         const double a = dt_s * 0.161;
-        xy = y + a * kFy; xG = G + a * kFG;
-        aEy = lBT[1] * kFy; aEG = lBT[1] * kFG; SbG = lB7[1] * kFG;
+        xy = y + a * kFy;
+        if (!GWS) xG = G + a * kFG;
+        aEy = lBT[1] * kFy;
+        if (GWS) {
+          if (gw_lane) { const double kfg = LM(KM_KFG); SETM(KM_AEG, lBT[1] * kfg); SETM(KM_SBG, lB7[1] * kfg); }
+        } else { aEG = lBT[1] * kFG; SbG = lB7[1] * kFG; }
 #pragma unroll
         for (int p = 0; p < 5; p++) qy[p] = lCQ[1][p] * kFy;
         if (gw_feedback) {
@@ -613,7 +627,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
 #pragma unroll
         for (int p = 0; p < 4; p++) qy[p] = qy[p + 1];
         qy[4] = 0;
-        if (s == 6) xG = G + dt_s * SbG;             // the new GWAT: uprev + dt * sum a7j kj (same summation order)
+        if (s == 6) { if (!GWS) xG = G + dt_s * SbG; }   // the new GWAT: uprev + dt * sum a7j kj (same summation order)
         else if (gw_feedback) {
           xG = G + dt_s * qG[0];
 #pragma unroll
@@ -621,7 +635,8 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
           qG[3] = 0;
         }
       } else {
-        xy = y; xG = G;
+        xy = y;
+        if (!GWS) xG = G;
       }
       const double ts = (s == 0) ? t : ((s < 5) ? t + lC[s] * dt_s : t + dt_s);
       const bool skip0 = (s == 0) && !reeval;     // groups that do not need the re-evaluation keep their k1
@@ -820,7 +835,8 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       if (s == 0) {
         // the re-evaluated k1 is committed at once: a member that needed it either steps now or has ended
         if (!skip0 && can_step) {
-          kFy = kny; kFG = knG;
+          kFy = kny;
+          if (GWS) { if (gw_lane) SETM(KM_KFG, knG); } else kFG = knG;
 #pragma unroll
           for (int j = 0; j < EQ; j++) kFQ[j] = knQ[j];
         }
@@ -834,8 +850,17 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         }
       } else {
         const int ks = s + 1;
-        aEy = aEy + lBT[ks] * kny; aEG = aEG + lBT[ks] * knG;
-        if (ks <= 6) SbG = SbG + lB7[ks] * knG;
+        aEy = aEy + lBT[ks] * kny;
+        if (GWS) {
+          if (gw_lane) {
+            SETM(KM_AEG, LM(KM_AEG) + lBT[ks] * knG);
+            if (ks <= 6) SETM(KM_SBG, LM(KM_SBG) + lB7[ks] * knG);
+            else SETM(KM_KCG, knG);                  // k7 = the FSAL derivative of the next step
+          }
+        } else {
+          aEG = aEG + lBT[ks] * knG;
+          if (ks <= 6) SbG = SbG + lB7[ks] * knG;
+        }
 #pragma unroll
         for (int p = 0; p < 5; p++)
           if (ks + 1 + p <= 7) qy[p] = qy[p] + lCQ[ks][p] * kny;
@@ -850,7 +875,8 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
           Sbt[j] = Sbt[j] + lBT[ks] * knQ[j];
           kcQ[j] = knQ[j];
         }
-        kcy = kny; kcG = knG;
+        kcy = kny;
+        if (!GWS) kcG = knG;
         if (s == 6) xy = sw;          // the new state u: SWCHEK clamped it in place
       }
     }
@@ -862,6 +888,11 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       const double abstol = d.abstol, reltol = d.reltol;
       double r = div_z(dt_s * aEy, abstol + jmax_abs(y, xy) * reltol);
       const double r2y = r * r;
+      if (GWS) {                                     // the top lane's sums, the old GWAT; the new one as stage 7 would have formed it
+        __syncwarp(LFULL);
+        G = LM(KM_G); aEG = LM(KM_AEG);
+        xG = G + dt_s * LM(KM_SBG);
+      }
       r = div_z(dt_s * aEG, abstol + jmax_abs(G, xG) * reltol);
       const double r2G = r * r;
 #pragma unroll
@@ -915,7 +946,8 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       if (acc_s) {
         SETM(KM_NACCEPT, nacc0 + 1.0);
         y = xy; G = xG;
-        kFy = kcy; kFG = kcG;                       // FSAL
+        kFy = kcy;                                  // FSAL
+        if (GWS) { if (gw_lane) { SETM(KM_G, xG); SETM(KM_KFG, LM(KM_KCG)); } } else kFG = kcG;
 #pragma unroll
         for (int j = 0; j < EQ; j++) { Q[j] = Qn[j]; kFQ[j] = kcQ[j]; }
         SETM(KM_QOLD, jmax(EEst, qoldinit));
@@ -1056,7 +1088,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
         CKP(LWFB_CK_NACCEPT) = LM(KM_NACCEPT); CKP(LWFB_CK_NREJECT) = LM(KM_NREJECT); CKP(LWFB_CK_NF) = LM(KM_NF);
         CKP(LWFB_CK_REC) = (double)rec; CKP(LWFB_CK_T) = t; CKP(LWFB_CK_TSTOP) = LM(KM_TSTOP);
         CKP(LWFB_CK_FLAGS) = (double)((reeval ? 1 : 0) | (at_boundary ? 2 : 0));
-        CKP(LWFB_CK_RS) = LM(KM_RS); CKP(LWFB_CK_SLVP) = LM(KM_SLVP); CKP(LWFB_CK_KFG) = kFG;
+        CKP(LWFB_CK_RS) = LM(KM_RS); CKP(LWFB_CK_SLVP) = LM(KM_SLVP); CKP(LWFB_CK_KFG) = GWS ? LM(KM_KFG) : kFG;
         CKP(LWFB_CK_SUMT) = LM(KM_SUMT); CKP(LWFB_CK_SUMT_V) = LM(KM_SUMT_V);
         CKP(LWFB_CK_D0_18O) = LM(KM_D0_18O); CKP(LWFB_CK_D0_2H) = LM(KM_D0_2H);
       }
