@@ -409,7 +409,7 @@ def main():
                                                  "; per step: integrate (scores accumulated at the observation days by the "
                                                  "integrator, " + ("daily record kept in HBM" if record else "no daily record")
                                                  + ") + score finalisation + score all-gather; every step cold (work quanta of "
-                                                 "128 block passes, members regrouped by progress between the launches)"),
+                                                 "64 block passes, members regrouped by progress between the launches)"),
                        "members_per_gpu": M, "members_total": total, "n_days": nd, "n_layers": N,
                        "l2": "member blocks (%.0f MB per GPU) exceed the 126 MB L2" % blocks_mb,
                        "members_ok": n_ok, "mean_accepted_steps_per_day": steps_acc,

@@ -320,7 +320,7 @@ int lwfb_debug_force_legacy(lwfb_handle* h, int32_t on);
 /* Placement of the members in the kernel's execution slots (no reference analogue; results do not depend on it).
  * The members that share a thread block advance in lock step and wait for each other at every step, so a block
  * is as slow as its member with the most steps.  mode 1 (default, "adaptive"): lwfb_run integrates in WORK QUANTA - a
- * launch ends after LWFB_QUANTUM (environment, default 128) passes of a block's loop, every member checkpoints where
+ * launch ends after LWFB_QUANTUM (environment, default 64) passes of a block's loop, every member checkpoints where
  * it is, the unfinished members are regrouped by progress (least first) and resumed; the front blocks of a launch keep
  * their slots for the whole launch (LWFB_PRIO_PCT % of the resident slots, default 15).  Nothing needs to be known
  * about the members in advance; if the handle has run before (same member count), the first launch is sorted by the

@@ -608,7 +608,11 @@ static int regroup_by_progress(lwfb_handle* h, cudaStream_t st, int64_t* n_left)
 extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
   if (!h || h->M < 1) return LWFB_ERR_ARG;
   CK(cudaSetDevice(h->o.device));
-  long long quantum = 128;
+  // passes of a block per launch while the device is full.  Round 1 settled on 128; since a callback phase costs a third
+  // of what it did (block-level callback), regrouping twice as often pays: 1,022,976 DAV2020 members 20.94 -> 19.90 s,
+  // 127872 members 2593 -> 2547 ms, isoBEA2016 unchanged; 48 is slower again (profiles/r02_exp_quantum.log).  A device that
+  // is not full keeps the longer quanta (BEA2016 10000: 4.37 s with 128, 4.44 s with 64 there).
+  long long quantum = 64;
   if (const char* e = getenv("LWFB_QUANTUM")) quantum = atoll(e);
   int prio_pct = 15;                                  // share of the resident slots given to the front blocks
   if (const char* e = getenv("LWFB_PRIO_PCT")) prio_pct = atoi(e);
@@ -667,7 +671,7 @@ extern "C" int lwfb_run(lwfb_handle* h, void* cuda_stream) {
     if (nb <= R) {
       // every block has a slot: longer quanta the emptier the device (regrouping only thins the blocks out)
       int64_t f = R / nb;
-      d.iter_budget = q * (f > 16 ? 16 : f);
+      d.iter_budget = (ramp ? q : 2 * q) * (f > 16 ? 16 : f);
       // ... and thinner blocks: the members are dealt to all resident slots, w warps per block instead of all eight,
       // so that a pass runs at the latency of few warps per SM (what is left at the end of a run is its critical path)
       const int64_t w = (n_left + R * mpw - 1) / (R * mpw);

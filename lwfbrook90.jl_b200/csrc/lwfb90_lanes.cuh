@@ -1027,7 +1027,11 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
       const double RDZ_up = LC(KC_RDZ_UP), RDZ_dn = LC(KC_RDZ_DN);
       const double rS1 = 1 / S1, VN_G = div_z(VN, G);
       // the two species share one copy of the code (rolled loop, state picked by select)
+#ifdef LWFB_ADE_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
       for (int s = 0; s < 2; s++) {
         const double R = s == 0 ? R18 : R2H;
         const double D0 = LM(KM_D0_18O + s);

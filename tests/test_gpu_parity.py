@@ -328,7 +328,7 @@ def test_tolerance_vs_libm_oracle_with_conditioning(dav_full, capsys):
     implementations agree to it only while they take the same sequence of accepted and rejected steps, and a one-ulp
     difference in one pow() can flip one such decision.  What the test establishes:
       * the fraction of members whose whole record stays within the north-star tolerance is reported and must be >= 0.8
-        (measured: 0.83 for these 64 members; member 0, the unmodified site definition, is among them);
+        (measured: 0.81 for these 64 members - 52 of 64; 0.83 with the round-1 exp - member 0, the unmodified site definition, is among them);
       * a member is CONDITIONED if the libm oracle itself stays within a tenth of the tolerance under six 1e-15 relative
         perturbations of its soil parameters; every conditioned member must be within tolerance;
       * every member outside the tolerance is one on which the oracle's own perturbed runs spread by a comparable amount
