@@ -220,8 +220,9 @@ def test_thread_per_member_kernel_agrees_with_lane_per_layer_kernel(dav_full, be
 
 
 @pytest.mark.parametrize("N", [3, 4, 6, 8, 9, 16, 22, 32])
-def test_lane_kernel_all_group_sizes(lw, N):
-    """Every lanes-per-member geometry (32/N members per warp, idle lanes, 1..3 extra components per lane)."""
+def test_lane_kernel_all_group_sizes(lw, N, monkeypatch):
+    """Every lanes-per-member geometry (32/N members per warp, idle lanes, 1..3 extra components per lane), through both
+    builds of the general instantiations (latency build: what a small ensemble runs in; throughput build forced)."""
     m = lw.loadSPAC(inputs("DAV2020-full"), "DAV2020-full", simulate_isotopes=True, Δz_thickness_m=aligned_grid(N),
                     root_distribution=dict(beta=0.97, z_rootMax_m=None),
                     IC_soil=dict(PSIM_init_kPa=-6.0, delta18O_init_permil=-12.0, delta2H_init_permil=-90.0))
@@ -229,7 +230,10 @@ def test_lane_kernel_all_group_sizes(lw, N):
     assert s.N == N
     e = en.make_ensemble(s, 11)
     h, sub, nd = gpu_run(e)
-    assert_bit_identical(h, sub, nd)
+    gpu = assert_bit_identical(h, sub, nd)
+    monkeypatch.setenv("LWFB_LATENCY_KERNEL", "0")
+    h.run()
+    assert np.array_equal(h.get_daily(), gpu, equal_nan=True)
     h.close()
 
 
