@@ -199,7 +199,7 @@ __device__ __forceinline__ bool lanes_body(const DevData& d, const int lane, con
   const bool live = lane_valid && m_raw < n_slots && placed >= 0;
   const int64_t m = placed >= 0 ? placed : 0;        // (lanes that are not live read some member's data and never write)
   const bool top = (i == 0), bot = (i == N - 1);
-  const bool nodn = bot || !lane_valid, noup = top || !lane_valid;   // lanes without a real neighbour below / above
+  const bool nodn = bot || !lane_valid;              // lanes without a real neighbour below
   const int L = d.L;
   const bool iso = d.iso != 0;
   const SIdx ix(N, d.iso);
