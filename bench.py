@@ -222,13 +222,15 @@ def main():
     ap.add_argument("--ref-members", type=int, default=2048, help="members per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--balance", type=int, default=0, help="N > 1, strong scaling: days of a probe run whose RHS counts deal the "
+                    "members to the ranks by cost (snake deal of the cost-sorted members) instead of contiguous shards; 0: off")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     from lwfbrook90.jl_b200 import capi, layout as lo
-    from lwfbrook90.jl_b200.parallel import DeviceArray, allgather_scores, shard_range
+    from lwfbrook90.jl_b200.parallel import DeviceArray, allgather_by_members, allgather_rows, allgather_scores, balanced_deal, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -251,6 +253,26 @@ def main():
     sim = load_site(args.config)
     kb = en.make_knob_block(sim, M, seed=1234, first_member=first)     # each GPU integrates its own slice of the ensemble:
     t_gen = time.perf_counter() - t_gen                                # Philox knob rows on the host, setup on the GPU
+    member_ids = None                                                  # (contiguous shard: first .. first + M - 1)
+    balance_note = None
+    if args.balance > 0 and world > 1 and not args.members:
+        # cost-balanced shards: a short probe run of the contiguous shard, its RHS counts all-gathered, the
+        # members sorted by cost and dealt to the ranks in a snake.  The knob generator is counter-based: every rank can
+        # produce any member, nothing has to move.  Outside the timed region (a calibration loop does it once).
+        t_bal = time.perf_counter()
+        hp = capi.Handle(kb.N, iso, kb.t0_day, min(args.balance, kb.n_days), device=local_rank, record_daily=False)
+        hp.set_sites(kb.forcing); hp.setup_members(kb); hp.run()
+        _, cnt_p = hp.get_status()
+        hp.close()
+        cost_blocks = allgather_rows(torch.from_numpy(cnt_p[:, 2:3].astype(np.float64)).to(f"cuda:{local_rank}"), rank, world)
+        cost = torch.cat(cost_blocks, dim=0)[:, 0].cpu().numpy()           # contiguous shards in rank order = global member order
+        deal = balanced_deal(cost, world)
+        member_ids = deal[rank]
+        M = len(member_ids)
+        kb = en.make_knob_block(sim, M, seed=1234, members=member_ids)
+        balance_note = {"probe_days": int(min(args.balance, kb.n_days)), "seconds": time.perf_counter() - t_bal,
+                        "cost_share_of_rank_max_over_mean": float(max(cost[d_].sum() for d_ in deal) / (cost.sum() / world)),
+                        "contiguous_would_be": float(max(cost[slice(*shard_range(total, r_, world))].sum() for r_ in range(world)) / (cost.sum() / world))}
     ens = en.make_ensemble(sim, min(M, 8192), seed=1234, first_member=first)   # host-built blocks of the CPU legs
     N, L, nd = kb.N, kb.base_u0.shape[0], kb.n_days
     obs_day, obs_layer, obs_th, obs_d18 = synthetic_observations(sim)
@@ -277,6 +299,8 @@ def main():
         if dist is None:
             return None
         t = torch.as_tensor(DeviceArray(ptr, (M, lo.NSCORES)), device=f"cuda:{local_rank}")
+        if member_ids is not None:
+            return allgather_by_members(t, member_ids, total, rank, world)
         return allgather_scores(t, total, rank, world)
 
     # our kernels launched per step: n integrator launches, one placement_keys kernel after each of them (regrouping),
@@ -299,7 +323,10 @@ def main():
         st, cnt = h.get_status()
         if dist is not None:
             t = torch.from_numpy(sc).to(f"cuda:{local_rank}")
-            allgather_scores(t, total, rank, world)
+            if member_ids is not None:
+                allgather_by_members(t, member_ids, total, rank, world)
+            else:
+                allgather_scores(t, total, rank, world)
         return sc, st, cnt
 
     for _ in range(args.warmup):
@@ -414,7 +441,8 @@ def main():
                        "l2": "member blocks (%.0f MB per GPU) exceed the 126 MB L2" % blocks_mb,
                        "members_ok": n_ok, "mean_accepted_steps_per_day": steps_acc,
                        "mean_attempted_steps_per_day": steps_att, "mean_rhs_evaluations_per_day": nf_day,
-                       "host_knob_generation_s": t_gen},
+                       "host_knob_generation_s": t_gen,
+                       **({"balanced_shards": balance_note} if balance_note else {})},
             "e2e": {"value": e2e_val, "unit": "site-days/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": n_launched,
             "clocks": clocks,

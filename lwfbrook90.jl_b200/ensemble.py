@@ -225,11 +225,12 @@ def batched_setup(base: DiscretizedSPAC, *, ths_f=None, ksat_f=None, alpha_f=Non
                     site_of_member=np.zeros(M, np.int32), scal=scal, lay=lay, u0=u0)
 
 
-def draw_knobs(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member: int = 0) -> dict:
+def draw_knobs(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member: int = 0, members=None) -> dict:
     """The perturbations of members first_member .. first_member+M-1 of the synthetic ensemble of SURVEY.md section
-    8(d) as keyword arguments of batched_setup (Philox4x32-10, key = seed, counter = global member index).  Global
-    member 0 is the unmodified site definition (neutral knobs; `keep` marks it)."""
-    idx = np.arange(first_member, first_member + M, dtype=np.uint64)
+    8(d) - or of the members listed in `members` (global ids, any order: the generator is counter-based) - as keyword
+    arguments of batched_setup (Philox4x32-10, key = seed, counter = global member index).  Global member 0 is the
+    unmodified site definition (neutral knobs; `keep` marks it)."""
+    idx = np.arange(first_member, first_member + M, dtype=np.uint64) if members is None else np.asarray(members, dtype=np.uint64)
     U = uniforms(idx, 20, seed)
     u = lambda j, a, b: a + (b - a) * U[:, j]
     logu = lambda j, a, b: np.exp(np.log(a) + (np.log(b) - np.log(a)) * U[:, j])
@@ -352,6 +353,6 @@ def knob_block(base: DiscretizedSPAC, *, ths_f=None, ksat_f=None, alpha_f=None, 
                      psim_base=np.asarray(df["uAux_PSIM_init_kPa"], float).copy(), ilayer=int(base.ILAYER))
 
 
-def make_knob_block(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member: int = 0) -> KnobBlock:
-    """The synthetic ensemble of make_ensemble as a knob block for the device-side setup."""
-    return knob_block(base, **draw_knobs(base, M, seed, first_member))
+def make_knob_block(base: DiscretizedSPAC, M: int, seed: int = 1234, first_member: int = 0, members=None) -> KnobBlock:
+    """The synthetic ensemble of make_ensemble as a knob block for the device-side setup (members: explicit global ids)."""
+    return knob_block(base, **draw_knobs(base, M, seed, first_member, members))
