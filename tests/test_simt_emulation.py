@@ -96,6 +96,11 @@ def test_lane_kernel_saturation_bypass_groundwater(lw):
     got, st, cnt_q = emul.run(emul.LANES, e.N, e.iso, e.t0_day, e.n_days, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
                               seg_len=11, resort=True)
     assert (st == 0).all() and np.array_equal(cnt_q, cnt) and np.array_equal(got, ref, equal_nan=True)
+    # the general instantiation in multi-warp blocks: the block-level callback phase serves members of other warps
+    # (thread k of the block = member k), the stage barriers and votes span the block
+    got, st, cnt_b = emul.run(emul.LANES, e.N, e.iso, e.t0_day, e.n_days, e.forcing, e.site_of_member, e.scal, e.lay, e.u0,
+                              warps_per_block=4)
+    assert (st == 0).all() and np.array_equal(cnt_b, cnt) and np.array_equal(got, ref, equal_nan=True)
 
 
 @pytest.mark.parametrize("N", [3, 4, 8, 16, 32])
