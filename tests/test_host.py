@@ -230,3 +230,16 @@ def test_setup_twin_matches_batched_setup(which, request):
     st = orc.setup_members(kb.N, kb.iso, kb.base_scal, kb.base_lay, kb.base_u0, kb.knobs, kb.over_idx, kb.profiles,
                            kb.psim_base, kb.ilayer)[3]
     assert st[5] == lo.ST.INPUT and (np.delete(st, 5) == 0).all()
+
+
+def test_knob_rows_of_arbitrary_members(dav_full):
+    """The synthetic ensemble is counter-based (Philox, counter = global member index): the knob rows of any list of members
+    equal the rows of a contiguous block - what lets every rank of a multi-GPU run produce the members a cost-balanced deal
+    gives it without moving data (bench.py --balance)."""
+    from lwfbrook90.jl_b200 import ensemble as en
+    block = en.make_knob_block(dav_full, 40)
+    ids = np.array([17, 3, 39, 0, 8])
+    picked = en.make_knob_block(dav_full, len(ids), members=ids)
+    assert np.array_equal(picked.knobs, block.knobs[ids], equal_nan=True)
+    shifted = en.make_knob_block(dav_full, 5, first_member=10)
+    assert np.array_equal(shifted.knobs, block.knobs[10:15], equal_nan=True)
